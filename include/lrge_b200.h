@@ -1,0 +1,157 @@
+/*
+ * lrge_b200.h -- C-ABI of the B200-native overlap hot path (liblrge_b200.so).
+ *
+ * Drop-in boundary for liblrge's hot path.  liblrge reaches minimap2 through
+ * per-read FFI calls (mm_set_opt, mm_idx_reader_open/read/close, mm_mapopt_update, mm_map:
+ * liblrge/src/minimap2/aligner.rs:53-303, thread_buf.rs:20-34).  A per-read call cannot feed a GPU, so
+ * the boundary moves up one level to what the strategies consume -- everything between "target.fa /
+ * query.fa written" and "Vec<f32> estimates returned":
+ *
+ *   lrge_gpu_twoset_counts   replaces AlignerWrapper::new + TwoSetStrategy::align_reads
+ *                            (twoset.rs:602-603 -> aligner.rs:311-328, twoset.rs:204-367)
+ *   lrge_gpu_twoset_counts (use_min_ref=1) ... align_reads_inverse (twoset.rs:596-599, 370-584)
+ *   lrge_gpu_ava_counts      replaces AlignerWrapper::new + AvaStrategy::align_reads
+ *                            (ava.rs:378-380 -> ava.rs:165-366)
+ *   lrge_per_read_estimate   estimate.rs:142-157          lrge_estimate   estimate.rs:55-132
+ *
+ * Plain pointers and sizes only; the caller owns every input and output buffer, the library owns
+ * device memory inside the context; nothing allocated on one side is freed on the other.  Every
+ * function returns an lrge_status (0 = ok) and never throws or aborts across the boundary; the message
+ * for the last failure on a context is available from lrge_gpu_last_error.  There is no CPU fallback:
+ * without a CUDA device lrge_gpu_create fails with LRGE_ERR_CUDA.
+ */
+#ifndef LRGE_B200_H
+#define LRGE_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mirrors LrgeError (liblrge/src/error.rs:6-33) + device-side failures */
+typedef enum lrge_status {
+    LRGE_OK = 0,
+    LRGE_ERR_IO = 1,                /* IoError */
+    LRGE_ERR_FASTQ_PARSE = 2,       /* FastqParseError */
+    LRGE_ERR_TOO_MANY_READS = 3,    /* TooManyReadsError */
+    LRGE_ERR_TOO_FEW_READS = 4,     /* TooFewReadsError */
+    LRGE_ERR_INVALID_PLATFORM = 5,  /* InvalidPlatform */
+    LRGE_ERR_THREAD = 6,            /* ThreadError */
+    LRGE_ERR_PAF_WRITE = 7,         /* PafWriteError */
+    LRGE_ERR_MAP = 8,               /* MapError, e.g. "Sequence is empty" (aligner.rs:214-216) */
+    LRGE_ERR_DUPLICATE_READ_ID = 9, /* DuplicateReadIdentifier (ava.rs:195-199, twoset.rs:439-449) */
+    LRGE_ERR_CUDA = 100,
+    LRGE_ERR_NCCL = 101,
+    LRGE_ERR_INVALID_ARG = 102,
+    LRGE_ERR_OUT_OF_MEMORY = 103,
+    LRGE_ERR_UNSUPPORTED = 104
+} lrge_status;
+
+/* Platform (liblrge/src/lib.rs:163-180): Nanopore -> ava-ont, PacBio -> ava-pb (twoset.rs:591-594) */
+typedef enum lrge_platform { LRGE_PLATFORM_NANOPORE = 0, LRGE_PLATFORM_PACBIO = 1 } lrge_platform;
+
+/* A read set = the temp FASTA liblrge hands to minimap2 (twoset.rs:157-186): read order is rid order;
+ * names are the header tokens up to the first whitespace (io.rs:192-205). */
+typedef struct lrge_readset {
+    const uint8_t  *bases;     /* concatenated ASCII bases (ACGTUN, either case; anything else is ambiguous) */
+    const uint64_t *off;       /* n+1 offsets into bases */
+    const char     *names;     /* concatenated names, no terminators */
+    const uint32_t *name_off;  /* n+1 offsets into names */
+    uint32_t n;
+} lrge_readset;
+
+/* Builder fields that reach the hot path (twoset/builder.rs:22-39, ava/builder.rs:18-32) */
+typedef struct lrge_opts {
+    int32_t platform;            /* lrge_platform; default Nanopore */
+    int32_t remove_internal;     /* -F: drop overlaps that PafRecord::is_internal (mapping.rs:59-77); default 0 */
+    float   max_overhang_ratio;  /* default 0.2 */
+    int32_t use_min_ref;         /* two-set: index the smaller set (twoset.rs:596-599); default 0 */
+    /* target sharding (one process per GPU): this context keeps anchors only for targets with
+     * rid % shard_count == shard_index; seed filtering still uses global occurrence counts. */
+    int32_t shard_index;         /* default 0 */
+    int32_t shard_count;         /* default 1 */
+    int32_t reserved[6];
+} lrge_opts;
+
+typedef struct lrge_stats {
+    uint64_t n_target_bases, n_query_bases;
+    uint64_t n_target_minimizers, n_query_minimizers, n_keys;
+    uint64_t n_seeds;            /* query minimizers that survive mm_seed_mz_flt and the mid_occ filter */
+    uint64_t n_hits;             /* hit-list entries read */
+    uint64_t n_anchors;          /* anchors kept after skip_seed (and sharding) */
+    uint64_t n_pairs;            /* (query, target) pairs holding anchors */
+    uint64_t n_overlaps;         /* pairs with at least one kept chain that passes the -F filter */
+    uint32_t no_mapping_count;   /* twoset.rs:303-309 / ava.rs:329-330 semantics */
+    int32_t  mid_occ;
+    uint32_t n_batches;
+    uint32_t n_kernel_launches;
+    /* device time per stage in ms (CUDA events on the context's stream) */
+    float ms_h2d, ms_pack, ms_sketch, ms_index, ms_seed, ms_sort, ms_chain, ms_d2h, ms_total;
+    float reserved[7];
+} lrge_stats;
+
+typedef struct lrge_ctx lrge_ctx;
+typedef struct lrge_staged lrge_staged;   /* a read set resident in HBM (ASCII + offsets), owned by the context */
+
+void lrge_opts_default(lrge_opts *opts);
+
+int  lrge_gpu_create(int device, lrge_ctx **out);
+void lrge_gpu_destroy(lrge_ctx *ctx);
+const char *lrge_gpu_last_error(const lrge_ctx *ctx);   /* ctx may be NULL: last error of lrge_gpu_create */
+
+/* Host buffers in, per-read overlap counts out (host<->device copies inside).
+ *   counts[Q->n]      number of distinct target reads overlapping each query (twoset.rs:286-302);
+ *                     with use_min_ref and more target than query bases the index is built on Q and T is
+ *                     streamed (twoset.rs:370-584) -- counts are still per query read
+ *   had_mapping[Q->n] 1 if mm_map returned any region for the read (twoset.rs:288); may be NULL */
+int  lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,
+                            uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats);
+/* counts[R->n]: unique overlapping partners per read (ava.rs:265-306) */
+int  lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts,
+                         uint32_t *counts, lrge_stats *stats);
+
+/* Same computation with the read sets already resident in HBM (what bench.py times as `value`). */
+int  lrge_gpu_stage(lrge_ctx *ctx, const lrge_readset *rs, lrge_staged **out);
+void lrge_gpu_unstage(lrge_ctx *ctx, lrge_staged *s);
+int  lrge_gpu_twoset_counts_staged(lrge_ctx *ctx, lrge_staged *T, lrge_staged *Q, const lrge_opts *opts,
+                                   uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats);
+int  lrge_gpu_ava_counts_staged(lrge_ctx *ctx, lrge_staged *R, const lrge_opts *opts,
+                                uint32_t *counts, lrge_stats *stats);
+
+/* Pinned host memory for the caller's read buffers (optional; pageable memory works, slower). */
+int  lrge_gpu_host_alloc(size_t bytes, void **out);
+void lrge_gpu_host_free(void *p);
+
+/* Stage dumps for parity tests (device -> host). mm128-style records, x/y as in minimap2:
+ *   minimizers of a read set in (rid, position) order: x = hash<<8|span, y = rid<<32|pos<<1|strand;
+ *   cnt[rs->n] = minimizers per read (may be NULL). *n_out receives the number written; cap = capacity. */
+int  lrge_gpu_dump_minimizers(lrge_ctx *ctx, const lrge_readset *rs, int32_t platform,
+                              uint64_t *x, uint64_t *y, uint64_t cap, uint64_t *n_out, uint32_t *cnt);
+/* mid_occ of an index built over T (mm_mapopt_update, aligner.rs:189) */
+int  lrge_gpu_dump_mid_occ(lrge_ctx *ctx, const lrge_readset *T, int32_t platform, int32_t *mid_occ, uint64_t *n_keys);
+
+/* host-side estimator arithmetic (f32, evaluation order of estimate.rs) */
+float lrge_per_read_estimate(uint64_t read_len, float avg_target_len, uint64_t n_target_reads,
+                             uint64_t n_ovlaps, uint32_t ovlap_thresh);
+/* Estimate::estimate: filter finite (if finite != 0), median and optional quantiles (q < 0 => None).
+ * Returns a bit mask of the outputs that are Some: 1 lower, 2 median, 4 upper; -1 on a bad quantile. */
+int   lrge_estimate(const float *estimates, uint64_t n, int finite, float lower_q, float upper_q,
+                    float *lower, float *median, float *upper);
+/* PafRecord::is_internal (mapping.rs:59-77) */
+int   lrge_is_internal(int32_t qlen, int32_t qs, int32_t qe, int32_t rev, int32_t tlen, int32_t ts, int32_t te, float ratio);
+
+/* Whole strategies on host buffers: counts via the GPU, then per_read_estimate for every read.
+ *   estimates[Q->n] / [R->n]; *no_mapping_count as the reference reports it.
+ * TwoSetStrategy::generate_estimates (twoset.rs:587-606) / AvaStrategy::generate_estimates (ava.rs:369-381)
+ * minus the random subsampling that precedes the hot path. */
+int  lrge_twoset_generate_estimates(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,
+                                    float *estimates, uint32_t *no_mapping_count, lrge_stats *stats);
+int  lrge_ava_generate_estimates(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts,
+                                 float *estimates, uint32_t *no_mapping_count, lrge_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

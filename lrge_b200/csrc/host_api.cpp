@@ -1,0 +1,111 @@
+// host_api.cpp -- host-side arithmetic of liblrge that follows the hot path (f32, evaluation order of the
+// reference): per_read_estimate (estimate.rs:142-157), median / calculate_quantile / Estimate::estimate
+// (estimate.rs:55-132), PafRecord::is_internal (mapping.rs:59-77), and the generate_estimates wrappers
+// (twoset.rs:587-606, ava.rs:369-381) over the GPU counts.
+#include "../../include/lrge_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+extern "C" {
+
+float lrge_per_read_estimate(uint64_t read_len, float avg_target_len, uint64_t n_target_reads, uint64_t n_ovlaps,
+                             uint32_t ovlap_thresh) {
+    if (n_ovlaps == 0) return std::numeric_limits<float>::infinity();
+    volatile float ovlap_ratio = (float)n_target_reads / (float)n_ovlaps;
+    volatile float a = (float)read_len + avg_target_len;
+    volatile float two_t = 2.0f * (float)ovlap_thresh;
+    volatile float b = a - two_t;
+    volatile float c = b + 1.0f;
+    volatile float d = ovlap_ratio * c;
+    volatile float e = (float)read_len + d;
+    return e;
+}
+
+static bool quantile(const std::vector<float> &data, float q, float *out) {
+    if (data.empty()) return false;
+    const size_t n = data.size();
+    volatile float pos = q * (float)(n - 1);
+    const size_t idx = (size_t)std::floor((float)pos);
+    volatile float frac = pos - (float)idx;
+    if (idx + 1 < n) {
+        volatile float w0 = 1.0f - frac;
+        volatile float t0 = data[idx] * w0;
+        volatile float t1 = data[idx + 1] * frac;
+        volatile float r = t0 + t1;
+        *out = r;
+    } else *out = data[idx];
+    return true;
+}
+
+int lrge_estimate(const float *estimates, uint64_t n, int finite, float lower_q, float upper_q, float *lower, float *median,
+                  float *upper) {
+    // calculate_quantile panics outside [0, 1] (estimate.rs:118-120)
+    if ((lower_q >= 0.0f && lower_q > 1.0f) || (upper_q >= 0.0f && upper_q > 1.0f)) return -1;
+    std::vector<float> v;
+    v.reserve(n);
+    for (uint64_t i = 0; i < n; ++i)
+        if (!finite || std::isfinite(estimates[i])) v.push_back(estimates[i]);
+    if (v.empty()) return 0;
+    std::sort(v.begin(), v.end());   // partial_cmp: no NaN expected (estimate.rs:92-93)
+    int mask = 0;
+    float tmp;
+    if (quantile(v, 0.5f, &tmp)) { if (median) *median = tmp; mask |= 2; }
+    if (lower_q >= 0.0f && quantile(v, lower_q, &tmp)) { if (lower) *lower = tmp; mask |= 1; }
+    if (upper_q >= 0.0f && quantile(v, upper_q, &tmp)) { if (upper) *upper = tmp; mask |= 4; }
+    return mask;
+}
+
+int lrge_is_internal(int32_t qlen, int32_t qs, int32_t qe, int32_t rev, int32_t tlen, int32_t ts, int32_t te, float ratio) {
+    int32_t overhang;
+    if (!rev) overhang = std::min(qs, ts) + std::min(qlen - qe, tlen - te);
+    else overhang = std::min(qs, tlen - te) + std::min(qlen - qe, ts);
+    const int32_t maplen = std::max(qe - qs, te - ts);
+    volatile float r = (float)overhang / (float)maplen;
+    return r < ratio;
+}
+
+int lrge_twoset_generate_estimates(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,
+                                   float *estimates, uint32_t *no_mapping_count, lrge_stats *stats) {
+    if (!T || !Q || !estimates || !opts) return LRGE_ERR_INVALID_ARG;
+    std::vector<uint32_t> counts(Q->n);
+    std::vector<uint8_t> had(Q->n);
+    lrge_stats st;
+    memset(&st, 0, sizeof st);
+    const int rc = lrge_gpu_twoset_counts(ctx, T, Q, opts, counts.data(), had.data(), &st);
+    if (rc != LRGE_OK) return rc;
+    // twoset.rs:191: avg_target_len = sum_target_len as f32 / target_num_reads as f32
+    const uint64_t sum_t = T->n ? T->off[T->n] - T->off[0] : 0;
+    const float avg_target_len = (float)sum_t / (float)T->n;
+    for (uint32_t q = 0; q < Q->n; ++q)   // twoset.rs:311-317; overlap threshold = min_chain_score (twoset.rs:213)
+        estimates[q] = lrge_per_read_estimate(Q->off[q + 1] - Q->off[q], avg_target_len, T->n, counts[q], 100);
+    if (no_mapping_count) *no_mapping_count = st.no_mapping_count;
+    if (stats) *stats = st;
+    return LRGE_OK;
+}
+
+int lrge_ava_generate_estimates(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts, float *estimates,
+                                uint32_t *no_mapping_count, lrge_stats *stats) {
+    if (!R || !estimates || !opts) return LRGE_ERR_INVALID_ARG;
+    std::vector<uint32_t> counts(R->n);
+    lrge_stats st;
+    memset(&st, 0, sizeof st);
+    const int rc = lrge_gpu_ava_counts(ctx, R, opts, counts.data(), &st);
+    if (rc != LRGE_OK) return rc;
+    // ava.rs:339-346: avg_read_len = sum_len / (n - 1), n_target_reads = n - 1 (sum_len includes the read itself)
+    const uint64_t sum_len = R->n ? R->off[R->n] - R->off[0] : 0;
+    const float avg_read_len = (float)sum_len / (float)(R->n - 1);
+    uint32_t nomap = 0;
+    for (uint32_t i = 0; i < R->n; ++i) {
+        if (counts[i] == 0) { ++nomap; estimates[i] = std::numeric_limits<float>::infinity(); }
+        else estimates[i] = lrge_per_read_estimate(R->off[i + 1] - R->off[i], avg_read_len, (uint64_t)R->n - 1, counts[i], 100);
+    }
+    if (no_mapping_count) *no_mapping_count = nomap;
+    if (stats) *stats = st;
+    return LRGE_OK;
+}
+
+}  // extern "C"

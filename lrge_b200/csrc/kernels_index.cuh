@@ -1,0 +1,105 @@
+// kernels_index.cuh -- K2/K3: target minimizer index in HBM.
+//
+// Replaces minimap2 mm_idx_add / worker_post / mm_idx_get / mm_idx_cal_max_occ (index.c) and
+// mm_mapopt_update (options.c), SURVEY.md rows a4/a5.  minimap2 buckets minimizers by the low 14 hash
+// bits, sorts each bucket and builds a hash table per bucket; what a lookup returns is the list of
+// y = rid<<32|pos<<1|strand of one key in ascending order.  Here all target minimizers are radix-sorted
+// by hash (stable, so y stays ascending inside a key) into one CSR-like array, and a direct-address
+// table over the TOP b hash bits gives the sub-range to search:
+//     tx[M], ty[M]   sorted by tx>>8;   boff[2^b + 1]:  bucket(key) = key >> (2k - b)
+// A lookup is one read of two adjacent boff entries plus a binary search over ~1-2 entries.
+#pragma once
+#include "common.cuh"
+
+namespace lrge {
+
+constexpr int OCC_BINS = 4096;   // occurrence histogram bins; the last bin collects everything >= OCC_BINS-1
+
+// boff[b] = first i with bucket(tx[i]) >= b, for b in [0, nb]; nb = 2^bits
+__global__ void bucket_bounds_kernel(const uint64_t *__restrict__ tx, uint64_t M, int shift, uint32_t nb,
+                                     uint32_t *__restrict__ boff) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > M) return;
+    const int64_t b_prev = i == 0 ? -1 : (int64_t)(tx[i - 1] >> shift);
+    const int64_t b_cur = i == M ? (int64_t)nb : (int64_t)(tx[i] >> shift);
+    for (int64_t b = b_prev + 1; b <= b_cur; ++b) boff[b] = (uint32_t)i;
+}
+
+// Per distinct key (run of equal tx>>8): histogram of the run length, number of keys.
+// hist[OCC_BINS] + n_keys are 64-bit device counters.
+__global__ void occ_hist_kernel(const uint64_t *__restrict__ tx, uint64_t M, unsigned long long *hist,
+                                unsigned long long *n_keys) {
+    __shared__ unsigned int sh[OCC_BINS];
+    for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    unsigned int my_keys = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = tx[i] >> 8;
+        if (i > 0 && (tx[i - 1] >> 8) == key) continue;      // not a run start
+        // run length by galloping then bisection
+        uint64_t lo = i, step = 1;                            // invariant: key(lo) == key
+        while (lo + step < M && (tx[lo + step] >> 8) == key) { lo += step; step <<= 1; }
+        uint64_t hi = lo + step < M ? lo + step : M;          // key(hi) != key or hi == M
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if ((tx[mid] >> 8) == key) lo = mid; else hi = mid;
+        }
+        const uint64_t n = hi - i;
+        atomicAdd(&sh[n < OCC_BINS - 1 ? n : OCC_BINS - 1], 1u);
+        ++my_keys;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+    // block-reduce the key count
+    for (int o = 16; o > 0; o >>= 1) my_keys += __shfl_down_sync(0xffffffffu, my_keys, o);
+    if ((threadIdx.x & 31) == 0 && my_keys) atomicAdd(n_keys, (unsigned long long)my_keys);
+}
+
+// Run lengths that fell into the overflow bin, collected for an exact order statistic on the host
+// (only reached when the mid_occ rank lands among keys occurring >= OCC_BINS-1 times).
+__global__ void occ_overflow_kernel(const uint64_t *__restrict__ tx, uint64_t M, uint32_t *out, unsigned long long *n_out,
+                                    uint64_t cap) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = tx[i] >> 8;
+        if (i > 0 && (tx[i - 1] >> 8) == key) continue;
+        if (i + OCC_BINS - 2 >= M || (tx[i + OCC_BINS - 2] >> 8) != key) continue;   // n < OCC_BINS-1
+        uint64_t lo = i + OCC_BINS - 2, step = 1;
+        while (lo + step < M && (tx[lo + step] >> 8) == key) { lo += step; step <<= 1; }
+        uint64_t hi = lo + step < M ? lo + step : M;
+        while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if ((tx[mid] >> 8) == key) lo = mid; else hi = mid;
+        }
+        const unsigned long long slot = atomicAdd(n_out, 1ull);
+        if (slot < cap) out[slot] = (uint32_t)(hi - i);
+    }
+}
+
+struct IndexView {
+    const uint64_t *tx;      // sorted by tx>>8
+    const uint64_t *ty;
+    const uint32_t *boff;
+    uint64_t M;
+    int shift;               // bucket = tx >> shift  (shift = 8 + 2k - bits)
+};
+
+// mm_idx_get, bounded: returns the start of the run of `key` and its length capped at cap+1
+// (callers only distinguish n <= mid_occ from n > mid_occ).  n = 0 if absent.
+__device__ __forceinline__ uint32_t index_lookup(const IndexView &I, uint64_t key, uint32_t cap, uint32_t *start) {
+    const uint64_t b = (key << 8) >> I.shift;
+    uint32_t lo = I.boff[b], hi = I.boff[b + 1];
+    // lower bound of key in [lo, hi)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((I.tx[mid] >> 8) < key) lo = mid + 1; else hi = mid;
+    }
+    *start = lo;
+    if (lo >= I.M || (I.tx[lo] >> 8) != key) return 0;
+    uint32_t n = 1;
+    const uint64_t lim = (uint64_t)lo + cap + 1 < I.M ? (uint64_t)lo + cap + 1 : I.M;
+    while ((uint64_t)lo + n < lim && (I.tx[lo + n] >> 8) == key) ++n;
+    return n;
+}
+
+}  // namespace lrge

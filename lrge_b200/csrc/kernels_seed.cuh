@@ -1,0 +1,123 @@
+// kernels_seed.cuh -- K4: query-side seed filter, index lookup and anchor emission.
+//
+// Replaces minimap2 mm_seed_mz_flt / mm_seed_collect_all / mm_collect_matches (seed.c) and
+// skip_seed / collect_seed_hits (map.c), SURVEY.md rows a7-a9, for ALL queries of a batch at once.
+// Anchors leave this stage as (64-bit sort key, 32-bit payload):
+//     key = ((qid_local << RB | rid) << 1 | rev) << PB | rpos        payload = q_span << 24 | qpos'
+// Sorting by key groups anchors per (query, target), forward strand before reverse, ascending target
+// position -- the order mg_lchain_dp needs inside one (target, strand) group.  Groups never interact
+// in minimap2's DP, so ordering targets before strands is free; it makes the two
+// strand groups of one (query, target) pair adjacent for the distinct-target count.
+#pragma once
+#include "common.cuh"
+#include "kernels_index.cuh"
+
+namespace lrge {
+
+constexpr int MZ_TABLE = 8192;
+
+// mm_seed_mz_flt: flag query minimizers whose x occurs > mid_occ times AND > q_occ_frac * n times in
+// the query.  A counting table over-estimates occurrences; candidates are then counted exactly.
+__global__ void __launch_bounds__(256) mz_flt_kernel(const uint64_t *__restrict__ qx, const uint32_t *__restrict__ moff,
+                                                     int mid_occ, float q_occ_frac, uint8_t *__restrict__ flt) {
+    __shared__ uint32_t tab[MZ_TABLE];
+    const uint32_t q = blockIdx.x;
+    const uint32_t b = moff[q], n = moff[q + 1] - b;
+    if ((int64_t)n <= (int64_t)mid_occ || q_occ_frac <= 0.0f || mid_occ <= 0) return;
+    for (int i = threadIdx.x; i < MZ_TABLE; i += blockDim.x) tab[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t x = qx[b + i];
+        atomicAdd(&tab[(uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> 51)], 1u);
+    }
+    __syncthreads();
+    const float thr = __fmul_rn((float)n, q_occ_frac);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t x = qx[b + i];
+        if (tab[(uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> 51)] <= (uint32_t)mid_occ) continue;
+        int32_t cnt = 0;
+        for (uint32_t j = 0; j < n; ++j) cnt += (qx[b + j] == x);
+        if (cnt > mid_occ && (float)cnt > thr) flt[b + i] = 1;
+    }
+}
+
+struct SkipCtx {
+    const uint32_t *rank_q, *rank_t;   // lexicographic name rank over the union of both sets
+    const uint32_t *len_q, *len_t;     // original read lengths
+    int check_names;                   // any (query, target) name comparison can matter
+    int no_dual;                       // MM_F_NO_DUAL: skip when qname > tname
+    uint32_t shard_index, shard_count;
+};
+
+// skip_seed (map.c) + target sharding
+__device__ __forceinline__ bool skip_hit(uint64_t r, uint32_t qid, uint32_t q_pos, const SkipCtx &S) {
+    const uint32_t rid = (uint32_t)(r >> 32);
+    if (S.shard_count > 1 && rid % S.shard_count != S.shard_index) return true;
+    if (S.check_names) {
+        const uint32_t rq = S.rank_q[qid], rt = S.rank_t[rid];
+        if (rq == rt && S.len_t[rid] == S.len_q[qid] && ((uint32_t)r >> 1) == (q_pos >> 1)) return true;   // diagonal
+        if (S.no_dual && rq > rt) return true;
+    }
+    return false;
+}
+
+// One thread per query minimizer: lookup, mid_occ filter, exact anchor count.
+__global__ void seed_count_kernel(const uint64_t *__restrict__ qx, const uint64_t *__restrict__ qy,
+                                  const uint8_t *__restrict__ flt, uint64_t MQ, IndexView I, int mid_occ, SkipCtx S,
+                                  uint32_t *__restrict__ hstart, uint32_t *__restrict__ hn, uint32_t *__restrict__ acnt,
+                                  unsigned long long *n_seeds, unsigned long long *n_hits) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t cnt = 0, n = 0, start = 0;
+    if (i < MQ && !flt[i]) {
+        const uint64_t x = qx[i];
+        n = index_lookup(I, x >> 8, (uint32_t)mid_occ, &start);
+        if (n > (uint32_t)mid_occ) n = 0;                     // m[i].flt = 1 (seed.c mm_collect_matches)
+        if (n) {
+            if (S.check_names || S.shard_count > 1) {
+                const uint64_t y = qy[i];
+                for (uint32_t j = 0; j < n; ++j) cnt += !skip_hit(I.ty[start + j], (uint32_t)(y >> 32), (uint32_t)y, S);
+            } else cnt = n;
+        }
+        hstart[i] = start;
+        hn[i] = n;                                            // hits to visit
+        acnt[i] = cnt;                                        // anchors kept
+    } else if (i < MQ) { hstart[i] = 0; hn[i] = 0; acnt[i] = 0; }
+    // stats
+    unsigned int seeds = n ? 1 : 0, hits = n;
+    for (int o = 16; o > 0; o >>= 1) { seeds += __shfl_down_sync(0xffffffffu, seeds, o); hits += __shfl_down_sync(0xffffffffu, hits, o); }
+    if ((threadIdx.x & 31) == 0 && hits) { atomicAdd(n_seeds, (unsigned long long)seeds); atomicAdd(n_hits, (unsigned long long)hits); }
+}
+
+struct KeyLayout { int PB, RB; };   // bits of target position / target id in the sort key
+
+// One thread per query minimizer of the batch [m0, m1): expands its hit list to anchors.
+// aoff = exclusive scan of anchor counts over ALL query minimizers (64-bit); a0 = aoff[m0].
+__global__ void anchor_fill_kernel(const uint64_t *__restrict__ qx, const uint64_t *__restrict__ qy,
+                                   const uint32_t *__restrict__ hstart, const uint32_t *__restrict__ hn,
+                                   const uint32_t *__restrict__ acnt, const uint64_t *__restrict__ aoff, uint64_t m0, uint64_t m1, uint64_t a0,
+                                   uint32_t q0, IndexView I, SkipCtx S, KeyLayout K,
+                                   uint64_t *__restrict__ akey, uint32_t *__restrict__ aval) {
+    const uint64_t i = m0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m1) return;
+    if (acnt[i] == 0) return;
+    const uint32_t n = hn[i];
+    const uint64_t x = qx[i], y = qy[i];
+    const uint32_t qid = (uint32_t)(y >> 32), q_pos = (uint32_t)y, q_span = (uint32_t)(x & 0xff);
+    const uint32_t qlen = S.len_q[qid];
+    const uint64_t qpart = (uint64_t)(qid - q0) << K.RB;
+    const bool scan = S.check_names || S.shard_count > 1;
+    uint64_t o = aoff[i] - a0;
+    const uint32_t start = hstart[i];
+    for (uint32_t j = 0; j < n; ++j) {
+        const uint64_t r = I.ty[start + j];
+        if (scan && skip_hit(r, qid, q_pos, S)) continue;
+        const uint32_t rpos = (uint32_t)r >> 1;
+        const uint32_t rev = ((uint32_t)r ^ q_pos) & 1;
+        const uint32_t qp = rev ? (qlen - ((q_pos >> 1) + 1 - q_span) - 1) : (q_pos >> 1);
+        akey[o] = (((qpart | (r >> 32)) << 1 | rev) << K.PB) | rpos;
+        aval[o] = q_span << 24 | qp;
+        ++o;
+    }
+}
+
+}  // namespace lrge

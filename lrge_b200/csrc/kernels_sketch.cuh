@@ -1,0 +1,297 @@
+// kernels_sketch.cuh -- K0 pack (ASCII -> 2-bit + ambiguity mask), K0h homopolymer compression,
+// K1 minimizer sketch.
+//
+// Replaces minimap2 mm_sketch (sketch.c) as called per target at index time and per query in
+// collect_minimizers.  mm_sketch is a sequential state machine; the emitted
+// set is nevertheless a pure function of a bounded history, which is what lets every position be
+// evaluated independently here:
+//   * info[t] (hash<<8|span, or MAX) depends on the k bases ending at step t and on l_t, the number of
+//     unambiguous steps since the last ambiguous base, saturated at w+k;
+//   * the running `min` of mm_sketch is always the RIGHTMOST minimum of the last w infos, so
+//     m[t-1] and m[t] follow from info[t-w..t];
+//   * the pushes done at step t (first-window ties, replaced minimum, minimum leaving the window,
+//     ties after a rescan, final flush) depend only on info[t-w..t], m[t-1], m[t] and l_t.
+// Steps are base positions, or homopolymer runs in HPC mode (ava-pb).  k must be odd (15 / 19): the
+// "symmetric k-mer" skip of mm_sketch cannot occur.
+#pragma once
+#include "common.cuh"
+
+namespace lrge {
+
+constexpr int PAD_BASES = 128;            // every read starts at a multiple of this in padded coordinates
+constexpr int TILE_POS = 8192;            // steps per CTA tile
+constexpr int SK_THREADS = 256;           // 8 warps x 1024 steps
+constexpr int WARP_POS = TILE_POS / (SK_THREADS / 32);
+constexpr int TILE_WORDS = (TILE_POS + PAD_BASES) / 32;   // 260 u64 of bases / u32 of mask
+constexpr int MAXW = 5;                   // minimizer window of both presets
+
+__constant__ uint8_t c_nt4[256];
+
+struct ReadLayout {
+    const uint8_t  *asc;       // ASCII bases (HPC: run-compressed ASCII)
+    const uint64_t *off;       // n+1 offsets into asc
+    const uint64_t *poff;      // n   padded start (bases), multiple of PAD_BASES, >= PAD_BASES
+    const uint32_t *len;       // n   number of steps (HPC: compressed length)
+    const uint32_t *tile_off;  // n+1 tiles before read r (tiles computed from the uncompressed length)
+    uint64_t *w2;              // 2-bit packed, 32 steps per u64, first step in the top bits
+    uint32_t *nm;              // ambiguity mask, 32 steps per u32, step i at bit i
+    uint32_t n;
+};
+
+__device__ __forceinline__ uint32_t find_read(const uint32_t *tile_off, uint32_t n, uint32_t tile) {
+    uint32_t lo = 0, hi = n;   // largest r with tile_off[r] <= tile
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (tile_off[mid] <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- K0: pack ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SK_THREADS) pack_kernel(ReadLayout L) {
+    __shared__ uint32_t s_r;
+    if (threadIdx.x == 0) s_r = find_read(L.tile_off, L.n, blockIdx.x);
+    __syncthreads();
+    const uint32_t r = s_r;
+    const uint32_t len = L.len[r];
+    const uint64_t s = (uint64_t)(blockIdx.x - L.tile_off[r]) * TILE_POS;
+    const uint64_t p0 = s + 32ull * threadIdx.x;
+    const uint64_t plen = ((uint64_t)len + PAD_BASES - 1) / PAD_BASES * PAD_BASES;
+    if (p0 >= plen) return;
+    uint64_t word = 0;
+    uint32_t mask = 0;
+    if (p0 < len) {
+        const uint8_t *src = L.asc + L.off[r] + p0;
+        const uint32_t *a4 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3) * 8;
+        uint32_t v[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) v[i] = __ldg(a4 + i);
+        const uint32_t nvalid = (uint32_t)min((uint64_t)32, (uint64_t)len - p0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t q = __funnelshift_r(v[i], v[i + 1], sh);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                uint32_t idx = i * 4 + b;
+                uint32_t c = c_nt4[(q >> (8 * b)) & 0xff];
+                if (idx >= nvalid) c = 4;
+                word |= (uint64_t)(c & 3) << (62 - 2 * idx);
+                mask |= (uint32_t)(c >> 2) << idx;
+            }
+        }
+    } else {
+        mask = 0xffffffffu;
+    }
+    const uint64_t wi = (L.poff[r] + p0) >> 5;
+    L.w2[wi] = word;
+    L.nm[wi] = mask;
+}
+
+// ---- K0h: homopolymer compression (ava-pb) -------------------------------------------------------
+// One warp per read.  Step = a run of equal unambiguous bases, or a single ambiguous base
+// (sketch.c: the HPC branch of mm_sketch). Emits the run base as ASCII, the position of the run's last
+// base, and the number of steps.
+__global__ void __launch_bounds__(256) hpc_compress_kernel(const uint8_t *asc, const uint64_t *off, uint32_t n,
+                                                           uint8_t *casc, uint32_t *cend, uint32_t *clen) {
+    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const uint32_t lane = lane_id();
+    const uint64_t o = off[r];
+    const uint32_t len = (uint32_t)(off[r + 1] - o);
+    const char kAsc[5] = {'A', 'C', 'G', 'T', 'N'};
+    uint32_t count = 0;
+    for (uint32_t c0 = 0; c0 < len; c0 += 32) {
+        const uint32_t i = c0 + lane;
+        uint32_t c = 255, cn = 254;
+        if (i < len) c = c_nt4[asc[o + i]];
+        if (i + 1 < len) cn = c_nt4[asc[o + i + 1]];
+        const bool is_end = (i < len) && (c >= 4 || cn != c);
+        const uint32_t b = __ballot_sync(0xffffffffu, is_end);
+        if (is_end) {
+            const uint32_t idx = count + __popc(b & ((1u << lane) - 1));
+            casc[o + idx] = (uint8_t)kAsc[c];
+            cend[o + idx] = i;
+        }
+        count += __popc(b);
+    }
+    if (lane == 0) clen[r] = count;
+}
+
+// ---- K1: sketch ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t hash64_masked(uint64_t key, uint64_t mask) {
+    key = (~key + (key << 21)) & mask;
+    key = key ^ key >> 24;
+    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = key ^ key >> 14;
+    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = key ^ key >> 28;
+    key = (key + (key << 31)) & mask;
+    return key;
+}
+
+template <int W>
+__device__ __forceinline__ uint64_t pick_x(const uint64_t (&xs)[W + 1], int d) {
+    uint64_t v = xs[0];
+#pragma unroll
+    for (int i = 1; i <= W; ++i) v = d == i ? xs[i] : v;
+    return v;
+}
+
+struct SketchArgs {
+    ReadLayout L;
+    const uint32_t *cend;     // HPC: original position of the last base of each step (indexed off[r] + t)
+    const uint32_t *woff;     // EMIT: exclusive scan of wcnt (one entry per warp sub-tile)
+    uint32_t *wcnt;           // COUNT: emissions per warp sub-tile
+    uint64_t *ox, *oy;        // EMIT: minimizers, (rid, position) order
+    int k;
+};
+
+template <bool HPC, bool EMIT>
+__global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
+    constexpr int W = MAXW;
+    __shared__ alignas(16) uint64_t sW[TILE_WORDS + 4];
+    __shared__ alignas(16) uint32_t sN[TILE_WORDS + 4];
+    __shared__ alignas(8) uint64_t bar;
+    __shared__ uint32_t s_r;
+
+    const ReadLayout &L = A.L;
+    const uint32_t tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        s_r = find_read(L.tile_off, L.n, tile);
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 4) { sW[TILE_WORDS + threadIdx.x] = 0; sN[TILE_WORDS + threadIdx.x] = 0; }
+    __syncthreads();
+    const uint32_t r = s_r;
+    const int64_t len = L.len[r];
+    const int64_t s = (int64_t)(tile - L.tile_off[r]) * TILE_POS;
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const int64_t ws = s + (int64_t)warp * WARP_POS;          // first step of this warp's sub-tile
+    if (s >= len) {                                            // HPC: tile lies past the compressed length
+        if (!EMIT && lane == 0) A.wcnt[tile * (SK_THREADS / 32) + warp] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const uint64_t g = (L.poff[r] + (uint64_t)s - PAD_BASES) >> 5;   // first word of the tile
+        mbar_expect_tx(&bar, TILE_WORDS * 12);
+        tma_load_1d(sW, L.w2 + g, TILE_WORDS * 8, &bar);
+        tma_load_1d(sN, L.nm + g, TILE_WORDS * 4, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    const int k = A.k;
+    const uint64_t kmask = (1ULL << (2 * k)) - 1;
+    const int LW = W + k;                                      // l is only compared with k, w+k-1, w+k
+    const uint32_t lw_mask = LW >= 32 ? 0xffffffffu : ((1u << LW) - 1);
+    const uint64_t rbase = L.off[r];
+
+    uint64_t xprev = U64MAX;
+    uint32_t zprev = 0;
+    uint32_t total = 0;
+    uint32_t obase = EMIT ? A.woff[tile * (SK_THREADS / 32) + warp] : 0;
+    const int n_chunks = WARP_POS / 32 + 1;                    // chunk 0 is warm-up (steps ws-32 .. ws-1)
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t p = ws + 32 * (c - 1) + lane;            // step handled by this lane
+        if (ws + 32 * (int64_t)(c - 1) >= len) break;          // warp-uniform
+        const int32_t q = (int32_t)(p - s) + PAD_BASES;        // index inside the staged tile (>= 96)
+        uint64_t x = U64MAX;
+        uint32_t z = 0;
+        int32_t l = 0;
+        if (p >= 0 && p < len) {
+            // l_t from the ambiguity mask: bit j of mr <-> step p-j
+            const int32_t st2 = q + 1 - 32;
+            const uint32_t wi2 = st2 >> 5, sh2 = st2 & 31;
+            const uint32_t m = __funnelshift_r(sN[wi2], sN[wi2 + 1], sh2);
+            const uint32_t mr = __brev(m) & lw_mask;
+            const int32_t lrun = mr ? (__ffs(mr) - 1) : LW;
+            l = (int32_t)min((int64_t)lrun, p + 1);
+            if (l >= k) {
+                const int32_t b0 = q - k + 1;
+                const uint32_t wi = b0 >> 5, sh = (b0 & 31) * 2;
+                const uint64_t hi = sW[wi], lo = sW[wi + 1];
+                const uint64_t v = sh ? (hi << sh) | (lo >> (64 - sh)) : hi;
+                const uint64_t fwd = v >> (64 - 2 * k);
+                uint64_t t = __brevll(~fwd);
+                t = ((t & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((t & 0x5555555555555555ULL) << 1);
+                const uint64_t rc = t >> (64 - 2 * k);
+                z = fwd < rc ? 0 : 1;
+                const uint64_t h = hash64_masked(z ? rc : fwd, kmask);
+                uint32_t span = k;
+                if (HPC) {
+                    const int64_t e1 = A.cend[rbase + p];
+                    const int64_t e0 = p - k >= 0 ? (int64_t)A.cend[rbase + p - k] : -1;
+                    span = (uint32_t)(e1 - e0);
+                }
+                if (span < 256) x = h << 8 | span;
+            }
+        }
+        // infos of steps t-d, d = 0..W, through warp shuffles (previous chunk supplies lanes < d)
+        uint64_t xs[W + 1];
+        xs[0] = x;
+#pragma unroll
+        for (int d = 1; d <= W; ++d) {
+            const int src = ((int)lane - d) & 31;
+            const uint64_t vc = __shfl_sync(0xffffffffu, x, src);
+            const uint64_t vp = __shfl_sync(0xffffffffu, xprev, src);
+            xs[d] = (int)lane - d >= 0 ? vc : vp;
+        }
+        const uint32_t zb = __ballot_sync(0xffffffffu, z);
+        const uint64_t zcomb = (uint64_t)zb << 32 | zprev;
+
+        uint64_t em = 0;       // emitted offsets d, 4 bits each, in push order
+        uint32_t cnt = 0;
+        if (c > 0 && p < len) {
+            // m[t-1]: rightmost minimum of steps t-W .. t-1;  m[t]: of steps t-W+1 .. t
+            uint64_t xm1 = xs[W]; int dm1 = W;
+#pragma unroll
+            for (int d = W - 1; d >= 1; --d) if (xs[d] <= xm1) { xm1 = xs[d]; dm1 = d; }
+            uint64_t xm = xs[W - 1]; int dm = W - 1;
+#pragma unroll
+            for (int d = W - 2; d >= 0; --d) if (xs[d] <= xm) { xm = xs[d]; dm = d; }
+            if (l == W + k - 1 && xm1 != U64MAX) {             // first full window: ties of the old minimum
+#pragma unroll
+                for (int d = W - 1; d >= 1; --d)
+                    if (xs[d] == xm1 && d != dm1) { em |= (uint64_t)d << (4 * cnt); ++cnt; }
+            }
+            if (x <= xm1) {                                    // new minimum replaces the old one
+                if (l >= W + k && xm1 != U64MAX) { em |= (uint64_t)dm1 << (4 * cnt); ++cnt; }
+            } else if (dm1 == W) {                             // old minimum left the window
+                if (l >= W + k - 1 && xm1 != U64MAX) { em |= (uint64_t)W << (4 * cnt); ++cnt; }
+                if (l >= W + k - 1 && xm != U64MAX) {
+#pragma unroll
+                    for (int d = W - 1; d >= 0; --d)
+                        if (xs[d] == xm && d != dm) { em |= (uint64_t)d << (4 * cnt); ++cnt; }
+                }
+            }
+            if (p == len - 1 && xm != U64MAX) { em |= (uint64_t)dm << (4 * cnt); ++cnt; }   // final flush
+        }
+        // ordered output: exclusive prefix of cnt over the warp
+        uint32_t pre = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, pre, o);
+            if ((int)lane >= o) pre += v;
+        }
+        const uint32_t chunk_total = __shfl_sync(0xffffffffu, pre, 31);
+        if (EMIT) {
+            uint32_t o = obase + total + pre - cnt;
+            for (uint32_t e = 0; e < cnt; ++e, ++o) {
+                const int d = (int)((em >> (4 * e)) & 15);
+                const int64_t pt = p - d;
+                const uint64_t zz = (zcomb >> (32 + (int)lane - d)) & 1;
+                const uint64_t pos = HPC ? (uint64_t)A.cend[rbase + pt] : (uint64_t)pt;
+                A.ox[o] = pick_x<W>(xs, d);
+                A.oy[o] = (uint64_t)r << 32 | pos << 1 | zz;
+            }
+        }
+        total += chunk_total;
+        xprev = x;
+        zprev = zb;
+    }
+    if (!EMIT && lane == 0) A.wcnt[tile * (SK_THREADS / 32) + warp] = total;
+}
+
+}  // namespace lrge

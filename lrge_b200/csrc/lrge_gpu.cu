@@ -1,0 +1,757 @@
+// lrge_gpu.cu -- context, device pipeline and C-ABI of liblrge_b200.so (include/lrge_b200.h).
+//
+// Pipeline (one CUDA stream per context; every kernel is hand-written except the radix sorts and
+// prefix sums, which are CUB device primitives):
+//   K0  pack_kernel            ASCII -> 2-bit + ambiguity mask          (+ K0h hpc_compress for ava-pb)
+//   K1  sketch_kernel<COUNT>   minimizers per warp sub-tile -> scan -> sketch_kernel<EMIT>
+//   K2  radix sort of target minimizers by hash, bucket_bounds_kernel   (index in HBM)
+//   K3  occ_hist_kernel        occurrence histogram -> mid_occ          (mm_mapopt_update)
+//   K4  mz_flt_kernel, seed_count_kernel -> scan -> anchor_fill_kernel  (per query batch)
+//   K5  radix sort of anchors by (query, target, strand, target pos), pair_flag_kernel + select
+//   K6  chain_pair_kernel      chaining DP + backtrack + overlap decision per (query, target) pair
+// There is no CPU fallback anywhere in this file: without a device every entry point fails.
+#include "../../include/lrge_b200.h"
+#include "common.cuh"
+#include "kernels_sketch.cuh"
+#include "kernels_index.cuh"
+#include "kernels_seed.cuh"
+#include "kernels_chain.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace lrge;
+
+// ------------------------------------------------------------------------------------------------
+// host-side option block: minimap2 defaults o preset o liblrge
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct MapOpt {
+    int k, w, is_hpc;
+    int bw, max_gap, max_chain_skip, max_chain_iter, min_cnt, min_chain_score;
+    float chain_gap_scale;
+    float mid_occ_frac, q_occ_frac;
+    int min_mid_occ, max_mid_occ;
+};
+
+MapOpt preset_for(int platform) {
+    MapOpt o{};
+    o.w = 5;
+    o.max_gap = 5000; o.max_chain_skip = 25; o.max_chain_iter = 5000; o.min_cnt = 3; o.min_chain_score = 100;
+    o.chain_gap_scale = 0.8f;
+    o.mid_occ_frac = 2e-4f; o.q_occ_frac = 0.01f; o.min_mid_occ = 10; o.max_mid_occ = 1000000;
+    if (platform == LRGE_PLATFORM_PACBIO) { o.k = 19; o.is_hpc = 1; o.bw = 500; }   // ava-pb
+    else { o.k = 15; o.is_hpc = 0; o.bw = 2000; }                                    // ava-ont
+    return o;
+}
+
+// mg_log2 (mmpriv.h) and the comput_sc gap penalty (lchain.c) in f32, one rounding per operation.
+inline float mg_log2_host(float x) {
+    union { float f; uint32_t i; } z;
+    z.f = x;
+    volatile float log_2 = (float)(int)(((z.i >> 23) & 255) - 128);
+    z.i &= ~(255U << 23);
+    z.i += 127U << 23;
+    volatile float a = -0.34484843f * z.f;
+    volatile float b = a + 2.02466578f;
+    volatile float c = b * z.f;
+    volatile float d = c - 0.67487759f;
+    volatile float e = log_2 + d;
+    return e;
+}
+void gap_penalty_table(int k, float chain_gap_scale, int n, std::vector<int32_t> &pen) {
+    const float chn_pen_gap = (float)(chain_gap_scale * 0.01 * k);   // float * double * int, then narrowed
+    pen.resize(n);
+    for (int dd = 0; dd < n; ++dd) {
+        volatile float lin = chn_pen_gap * (float)dd;
+        volatile float lg = dd >= 1 ? mg_log2_host((float)(dd + 1)) : 0.0f;
+        volatile float half = 0.5f * lg;
+        volatile float sum = lin + half;
+        pen[dd] = (int32_t)sum;
+    }
+}
+
+inline int bits_for(uint64_t v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }   // bits to hold v
+
+const uint8_t kNt4[256] = {
+    0, 1, 2, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+
+thread_local std::string g_create_error;
+
+struct Timer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// staged read set and context
+// ------------------------------------------------------------------------------------------------
+struct lrge_staged {
+    uint32_t n = 0;
+    uint64_t total_bases = 0;
+    uint32_t max_len = 0;
+    DevBuf asc, off;                       // device: ASCII (+64 slack), n+1 offsets
+    std::vector<uint64_t> h_off;           // host copies
+    std::vector<uint32_t> h_len;
+    std::string names;
+    std::vector<uint32_t> name_off;
+};
+
+struct Sketch {                            // minimizers of a read set, (rid, position) order
+    DevBuf x, y, moff;                     // moff: n+1 u32 per-read offsets
+    uint64_t M = 0;
+};
+
+struct lrge_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint32_t launches = 0;
+    // layout / sketch scratch
+    DevBuf poff, len, tile_off, w2, nm, wcnt, woff, casc, cend, clen;
+    DevBuf cub_tmp;
+    // index
+    Sketch sk_idx, sk_str;
+    DevBuf tx, ty, boff, hist;
+    // seed / anchors
+    DevBuf flt, hstart, hn, acnt, aoff, qaoff;
+    DevBuf akey0, akey1, aval0, aval1, flags, pstart, npairs, f, p, t, pair_res;
+    DevBuf rank_idx, rank_str, len_idx, len_str, pen, counts, had, counters;
+    std::vector<int32_t> pen_host; int pen_k = 0, pen_bw = 0;
+};
+
+namespace {
+
+void *cub_temp(lrge_ctx *c, size_t bytes) { c->cub_tmp.reserve(bytes ? bytes : 16); return c->cub_tmp.p; }
+
+template <typename T> void h2d(lrge_ctx *c, DevBuf &d, const T *src, size_t n) {
+    d.reserve(std::max<size_t>(n, 1) * sizeof(T));
+    if (n) CUDA_CHECK(cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+}
+
+void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s) {
+    s->n = rs->n;
+    s->h_off.assign(rs->off, rs->off + rs->n + 1);
+    s->total_bases = rs->n ? rs->off[rs->n] - rs->off[0] : 0;
+    if (rs->n && rs->off[0] != 0) {
+        const uint64_t b = rs->off[0];
+        for (auto &o : s->h_off) o -= b;
+    }
+    s->h_len.resize(rs->n);
+    s->max_len = 0;
+    for (uint32_t i = 0; i < rs->n; ++i) {
+        const uint64_t l = s->h_off[i + 1] - s->h_off[i];
+        if (l == 0) throw std::invalid_argument("MapError: Sequence is empty");          // aligner.rs:214-216
+        if (l >= (1u << 24)) throw std::length_error("reads of 16 Mbases or more are not supported");
+        s->h_len[i] = (uint32_t)l;
+        s->max_len = std::max(s->max_len, (uint32_t)l);
+    }
+    s->name_off.assign(rs->name_off, rs->name_off + rs->n + 1);
+    s->names.assign(rs->names + rs->name_off[0], rs->names + rs->name_off[rs->n]);
+    if (rs->n && rs->name_off[0] != 0) { const uint32_t b = rs->name_off[0]; for (auto &o : s->name_off) o -= b; }
+    s->asc.reserve(s->total_bases + 64);
+    if (s->total_bases)
+        CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + rs->off[0], s->total_bases, cudaMemcpyHostToDevice, c->stream));
+    h2d(c, s->off, s->h_off.data(), s->h_off.size());
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// K0 + K1: sketch a staged read set into `out`
+void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, float *ms_pack, float *ms_sketch) {
+    const uint32_t n = s->n;
+    std::vector<uint64_t> poff(n);
+    std::vector<uint32_t> tile_off(n + 1);
+    uint64_t pos = PAD_BASES;
+    uint32_t tiles = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        poff[i] = pos;
+        tile_off[i] = tiles;
+        pos += ((uint64_t)s->h_len[i] + PAD_BASES - 1) / PAD_BASES * PAD_BASES;
+        tiles += (s->h_len[i] + TILE_POS - 1) / TILE_POS;
+    }
+    tile_off[n] = tiles;
+    const uint64_t padded_words = (pos + TILE_POS + 2 * PAD_BASES) / 32 + 8;
+    Timer tm(c->stream);
+    tm.start();
+    h2d(c, c->poff, poff.data(), n);
+    h2d(c, c->tile_off, tile_off.data(), n + 1);
+    c->w2.reserve(padded_words * 8);
+    c->nm.reserve(padded_words * 4);
+    const uint32_t *len_dev;
+    ReadLayout L{};
+    L.off = s->off.as<uint64_t>();
+    L.poff = c->poff.as<uint64_t>();
+    L.tile_off = c->tile_off.as<uint32_t>();
+    L.w2 = c->w2.as<uint64_t>();
+    L.nm = c->nm.as<uint32_t>();
+    L.n = n;
+    if (o.is_hpc) {
+        c->casc.reserve(s->total_bases + 64);
+        c->cend.reserve((s->total_bases + 1) * 4);
+        c->clen.reserve((size_t)std::max(n, 1u) * 4);
+        if (n) {
+            hpc_compress_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(s->asc.as<uint8_t>(), s->off.as<uint64_t>(), n,
+                                                                    c->casc.as<uint8_t>(), c->cend.as<uint32_t>(),
+                                                                    c->clen.as<uint32_t>());
+            ++c->launches;
+        }
+        L.asc = c->casc.as<uint8_t>();
+        len_dev = c->clen.as<uint32_t>();
+    } else {
+        h2d(c, c->len, s->h_len.data(), n);
+        L.asc = s->asc.as<uint8_t>();
+        len_dev = c->len.as<uint32_t>();
+    }
+    L.len = len_dev;
+    if (tiles) { pack_kernel<<<tiles, SK_THREADS, 0, c->stream>>>(L); ++c->launches; }
+    CUDA_CHECK(cudaGetLastError());
+    if (ms_pack) *ms_pack += tm.stop();
+
+    tm.start();
+    const uint32_t nw = tiles * (SK_THREADS / 32);
+    c->wcnt.reserve(((size_t)nw + 1) * 4);
+    c->woff.reserve(((size_t)nw + 1) * 4);
+    SketchArgs A{};
+    A.L = L; A.cend = c->cend.as<uint32_t>(); A.wcnt = c->wcnt.as<uint32_t>(); A.woff = c->woff.as<uint32_t>(); A.k = o.k;
+    out->M = 0;
+    out->moff.reserve(((size_t)n + 1) * 4);
+    if (tiles) {
+        CUDA_CHECK(cudaMemsetAsync(c->wcnt.p, 0, ((size_t)nw + 1) * 4, c->stream));
+        if (o.is_hpc) sketch_kernel<true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        else sketch_kernel<false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        ++c->launches;
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream);
+        cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream);
+        ++c->launches;
+        uint32_t total = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&total, c->woff.as<uint32_t>() + nw, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        out->M = total;
+        out->x.reserve(((size_t)total + 1) * 8);
+        out->y.reserve(((size_t)total + 1) * 8);
+        A.ox = out->x.as<uint64_t>(); A.oy = out->y.as<uint64_t>();
+        if (o.is_hpc) sketch_kernel<true, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        else sketch_kernel<false, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        ++c->launches;
+        // per-read minimizer offsets: woff at the first warp sub-tile of every read
+        std::vector<uint32_t> woff_h((size_t)nw + 1);
+        CUDA_CHECK(cudaMemcpyAsync(woff_h.data(), c->woff.p, ((size_t)nw + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        std::vector<uint32_t> moff(n + 1);
+        for (uint32_t i = 0; i <= n; ++i) moff[i] = woff_h[(size_t)tile_off[i] * (SK_THREADS / 32)];
+        h2d(c, out->moff, moff.data(), n + 1);
+    } else {
+        uint32_t z = 0;
+        h2d(c, out->moff, &z, 1);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    if (ms_sketch) *ms_sketch += tm.stop();
+}
+
+struct BuiltIndex { IndexView view; int mid_occ; uint64_t n_keys; };
+
+// K2 + K3
+BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
+    BuiltIndex B{};
+    const uint64_t M = sk.M;
+    if (M >= (1ull << 32) - 2) throw std::length_error("more than 2^32 target minimizers per GPU are not supported");
+    c->tx.reserve((M + 1) * 8);
+    c->ty.reserve((M + 1) * 8);
+    if (M) {
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
+        cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
+        c->launches += 4;
+    }
+    int bits = 8;
+    while (bits < 2 * o.k && bits < 28 && (1ull << bits) < M) ++bits;
+    const uint32_t nb = 1u << bits;
+    const int shift = 8 + 2 * o.k - bits;
+    c->boff.reserve(((size_t)nb + 2) * 4);
+    bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>());
+    ++c->launches;
+    // occurrence histogram -> mid_occ (mm_idx_cal_max_occ + mm_mapopt_update)
+    c->hist.reserve((OCC_BINS + 2) * 8);
+    CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));
+    unsigned long long *hist = c->hist.as<unsigned long long>();
+    if (M) {
+        occ_hist_kernel<<<148 * 4, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, hist, hist + OCC_BINS);
+        ++c->launches;
+    }
+    std::vector<unsigned long long> h(OCC_BINS + 2);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), hist, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaGetLastError());
+    const uint64_t n_keys = h[OCC_BINS];
+    int mid_occ;
+    if (n_keys == 0) mid_occ = INT32_MAX;
+    else {
+        const uint64_t rank = (uint32_t)((1. - (double)o.mid_occ_frac) * (double)n_keys);   // (uint32_t)((1. - f) * n)
+        uint64_t cum = 0; int64_t val = -1;
+        for (int b = 0; b < OCC_BINS - 1; ++b) { cum += h[b]; if (cum > rank) { val = b; break; } }
+        if (val < 0) {   // rank lies among keys occurring >= OCC_BINS-1 times: exact order statistic of those
+            const uint64_t n_over = h[OCC_BINS - 1];
+            DevBuf over; over.reserve((n_over + 1) * 4);
+            CUDA_CHECK(cudaMemsetAsync(hist + OCC_BINS + 1, 0, 8, c->stream));
+            occ_overflow_kernel<<<148 * 4, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, over.as<uint32_t>(), hist + OCC_BINS + 1, n_over);
+            ++c->launches;
+            std::vector<uint32_t> ov(n_over);
+            CUDA_CHECK(cudaMemcpyAsync(ov.data(), over.p, n_over * 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            std::sort(ov.begin(), ov.end());
+            val = ov[rank - cum];
+        }
+        mid_occ = (int)val + 1;
+    }
+    if (mid_occ < o.min_mid_occ) mid_occ = o.min_mid_occ;
+    if (o.max_mid_occ > o.min_mid_occ && mid_occ > o.max_mid_occ) mid_occ = o.max_mid_occ;
+    B.view.tx = c->tx.as<uint64_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.M = M; B.view.shift = shift;
+    B.mid_occ = mid_occ; B.n_keys = n_keys;
+    return B;
+}
+
+// lexicographic name ranks over the union of two sets (equal names share a rank)
+struct NameRanks { std::vector<uint32_t> a, b; bool a_unique = true, b_unique = true, shared = false; };
+NameRanks rank_names(const lrge_staged *A, const lrge_staged *B) {
+    struct Ref { const char *s; uint32_t len, set, idx; };
+    std::vector<Ref> v;
+    v.reserve((size_t)A->n + (B ? B->n : 0));
+    for (uint32_t i = 0; i < A->n; ++i) v.push_back({A->names.data() + A->name_off[i], A->name_off[i + 1] - A->name_off[i], 0, i});
+    if (B) for (uint32_t i = 0; i < B->n; ++i) v.push_back({B->names.data() + B->name_off[i], B->name_off[i + 1] - B->name_off[i], 1, i});
+    auto cmp = [](const Ref &x, const Ref &y) {
+        const uint32_t m = std::min(x.len, y.len);
+        const int c = m ? memcmp(x.s, y.s, m) : 0;
+        return c ? c : (x.len < y.len ? -1 : x.len > y.len ? 1 : 0);
+    };
+    std::sort(v.begin(), v.end(), [&](const Ref &x, const Ref &y) { return cmp(x, y) < 0; });
+    NameRanks R;
+    R.a.resize(A->n);
+    if (B) R.b.resize(B->n);
+    uint32_t rank = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (i > 0 && cmp(v[i - 1], v[i]) != 0) ++rank;
+        else if (i > 0) {
+            if (v[i - 1].set == v[i].set) (v[i].set ? R.b_unique : R.a_unique) = false;
+            else R.shared = true;
+        }
+        (v[i].set ? R.b : R.a)[v[i].idx] = rank;
+    }
+    return R;
+}
+
+enum Mode { MODE_TWOSET = 0, MODE_AVA = 1, MODE_INVERSE = 2 };
+
+struct WidenU32 { __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; } };
+
+// The whole hot path: `idx` is the indexed read set, `str` the streamed one (the same object for AVA).
+// counts_out: MODE_TWOSET -> per streamed read; MODE_AVA -> per read; MODE_INVERSE -> per indexed read.
+void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, const lrge_opts &opts,
+                 uint32_t *counts_out, uint8_t *had_out, lrge_stats *st) {
+    const MapOpt o = preset_for(opts.platform);
+    const uint32_t n_counts = mode == MODE_TWOSET ? str->n : idx->n;
+    Timer total(c->stream), tm(c->stream);
+    total.start();
+    lrge_stats S{};
+    S.n_target_bases = idx->total_bases; S.n_query_bases = str->total_bases;
+    const uint32_t launches0 = c->launches;
+
+    // names -> ranks
+    NameRanks R = rank_names(idx, mode == MODE_AVA ? nullptr : str);
+    if (mode == MODE_AVA && !R.a_unique) throw std::domain_error("DuplicateReadIdentifier");
+    if (mode == MODE_INVERSE && !R.a_unique) throw std::domain_error("DuplicateReadIdentifier");
+    const std::vector<uint32_t> &rank_idx = R.a, &rank_str = mode == MODE_AVA ? R.a : R.b;
+
+    // K0/K1 on the indexed set, K2/K3
+    sketch_readset(c, idx, o, &c->sk_idx, &S.ms_pack, &S.ms_sketch);
+    tm.start();
+    BuiltIndex B = build_index(c, c->sk_idx, o);
+    S.ms_index = tm.stop();
+    S.n_target_minimizers = c->sk_idx.M; S.n_keys = B.n_keys; S.mid_occ = B.mid_occ;
+
+    // K1 on the streamed set
+    Sketch *sq = &c->sk_idx;
+    if (mode != MODE_AVA) { sketch_readset(c, str, o, &c->sk_str, &S.ms_pack, &S.ms_sketch); sq = &c->sk_str; }
+    const uint64_t MQ = sq->M;
+    S.n_query_minimizers = MQ;
+
+    tm.start();
+    h2d(c, c->rank_idx, rank_idx.data(), idx->n);
+    h2d(c, c->rank_str, rank_str.data(), str->n);
+    h2d(c, c->len_idx, idx->h_len.data(), idx->n);
+    h2d(c, c->len_str, str->h_len.data(), str->n);
+    if (c->pen_k != o.k || c->pen_bw != o.bw) { gap_penalty_table(o.k, o.chain_gap_scale, o.bw + 1, c->pen_host); c->pen_k = o.k; c->pen_bw = o.bw; }
+    h2d(c, c->pen, c->pen_host.data(), c->pen_host.size());
+
+    SkipCtx K{};
+    K.rank_q = c->rank_str.as<uint32_t>(); K.rank_t = c->rank_idx.as<uint32_t>();
+    K.len_q = c->len_str.as<uint32_t>(); K.len_t = c->len_idx.as<uint32_t>();
+    K.no_dual = mode == MODE_AVA;                                      // aligner.rs:93-103, ava.rs:378
+    K.check_names = mode == MODE_AVA || R.shared;                      // NO_DIAG only matters for equal names
+    K.shard_index = (uint32_t)opts.shard_index; K.shard_count = (uint32_t)std::max(opts.shard_count, 1);
+
+    c->counts.reserve(((size_t)n_counts + 1) * 4);
+    c->had.reserve((size_t)str->n + 1);
+    c->counters.reserve(64);
+    CUDA_CHECK(cudaMemsetAsync(c->counts.p, 0, ((size_t)n_counts + 1) * 4, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->had.p, 0, (size_t)str->n + 1, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+    unsigned long long *ctr = c->counters.as<unsigned long long>();   // [0] seeds [1] hits
+
+    // K4 part 1: filter + lookup + count
+    c->flt.reserve(MQ + 1);
+    c->hstart.reserve((MQ + 1) * 4); c->hn.reserve((MQ + 1) * 4); c->acnt.reserve((MQ + 1) * 4);
+    c->aoff.reserve((MQ + 2) * 8);
+    c->qaoff.reserve(((size_t)str->n + 2) * 8);
+    CUDA_CHECK(cudaMemsetAsync(c->flt.p, 0, MQ + 1, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->acnt.p, 0, (MQ + 1) * 4, c->stream));
+    std::vector<uint64_t> qa((size_t)str->n + 1, 0);
+    std::vector<uint32_t> moff_h((size_t)str->n + 1, 0);
+    if (MQ) {
+        mz_flt_kernel<<<str->n, 256, 0, c->stream>>>(sq->x.as<uint64_t>(), sq->moff.as<uint32_t>(), B.mid_occ, o.q_occ_frac, c->flt.as<uint8_t>());
+        seed_count_kernel<<<(unsigned)((MQ + 255) / 256), 256, 0, c->stream>>>(
+            sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->flt.as<uint8_t>(), MQ, B.view, B.mid_occ, K,
+            c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(), ctr, ctr + 1);
+        c->launches += 2;
+        size_t tb = 0;
+        cub::TransformInputIterator<uint64_t, WidenU32, const uint32_t *> in(c->acnt.as<uint32_t>(), WidenU32());
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream);
+        cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream);
+        ++c->launches;
+        // anchors before each query: aoff[moff[q]]
+        CUDA_CHECK(cudaMemcpyAsync(moff_h.data(), sq->moff.p, ((size_t)str->n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        std::vector<uint64_t> aoff_h(MQ + 1);
+        CUDA_CHECK(cudaMemcpyAsync(aoff_h.data(), c->aoff.p, (MQ + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (uint32_t q = 0; q <= str->n; ++q) qa[q] = aoff_h[moff_h[q]];
+    }
+    CUDA_CHECK(cudaGetLastError());
+    S.ms_seed = tm.stop();
+    const uint64_t A_total = qa[str->n];
+    S.n_anchors = A_total;
+
+    // batches of queries bounded by anchor memory
+    size_t free_b = 0, total_b = 0;
+    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    size_t reusable = c->akey0.cap + c->akey1.cap + c->aval0.cap + c->aval1.cap + c->flags.cap + c->pstart.cap +
+                      c->f.cap + c->p.cap + c->t.cap + c->pair_res.cap;
+    uint64_t a_max = (uint64_t)((free_b + reusable) * 0.7 / 48.0);
+    a_max = std::min<uint64_t>(a_max, (1ull << 31) - 1024);
+    const int PB = bits_for(idx->max_len ? idx->max_len - 1 : 0), RB = bits_for(idx->n ? idx->n - 1 : 0);
+
+    ChainParams P{};
+    P.max_dist_x = std::max(o.max_gap, o.bw); P.max_dist_y = std::max(o.max_gap, o.bw);
+    P.bw = o.bw; P.max_skip = o.max_chain_skip; P.max_iter = o.max_chain_iter; P.min_cnt = o.min_cnt; P.min_sc = o.min_chain_score;
+    P.pen = c->pen.as<int32_t>();
+
+    const bool host_dedupe = mode == MODE_TWOSET && !R.a_unique;      // duplicate target names: HashSet<name> semantics
+    std::vector<std::vector<uint32_t>> dedupe_sets;
+    if (host_dedupe) dedupe_sets.resize(str->n);
+
+    uint32_t q0 = 0;
+    while (q0 < str->n) {
+        uint32_t q1 = q0 + 1;
+        while (q1 < str->n && qa[q1 + 1] - qa[q0] <= a_max) ++q1;
+        const uint64_t nA = qa[q1] - qa[q0];
+        if (nA > a_max) throw std::length_error("a single read yields more anchors than fit in device memory");
+        const int QB = bits_for(q1 - q0 - 1);
+        if (QB + RB + 1 + PB > 64) throw std::length_error("sort key does not fit 64 bits (too many reads x read length)");
+        if (nA) {
+            ++S.n_batches;
+            tm.start();
+            c->akey0.reserve(nA * 8); c->akey1.reserve(nA * 8); c->aval0.reserve(nA * 4); c->aval1.reserve(nA * 4);
+            const uint64_t m0 = moff_h[q0], m1 = moff_h[q1];
+            KeyLayout KL{PB, RB};
+            anchor_fill_kernel<<<(unsigned)((m1 - m0 + 255) / 256), 256, 0, c->stream>>>(
+                sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
+                c->aoff.as<uint64_t>(), m0, m1, qa[q0], q0, B.view, K, KL, c->akey0.as<uint64_t>(), c->aval0.as<uint32_t>());
+            ++c->launches;
+            S.ms_seed += tm.stop();
+
+            tm.start();
+            size_t tb = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
+                                            c->aval1.as<uint32_t>(), (int64_t)nA, 0, QB + RB + 1 + PB, c->stream);
+            cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
+                                            c->aval1.as<uint32_t>(), (int64_t)nA, 0, QB + RB + 1 + PB, c->stream);
+            c->launches += 1 + (QB + RB + 1 + PB + 7) / 8;
+            // pair boundaries
+            c->flags.reserve(nA + 1);
+            c->pstart.reserve((nA + 2) * 4);
+            c->npairs.reserve(16);
+            pair_flag_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), nA, PB + 1, c->flags.as<uint8_t>());
+            cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
+                                       c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+            cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                       c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+            c->launches += 2;
+            uint32_t n_pairs = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&n_pairs, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            const uint32_t sentinel = (uint32_t)nA;
+            CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_pairs, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
+            S.ms_sort += tm.stop();
+            S.n_pairs += n_pairs;
+
+            tm.start();
+            c->f.reserve(nA * 4); c->p.reserve(nA * 4); c->t.reserve(nA * 4);
+            c->pair_res.reserve((size_t)n_pairs + 1);
+            CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
+            PairTask T{};
+            T.akey = c->akey1.as<uint64_t>(); T.aval = c->aval1.as<uint32_t>(); T.pstart = c->pstart.as<uint32_t>();
+            T.n_pairs = n_pairs; T.PB = PB; T.RB = RB; T.q0 = q0;
+            T.f = c->f.as<int32_t>(); T.p = c->p.as<int32_t>(); T.t = c->t.as<int32_t>();
+            CountOut O{};
+            O.counts = c->counts.as<uint32_t>(); O.had_mapping = c->had.as<uint8_t>(); O.pair_res = c->pair_res.as<uint8_t>();
+            O.len_q = K.len_q; O.len_t = K.len_t; O.rank_q = K.rank_q; O.rank_t = K.rank_t;
+            O.mode = mode; O.remove_internal = opts.remove_internal; O.ratio = opts.max_overhang_ratio;
+            O.names_unique = !host_dedupe;
+            chain_pair_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(T, P, O);
+            ++c->launches;
+            CUDA_CHECK(cudaGetLastError());
+            if (host_dedupe) {
+                std::vector<uint8_t> res(n_pairs);
+                std::vector<uint32_t> ps((size_t)n_pairs + 1);
+                std::vector<uint64_t> keys(nA);
+                CUDA_CHECK(cudaMemcpyAsync(res.data(), c->pair_res.p, n_pairs, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaMemcpyAsync(ps.data(), c->pstart.p, ((size_t)n_pairs + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaMemcpyAsync(keys.data(), c->akey1.p, nA * 8, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                for (uint32_t i = 0; i < n_pairs; ++i) if (res[i] & 2) {
+                    const uint64_t kk = keys[ps[i]];
+                    const uint32_t rid = (uint32_t)((kk >> (PB + 1)) & ((1ull << RB) - 1)), qid = q0 + (uint32_t)(kk >> (PB + 1 + RB));
+                    dedupe_sets[qid].push_back(rank_idx[rid]);
+                }
+            }
+            S.ms_chain += tm.stop();
+        }
+        q0 = q1;
+    }
+
+    // results
+    tm.start();
+    std::vector<uint32_t> counts(n_counts);
+    std::vector<uint8_t> had(str->n);
+    unsigned long long ctr_h[2] = {0, 0};
+    if (n_counts) CUDA_CHECK(cudaMemcpyAsync(counts.data(), c->counts.p, (size_t)n_counts * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (str->n) CUDA_CHECK(cudaMemcpyAsync(had.data(), c->had.p, str->n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctr_h, ctr, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    S.ms_d2h = tm.stop();
+    if (host_dedupe)
+        for (uint32_t q = 0; q < str->n; ++q) {
+            auto &v = dedupe_sets[q];
+            std::sort(v.begin(), v.end());
+            counts[q] = (uint32_t)(std::unique(v.begin(), v.end()) - v.begin());
+        }
+    S.n_seeds = ctr_h[0]; S.n_hits = ctr_h[1];
+    uint64_t sum = 0;
+    for (uint32_t i = 0; i < n_counts; ++i) sum += counts[i];
+    S.n_overlaps = mode == MODE_AVA ? sum / 2 : sum;
+    S.no_mapping_count = 0;
+    if (mode == MODE_TWOSET) { for (uint32_t q = 0; q < str->n; ++q) S.no_mapping_count += !had[q]; }
+    else for (uint32_t i = 0; i < n_counts; ++i) S.no_mapping_count += counts[i] == 0;
+    if (counts_out && n_counts) memcpy(counts_out, counts.data(), (size_t)n_counts * 4);
+    if (had_out && mode == MODE_TWOSET && str->n) memcpy(had_out, had.data(), str->n);
+    S.n_kernel_launches = c->launches - launches0;
+    S.ms_total = total.stop();
+    if (st) { const float h2d_ms = st->ms_h2d; *st = S; st->ms_h2d = h2d_ms; }
+}
+
+template <typename Fn> int guarded(lrge_ctx *ctx, Fn fn) {
+    if (!ctx) return LRGE_ERR_INVALID_ARG;
+    try {
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+        fn();
+        return LRGE_OK;
+    } catch (const CudaError &e) { ctx->err = e.what(); cudaGetLastError(); return LRGE_ERR_CUDA; }
+    catch (const std::domain_error &e) { ctx->err = e.what(); return LRGE_ERR_DUPLICATE_READ_ID; }
+    catch (const std::invalid_argument &e) { ctx->err = e.what(); return LRGE_ERR_MAP; }
+    catch (const std::length_error &e) { ctx->err = e.what(); return LRGE_ERR_UNSUPPORTED; }
+    catch (const std::bad_alloc &) { ctx->err = "host out of memory"; return LRGE_ERR_OUT_OF_MEMORY; }
+    catch (const std::exception &e) { ctx->err = e.what(); return LRGE_ERR_INVALID_ARG; }
+}
+
+bool valid_opts(const lrge_opts *o) {
+    return o && (o->platform == LRGE_PLATFORM_NANOPORE || o->platform == LRGE_PLATFORM_PACBIO) && o->shard_count >= 1 &&
+           o->shard_index >= 0 && o->shard_index < o->shard_count;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+void lrge_opts_default(lrge_opts *o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->platform = LRGE_PLATFORM_NANOPORE;      // Platform::default (lib.rs:163-168)
+    o->remove_internal = 0;                    // twoset/builder.rs:30
+    o->max_overhang_ratio = 0.2f;              // twoset/builder.rs:31
+    o->use_min_ref = 0;                        // twoset/builder.rs:32
+    o->shard_index = 0; o->shard_count = 1;
+}
+
+int lrge_gpu_create(int device, lrge_ctx **out) {
+    if (!out) return LRGE_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (liblrge_b200 has no CPU fallback)";
+        cudaGetLastError();
+        return LRGE_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return LRGE_ERR_INVALID_ARG; }
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        std::unique_ptr<lrge_ctx> c(new lrge_ctx());
+        c->device = device;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaMemcpyToSymbol(c_nt4, kNt4, 256));
+        *out = c.release();
+        return LRGE_OK;
+    } catch (const std::exception &ex) { g_create_error = ex.what(); cudaGetLastError(); return LRGE_ERR_CUDA; }
+}
+
+void lrge_gpu_destroy(lrge_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    delete ctx;
+}
+
+const char *lrge_gpu_last_error(const lrge_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int lrge_gpu_stage(lrge_ctx *ctx, const lrge_readset *rs, lrge_staged **out) {
+    if (!rs || !out) return LRGE_ERR_INVALID_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        std::unique_ptr<lrge_staged> s(new lrge_staged());
+        stage_readset(ctx, rs, s.get());
+        *out = s.release();
+    });
+}
+
+void lrge_gpu_unstage(lrge_ctx *ctx, lrge_staged *s) {
+    if (ctx) cudaSetDevice(ctx->device);
+    delete s;
+}
+
+int lrge_gpu_twoset_counts_staged(lrge_ctx *ctx, lrge_staged *T, lrge_staged *Q, const lrge_opts *opts,
+                                  uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats) {
+    if (!T || !Q || !counts || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
+    return guarded(ctx, [&] {
+        // twoset.rs:596-604: with use_min_ref and more target than query bases, index the query set
+        if (opts->use_min_ref && T->total_bases > Q->total_bases) run_overlap(ctx, Q, T, MODE_INVERSE, *opts, counts, nullptr, stats);
+        else run_overlap(ctx, T, Q, MODE_TWOSET, *opts, counts, had_mapping, stats);
+    });
+}
+
+int lrge_gpu_ava_counts_staged(lrge_ctx *ctx, lrge_staged *R, const lrge_opts *opts, uint32_t *counts, lrge_stats *stats) {
+    if (!R || !counts || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
+    return guarded(ctx, [&] { run_overlap(ctx, R, R, MODE_AVA, *opts, counts, nullptr, stats); });
+}
+
+int lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,
+                           uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats) {
+    if (!T || !Q || !counts || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
+    return guarded(ctx, [&] {
+        Timer tm(ctx->stream);
+        tm.start();
+        lrge_staged sT, sQ;
+        stage_readset(ctx, T, &sT);
+        stage_readset(ctx, Q, &sQ);
+        const float ms = tm.stop();
+        if (stats) stats->ms_h2d = ms;
+        if (opts->use_min_ref && sT.total_bases > sQ.total_bases) run_overlap(ctx, &sQ, &sT, MODE_INVERSE, *opts, counts, nullptr, stats);
+        else run_overlap(ctx, &sT, &sQ, MODE_TWOSET, *opts, counts, had_mapping, stats);
+        if (stats) stats->ms_total += ms;
+    });
+}
+
+int lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts, uint32_t *counts, lrge_stats *stats) {
+    if (!R || !counts || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
+    return guarded(ctx, [&] {
+        Timer tm(ctx->stream);
+        tm.start();
+        lrge_staged sR;
+        stage_readset(ctx, R, &sR);
+        const float ms = tm.stop();
+        if (stats) stats->ms_h2d = ms;
+        run_overlap(ctx, &sR, &sR, MODE_AVA, *opts, counts, nullptr, stats);
+        if (stats) stats->ms_total += ms;
+    });
+}
+
+int lrge_gpu_host_alloc(size_t bytes, void **out) {
+    if (!out) return LRGE_ERR_INVALID_ARG;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { *out = nullptr; cudaGetLastError(); return LRGE_ERR_CUDA; }
+    return LRGE_OK;
+}
+void lrge_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int lrge_gpu_dump_minimizers(lrge_ctx *ctx, const lrge_readset *rs, int32_t platform, uint64_t *x, uint64_t *y, uint64_t cap,
+                             uint64_t *n_out, uint32_t *cnt) {
+    if (!rs || !n_out) return LRGE_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        lrge_staged s;
+        stage_readset(ctx, rs, &s);
+        const MapOpt o = preset_for(platform);
+        sketch_readset(ctx, &s, o, &ctx->sk_str, nullptr, nullptr);
+        const uint64_t M = ctx->sk_str.M;
+        *n_out = M;
+        const uint64_t m = std::min(M, cap);
+        if (x && m) CUDA_CHECK(cudaMemcpyAsync(x, ctx->sk_str.x.p, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (y && m) CUDA_CHECK(cudaMemcpyAsync(y, ctx->sk_str.y.p, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cnt && rs->n) {
+            std::vector<uint32_t> moff((size_t)rs->n + 1);
+            CUDA_CHECK(cudaMemcpyAsync(moff.data(), ctx->sk_str.moff.p, ((size_t)rs->n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t i = 0; i < rs->n; ++i) cnt[i] = moff[i + 1] - moff[i];
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int lrge_gpu_dump_mid_occ(lrge_ctx *ctx, const lrge_readset *T, int32_t platform, int32_t *mid_occ, uint64_t *n_keys) {
+    if (!T || !mid_occ) return LRGE_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        lrge_staged s;
+        stage_readset(ctx, T, &s);
+        const MapOpt o = preset_for(platform);
+        sketch_readset(ctx, &s, o, &ctx->sk_idx, nullptr, nullptr);
+        BuiltIndex B = build_index(ctx, ctx->sk_idx, o);
+        *mid_occ = B.mid_occ;
+        if (n_keys) *n_keys = B.n_keys;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded
+inputs.  Integer work is compared bit-exactly."""
+import numpy as np
+import pytest
+
+import lrge_b200
+import oracle
+from lrge_b200 import readsim
+from lrge_b200.readset import ReadSet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = lrge_b200.Context(0)
+    yield c
+    c.close()
+
+
+def small_sets(nt=300, nq=120, mean=4000, gsize=300_000, err=readsim.ONT, n_rate=0.0):
+    g = readsim.genome(gsize)
+    T = readsim.reads(g, nt, mean, err, readsim.SEED_TARGET, "t", n_rate=n_rate)
+    Q = readsim.reads(g, nq, mean, err, readsim.SEED_QUERY, "q", n_rate=n_rate)
+    return T, Q
+
+
+def check_minimizers(ctx, rs, platform):
+    x, y, cnt = ctx.dump_minimizers(rs, platform)
+    want, wcnt = oracle.sketch_readset(rs, oracle.options(platform))
+    assert np.array_equal(cnt, wcnt)
+    assert x.shape[0] == want.shape[0]
+    assert np.array_equal(x, want["x"])
+    assert np.array_equal(y, want["y"])
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_sketch_parity(ctx, platform):
+    T, _ = small_sets(err=readsim.ONT if platform == "ont" else readsim.HIFI)
+    check_minimizers(ctx, T, platform)
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_sketch_parity_ambiguous_and_short(ctx, platform):
+    # N bases, lower case, reads shorter than k / shorter than w+k, homopolymers, tile-boundary lengths
+    T, _ = small_sets(nt=60, mean=3000, n_rate=0.003)
+    rng = np.random.default_rng(3)
+    recs = [(T.name(i), T.seq(i)) for i in range(T.n)]
+    recs += [("s%d" % L, bytes(rng.choice(list(b"ACGT"), size=L).tolist())) for L in (1, 5, 14, 15, 19, 20, 23, 24, 25, 31, 32, 33, 100)]
+    recs += [("hp", b"A" * 400 + b"C" * 300 + b"ACGT" * 50 + b"G" * 260 + b"TTTTACGTAGCATGCATGACTGACTAGCTAGCATG" * 4)]
+    recs += [("lc", T.seq(0).lower()), ("nn", b"N" * 50 + T.seq(1)[:500] + b"NNN" + T.seq(1)[500:900] + b"N")]
+    recs += [("tile%d" % L, bytes(rng.choice(list(b"ACGT"), size=L).tolist())) for L in (1023, 1024, 1025, 8191, 8192, 8193, 16384, 20000)]
+    recs += [("rep", b"ACGTTGCA" * 300)]
+    check_minimizers(ctx, ReadSet.from_records(recs), platform)
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_mid_occ_parity(ctx, platform):
+    T, _ = small_sets(nt=400, gsize=100_000, err=readsim.ONT if platform == "ont" else readsim.HIFI)
+    opt = oracle.options(platform)
+    idx = oracle.Index(T, opt, threads=4)
+    mid, nkeys = ctx.dump_mid_occ(T, platform)
+    assert nkeys == idx.n_keys
+    assert mid == opt.mid_occ
+
+
+def test_twoset_counts_parity_ont(ctx):
+    T, Q = small_sets()
+    res = ctx.twoset_counts(T, Q, "ont")
+    want, had, st = oracle.twoset_counts(T, Q, "ont", threads=8)
+    assert res.stats["mid_occ"] == st["mid_occ"]
+    assert res.stats["n_target_minimizers"] == st["n_t_minimizers"]
+    assert res.stats["n_query_minimizers"] == st["n_q_minimizers"]
+    assert res.stats["n_anchors"] == st["n_anchors"]
+    assert np.array_equal(res.counts, want)
+    assert np.array_equal(res.had_mapping, had)
+    assert res.stats["no_mapping_count"] == st["no_mapping_count"]
+    assert want.sum() > 0
+
+
+def test_twoset_counts_parity_c1(ctx):
+    _, platform, T, Q = readsim.make_config("C1")
+    res = ctx.twoset_counts(T, Q, platform)
+    want, had, st = oracle.twoset_counts(T, Q, platform, threads=8)
+    assert res.stats["n_anchors"] == st["n_anchors"]
+    assert np.array_equal(res.counts, want)
+    assert np.array_equal(res.had_mapping, had)
+
+
+def test_twoset_counts_parity_pb(ctx):
+    T, Q = small_sets(nt=200, nq=80, mean=5000, gsize=200_000, err=readsim.HIFI)
+    res = ctx.twoset_counts(T, Q, "pb")
+    want, had, st = oracle.twoset_counts(T, Q, "pb", threads=8)
+    assert res.stats["n_anchors"] == st["n_anchors"]
+    assert np.array_equal(res.counts, want)
+    assert np.array_equal(res.had_mapping, had)
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_ava_counts_parity(ctx, platform):
+    g = readsim.genome(200_000)
+    R = readsim.reads(g, 250, 4000, readsim.ONT if platform == "ont" else readsim.HIFI, readsim.SEED_AVA, "r")
+    res = ctx.ava_counts(R, platform)
+    want, st = oracle.ava_counts(R, platform, threads=8)
+    assert res.stats["n_anchors"] == st["n_anchors"]
+    assert np.array_equal(res.counts, want)
+    assert res.stats["n_overlaps"] == st["n_overlaps"]
+    assert res.stats["no_mapping_count"] == st["no_mapping_count"]
+
+
+def test_remove_internal_parity(ctx):
+    T, Q = small_sets(nt=300, nq=150, mean=3000)
+    for ratio in (0.2, 0.05):
+        res = ctx.twoset_counts(T, Q, "ont", remove_internal=True, max_overhang_ratio=ratio)
+        want, had, _ = oracle.twoset_counts(T, Q, "ont", remove_internal=True, max_overhang_ratio=ratio, threads=8)
+        assert np.array_equal(res.counts, want)
+        assert np.array_equal(res.had_mapping, had)
+    g = readsim.genome(150_000)
+    R = readsim.reads(g, 200, 3000, readsim.ONT, readsim.SEED_AVA, "r")
+    res = ctx.ava_counts(R, "ont", remove_internal=True)
+    want, _ = oracle.ava_counts(R, "ont", remove_internal=True, threads=8)
+    assert np.array_equal(res.counts, want)
+
+
+def test_use_min_ref_inverse_parity(ctx):
+    T, Q = small_sets(nt=300, nq=100)
+    assert T.total_bases > Q.total_bases
+    for F in (False, True):
+        res = ctx.twoset_counts(T, Q, "ont", use_min_ref=True, remove_internal=F)
+        want, st = oracle.twoset_inverse_counts(T, Q, "ont", remove_internal=F, threads=8)
+        assert np.array_equal(res.counts, want)
+        assert res.stats["no_mapping_count"] == st["no_mapping_count"]
+
+
+def test_target_sharding_is_additive(ctx):
+    T, Q = small_sets()
+    full = ctx.twoset_counts(T, Q, "ont")
+    for world in (2, 3):
+        parts = [ctx.twoset_counts(T, Q, "ont", shard_index=r, shard_count=world) for r in range(world)]
+        assert np.array_equal(sum(p.counts for p in parts), full.counts)
+        assert all(p.stats["mid_occ"] == full.stats["mid_occ"] for p in parts)
+        assert sum(p.stats["n_anchors"] for p in parts) == full.stats["n_anchors"]
+
+
+def test_shared_and_duplicate_names(ctx):
+    # a query that is also a target (NO_DIAG path) and two targets sharing a name (HashSet<name> dedupe)
+    T, Q = small_sets(nt=120, nq=40, gsize=100_000)
+    recs_t = [(T.name(i), T.seq(i)) for i in range(T.n)]
+    recs_q = [(Q.name(i), Q.seq(i)) for i in range(Q.n)]
+    recs_q[0] = recs_t[5]
+    recs_t[7] = (recs_t[6][0], recs_t[7][1])
+    T2, Q2 = ReadSet.from_records(recs_t), ReadSet.from_records(recs_q)
+    res = ctx.twoset_counts(T2, Q2, "ont")
+    want, had, _ = oracle.twoset_counts(T2, Q2, "ont", threads=4)
+    assert np.array_equal(res.counts, want)
+    assert np.array_equal(res.had_mapping, had)
+
+
+def test_error_paths(ctx):
+    T, Q = small_sets(nt=20, nq=5, gsize=50_000)
+    dup = ReadSet.from_records([(T.name(0), T.seq(0)), (T.name(0), T.seq(1)), (T.name(2), T.seq(2))])
+    with pytest.raises(lrge_b200.LrgeError) as e:
+        ctx.ava_counts(dup, "ont")
+    assert e.value.kind == "DuplicateReadIdentifier"
+    empty = ReadSet.from_records([("a", b"ACGT" * 100), ("b", b"")])
+    with pytest.raises(lrge_b200.LrgeError) as e:
+        ctx.twoset_counts(T, empty, "ont")
+    assert e.value.kind == "MapError"
+
+
+def test_strategy_estimates_match_oracle(ctx):
+    T, Q = small_sets()
+    s = lrge_b200.TwoSetStrategy(T, Q, ctx=ctx)
+    r = s.estimate(True, lrge_b200.LOWER_QUANTILE, lrge_b200.UPPER_QUANTILE)
+    want, had, _ = oracle.twoset_counts(T, Q, "ont", threads=8)
+    avg = np.float32(T.total_bases) / np.float32(T.n)
+    est = [oracle.per_read_estimate(int(l), avg, T.n, int(c), 100) for l, c in zip(Q.lengths(), want)]
+    lo, md, up = oracle.estimate(est, True, 0.15, 0.65)
+    assert (r.lower, r.estimate, r.upper) == (lo, md, up)
+    assert r.no_mapping_count == int((had == 0).sum())
+    assert abs(r.estimate - 300_000) / 300_000 < 0.5
