@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- read-pair overlaps/sec of the overlap hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (liblrge_b200.so through the C-ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A step is one pass of the whole hot path (sketch -> index -> seed lookup -> chaining -> per-read counts)
+over the two-set workload BASELINE.json's metric is quoted on (configs[1]: 5 000 query x 10 000 target
+synthetic ONT reads, mean 8 kb, 4.4 Mbp genome).  With N > 1 (one process per GPU under torchrun) the
+target set grows to N x 10 000 reads and is sharded rid % N across ranks -- per-GPU work stays fixed
+("weak") -- and every step ends with the library's NCCL all-reduce of the per-read counts.
+
+Prints ONE JSON line on rank 0.  `value` is timed with the read sets already resident in HBM; `e2e` goes
+through the host-buffer C-ABI call with pinned inputs, H2D and D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "read_pair_overlaps_per_sec"
+UNIT = "overlaps/s"
+WORKLOAD = "C2"
+
+
+def workload(name: str, n_gpus: int, scale: float):
+    from lrge_b200 import readsim
+    strat, platform, T, Q = readsim.make_config(name, scale=scale, target_mult=n_gpus)
+    assert strat == "twoset"
+    desc = (f"{name} two-set {Q.n} query x {T.n} target synthetic ONT reads, mean 8 kb, "
+            f"{readsim.CONFIGS[name][4] * scale / 1e6:.2f} Mbp genome")
+    return platform, T, Q, desc
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args):
+    """The reference's own CPU path for this workload: the oracle port (minimap2 2.30 restatement + liblrge
+    counting; the Rust/minimap2-sys build is not possible in this image), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    platform, T, Q, desc = workload(args.config, args.gpus, args.scale)
+    threads = os.cpu_count() or 1
+    times, ovl = [], 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        counts, had, st = oracle.twoset_counts(T, Q, platform, threads=threads)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+        ovl = int(counts.sum())
+    ms = 1e3 * sum(times) / len(times)
+    value = ovl / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": desc, "targets_scale_with_gpus": True},
+        "overlaps_per_step": ovl, "gbases_per_s": (T.total_bases + Q.total_bases) / 1e9 / (ms / 1e3),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "the full workload (index build + map + count), every step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import lrge_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: liblrge_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    platform, T, Q, desc = workload(args.config, world, args.scale)
+    ctx = lrge_b200.Context(local)
+    if world > 1:
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident.copy_(torch.frombuffer(bytearray(lrge_b200.Context.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(ident, 0)
+        ctx.comm_init(rank, world, bytes(ident.cpu().numpy().tobytes()))
+    shard = dict(shard_index=rank, shard_count=world)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sT, sQ = ctx.stage(T), ctx.stage(Q)
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------------
+    last = None
+    for _ in range(args.warmup):
+        last = ctx.twoset_counts(sT, sQ, platform, **shard)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev_ms, chain_ms, launches = 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        last = ctx.twoset_counts(sT, sQ, platform, **shard)
+        ev_ms += last.stats["ms_total"]
+        chain_ms += last.stats["ms_chain_kernel"]
+        launches += last.stats["n_kernel_launches"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.summary() if rank == 0 else None
+    t = torch.tensor([ev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ev_ms, wall_ms = float(t[0]), float(t[1])
+    ms_per_step = ev_ms / args.steps
+    overlaps = int(last.counts.sum())          # counts are already reduced over all shards
+    value = overlaps / (ms_per_step / 1e3)
+
+    # ---- e2e: host buffers through the C-ABI, H2D + D2H inside ------------------------------------------
+    pT, bT = lrge_b200.pinned_copy(T)
+    pQ, bQ = lrge_b200.pinned_copy(Q)
+    for _ in range(min(args.warmup, 2)):
+        ctx.twoset_counts(pT, pQ, platform, **shard)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_last = ctx.twoset_counts(pT, pQ, platform, **shard)
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0])
+    assert np.array_equal(e2e_last.counts, last.counts)
+    h2d = int(T.total_bases + Q.total_bases + 8 * (T.n + Q.n + 2))
+    d2h = int(5 * Q.n)
+
+    if rank != 0:
+        ctx.close()
+        dist.destroy_process_group()
+        return
+    st = last.stats
+    # ---- roofline of the dominant kernel (chain_pair_kernel, K6): SURVEY.md 8(d): 16*A + 8*C + 4*N_Q ----
+    peak, peak_src = measured_peak()
+    alg_bytes = 16 * st["n_anchors"] + 8 * st["n_overlaps"] + 4 * Q.n
+    k_ms = chain_ms / args.steps
+    achieved = alg_bytes / 1e9 / (k_ms / 1e3) if k_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("workload") == args.config and tj.get("kernel") == "chain_pair_kernel":
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    # ---- CPU baseline: the oracle port on this box's cores, rank 0, N = 1 only ------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        threads = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        oc, oh, ost = oracle.twoset_counts(T, Q, platform, threads=threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": int(oc.sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "the full workload once (index build + map + count)", "seconds": dt,
+               "counts_identical_to_gpu": bool(np.array_equal(oc, last.counts))}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": desc, "targets_scale_with_gpus": True, "sharding": f"targets rid % {world}",
+                   "l2": "256 MiB memset between steps; index + anchors (>1 GB) exceed L2"},
+        "overlaps_per_step": overlaps,
+        "gbases_per_s": (T.total_bases + Q.total_bases) / 1e9 / (ms_per_step / 1e3),
+        "candidate_pairs_per_s": T.n * Q.n / (ms_per_step / 1e3),
+        "wall_ms_per_step": wall_ms / args.steps,
+        "stage_ms": {k: st[k] for k in st if k.startswith("ms_")},
+        "counts": {k: st[k] for k in ("n_target_minimizers", "n_query_minimizers", "n_keys", "n_seeds", "n_hits", "n_anchors",
+                                      "n_pairs", "mid_occ", "n_batches")},
+        "roofline": {"kernel": "chain_pair_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms},
+        "cpu_baseline": cpu,
+        "e2e": {"value": overlaps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    for b in (bT, bQ):
+        b.free()
+    sT.free()
+    sQ.free()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=WORKLOAD)
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    need = [os.path.join(ROOT, "lrge_b200", "csrc", "liblrge_b200.so"), os.path.join(ROOT, "lrge_b200", "csrc", "libreadsim.so"),
+            os.path.join(ROOT, "oracle", "liboracle.so")]
+    if not all(os.path.exists(p) for p in need):
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            import __graft_entry__ as g
+            g.build()
+        else:
+            while not all(os.path.exists(p) for p in need):
+                time.sleep(1.0)
+            time.sleep(2.0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

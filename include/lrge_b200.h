@@ -89,7 +89,9 @@ typedef struct lrge_stats {
     uint32_t n_kernel_launches;
     /* device time per stage in ms (CUDA events on the context's stream) */
     float ms_h2d, ms_pack, ms_sketch, ms_index, ms_seed, ms_sort, ms_chain, ms_d2h, ms_total;
-    float reserved[7];
+    float ms_chain_kernel;       /* the chaining kernel alone, summed over batches */
+    float ms_comm;               /* NCCL reduction of the per-read counts */
+    float reserved[5];
 } lrge_stats;
 
 typedef struct lrge_ctx lrge_ctx;
@@ -119,6 +121,13 @@ int  lrge_gpu_twoset_counts_staged(lrge_ctx *ctx, lrge_staged *T, lrge_staged *Q
                                    uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats);
 int  lrge_gpu_ava_counts_staged(lrge_ctx *ctx, lrge_staged *R, const lrge_opts *opts,
                                 uint32_t *counts, lrge_stats *stats);
+
+/* One process per GPU. Rank 0 makes an id (LRGE_COMM_ID_BYTES bytes) and hands it to every rank out of band;
+ * each rank then joins.  With a communicator and opts->shard_count == world, the *_counts calls finish with
+ * one NCCL all-reduce over NVLink: counts are summed (target shards are additive), had_mapping is OR-ed. */
+#define LRGE_COMM_ID_BYTES 128
+int  lrge_gpu_comm_unique_id(uint8_t *out, size_t size);
+int  lrge_gpu_comm_init(lrge_ctx *ctx, int rank, int world, const uint8_t *unique_id, size_t size);
 
 /* Pinned host memory for the caller's read buffers (optional; pageable memory works, slower). */
 int  lrge_gpu_host_alloc(size_t bytes, void **out);

@@ -34,7 +34,7 @@ C_API = [
     "lrge_gpu_twoset_counts", "lrge_gpu_ava_counts", "lrge_gpu_stage", "lrge_gpu_unstage",
     "lrge_gpu_twoset_counts_staged", "lrge_gpu_ava_counts_staged", "lrge_gpu_host_alloc", "lrge_gpu_host_free",
     "lrge_gpu_dump_minimizers", "lrge_gpu_dump_mid_occ", "lrge_per_read_estimate", "lrge_estimate", "lrge_is_internal",
-    "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates",
+    "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates", "lrge_gpu_comm_unique_id", "lrge_gpu_comm_init",
 ]
 
 
@@ -64,7 +64,8 @@ class Stats(ctypes.Structure):
         ("ms_h2d", ctypes.c_float), ("ms_pack", ctypes.c_float), ("ms_sketch", ctypes.c_float),
         ("ms_index", ctypes.c_float), ("ms_seed", ctypes.c_float), ("ms_sort", ctypes.c_float),
         ("ms_chain", ctypes.c_float), ("ms_d2h", ctypes.c_float), ("ms_total", ctypes.c_float),
-        ("reserved", ctypes.c_float * 7),
+        ("ms_chain_kernel", ctypes.c_float), ("ms_comm", ctypes.c_float),
+        ("reserved", ctypes.c_float * 5),
     ]
 
     def as_dict(self):
@@ -102,6 +103,8 @@ def lib():
         L.lrge_gpu_unstage.restype = None
         L.lrge_gpu_twoset_counts_staged.argtypes = [vp, vp, vp, P(Opts), vp, vp, P(Stats)]
         L.lrge_gpu_ava_counts_staged.argtypes = [vp, vp, P(Opts), vp, P(Stats)]
+        L.lrge_gpu_comm_unique_id.argtypes = [vp, ctypes.c_size_t]
+        L.lrge_gpu_comm_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_size_t]
         L.lrge_gpu_host_alloc.argtypes = [ctypes.c_size_t, P(vp)]
         L.lrge_gpu_host_free.argtypes = [vp]
         L.lrge_gpu_host_free.restype = None
@@ -211,6 +214,19 @@ class Context:
     def _check(self, rc: int):
         if rc != 0:
             raise LrgeError(rc, lib().lrge_gpu_last_error(self.h).decode())
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (ctypes.c_uint8 * 128)()
+        rc = lib().lrge_gpu_comm_unique_id(buf, 128)
+        if rc != 0:
+            raise LrgeError(rc, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(lib().lrge_gpu_comm_init(self.h, rank, world, buf, 128))
+        self.rank, self.world = rank, world
 
     def stage(self, rs: ReadSet) -> Staged:
         return Staged(self, rs)

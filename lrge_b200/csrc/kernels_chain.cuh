@@ -211,4 +211,287 @@ __global__ void pair_flag_kernel(const uint64_t *__restrict__ akey, uint64_t n, 
     flags[i] = (i == 0 || (akey[i] >> shift) != (akey[i - 1] >> shift)) ? 1 : 0;
 }
 
+
+// =================================================================================================
+// v2: one WARP per (query, target, strand) group; anchors i are processed in order, the predecessors
+// j = i-1, i-2, ... of one anchor are scored 32 at a time (lane l takes j = base - l, i.e. lane order =
+// the serial visiting order of mg_lchain_dp).  The three order-dependent pieces of the inner loop are
+// resolved with warp scans so that the result equals the sequential loop exactly:
+//   * "sc > max_f"            -> exclusive prefix-max over lanes (plus the running max_f of earlier chunks);
+//   * t[p[j]] = i marks       -> every scored lane stores its mark, __syncwarp, then lanes read t[j]:
+//                                 a mark made by lane l targets p[j] < j, so only lanes > l can see it,
+//                                 which is the serial order; marks made past the break are never read
+//                                 again for this i and are stale for every later i;
+//   * n_skip (+1 on a marked non-improving lane, -1 floored at 0 on an improving lane, break when > max_skip)
+//                              -> a clamped walk: n_l = N_l - min(0, min_{k<=l} N_k) with N = unclamped
+//                                 prefix sum; the first lane where a marked step reaches > max_skip is
+//                                 the break lane, later lanes are discarded.
+// =================================================================================================
+
+constexpr int CG_THREADS = 256;
+
+struct GroupTask {
+    const uint2 *anc;            // compact sorted anchors: x = target pos, y = span << 24 | qpos'
+    const uint64_t *akey;        // sorted keys (query / target / strand of a group)
+    const uint32_t *gstart;      // n_groups + 1
+    const uint32_t *glist;       // 4 size classes, each a list of group ids, capacity n_groups
+    const uint32_t *gcount;      // entries per class
+    uint32_t n_groups;
+    uint32_t *work_ctr;
+    int2 *fp;                    // per anchor (f, p)
+    int32_t *t;                  // per anchor marks, zeroed before launch
+    uint32_t *pflag;             // per group: pair-level "already counted"
+    int PB, RB;
+    uint32_t q0;
+};
+
+__device__ __forceinline__ int32_t warp_prefix_max_incl(int32_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v = max(v, u);
+    }
+    return v;
+}
+__device__ __forceinline__ int32_t warp_prefix_min_incl(int32_t v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v = min(v, u);
+    }
+    return v;
+}
+
+__device__ __forceinline__ int32_t comput_sc_smem(int32_t ri, int32_t qi, int32_t rj, int32_t qj, int32_t span_j,
+                                                  const ChainParams &P, const uint8_t *s_pen) {
+    const int32_t dq = qi - qj;
+    if (dq <= 0 || dq > P.max_dist_x) return INT32_MIN;
+    const int32_t dr = ri - rj;
+    if (dr == 0 || dq > P.max_dist_y) return INT32_MIN;
+    const int32_t dd = dr > dq ? dr - dq : dq - dr;
+    if (dd > P.bw) return INT32_MIN;
+    const int32_t dg = dr < dq ? dr : dq;
+    int32_t sc = span_j < dg ? span_j : dg;
+    if (dd || dg > span_j) sc -= (int32_t)s_pen[dd];
+    return sc;
+}
+
+// mg_lchain_dp for one group, warp-cooperative
+__device__ void warp_group_dp(const uint2 *__restrict__ anc, int32_t n, const ChainParams &P, const uint8_t *s_pen,
+                              int2 *fp, int32_t *t, uint32_t lane) {
+    int32_t st = 0, max_ii = -1, r_maxii = 0, f_maxii = 0;
+    const uint32_t le_mask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1);
+    for (int32_t i = 0; i < n; ++i) {
+        const uint2 ai = anc[i];
+        const int32_t ri = (int32_t)ai.x, qi = (int32_t)(ai.y & 0xffffff);
+        int32_t max_f = (int32_t)(ai.y >> 24), max_j = -1, n_skip = 0;
+        while (st < i && ri > (int32_t)anc[st].x + P.max_dist_x) ++st;
+        if (i - st > P.max_iter) st = i - P.max_iter;
+        int32_t end_j = st - 1;
+        for (int32_t base = i - 1; base >= st; base -= 32) {
+            const int32_t j = base - (int32_t)lane;
+            int32_t s = INT32_MIN, pj = -1;
+            if (j >= st) {
+                const uint2 aj = anc[j];
+                s = comput_sc_smem(ri, qi, (int32_t)aj.x, (int32_t)(aj.y & 0xffffff), (int32_t)(aj.y >> 24), P, s_pen);
+                if (s != INT32_MIN) {
+                    const int2 v = fp[j];
+                    s += v.x;
+                    pj = v.y;
+                }
+            }
+            const bool scored = s != INT32_MIN;
+            if (scored && pj >= 0) t[pj] = i;
+            __syncwarp();
+            const int32_t tj = scored ? t[j] : -1;
+            const int32_t incl = warp_prefix_max_incl(s, lane);
+            int32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = INT32_MIN;
+            excl = max(excl, max_f);
+            const bool improved = scored && s > excl;
+            const bool marked = scored && !improved && tj == i;
+            const uint32_t I = __ballot_sync(0xffffffffu, improved), M = __ballot_sync(0xffffffffu, marked);
+            uint32_t keep = 0xffffffffu;
+            int32_t brk_lane = -1;
+            if (M) {
+                const int32_t N = n_skip + __popc(M & le_mask) - __popc(I & le_mask);
+                const int32_t mn = min(0, warp_prefix_min_incl(N, lane));
+                const int32_t nl = N - mn;
+                const uint32_t B = __ballot_sync(0xffffffffu, marked && nl > P.max_skip);
+                if (B) { brk_lane = __ffs(B) - 1; keep = (1u << brk_lane) - 1; }
+                n_skip = __shfl_sync(0xffffffffu, nl, 31);
+            } else {
+                n_skip = max(0, n_skip - __popc(I));
+            }
+            const uint32_t Ik = I & keep;
+            if (Ik) {
+                const int top = 31 - __clz(Ik);
+                max_f = __shfl_sync(0xffffffffu, s, top);
+                max_j = base - top;
+            }
+            if (brk_lane >= 0) { end_j = base - brk_lane; break; }
+        }
+        // rescue of a far best predecessor (max_ii)
+        if (max_ii < 0 || ri - r_maxii > P.max_dist_x) {
+            int32_t bf = INT32_MIN, bj = -1;
+            for (int32_t base = i - 1; base >= st; base -= 32) {
+                const int32_t j = base - (int32_t)lane;
+                if (j >= st) { const int32_t fj = fp[j].x; if (fj > bf) bf = fj, bj = j; }   // descending j per lane: first max = largest j
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int32_t of = __shfl_xor_sync(0xffffffffu, bf, o), oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (oj >= 0 && (bj < 0 || of > bf || (of == bf && oj > bj))) bf = of, bj = oj;
+            }
+            max_ii = bj;
+            if (bj >= 0) { r_maxii = (int32_t)anc[bj].x; f_maxii = bf; }
+        }
+        if (max_ii >= 0 && max_ii < end_j) {
+            const uint2 am = anc[max_ii];
+            const int32_t tmp = comput_sc_smem(ri, qi, (int32_t)am.x, (int32_t)(am.y & 0xffffff), (int32_t)(am.y >> 24), P, s_pen);
+            if (tmp != INT32_MIN && max_f < tmp + f_maxii) max_f = tmp + f_maxii, max_j = max_ii;
+        }
+        if (lane == 0) fp[i] = make_int2(max_f, max_j);
+        __syncwarp();
+        if (max_ii < 0 || (ri - r_maxii <= P.max_dist_x && f_maxii < max_f)) { max_ii = i; r_maxii = ri; f_maxii = max_f; }
+    }
+}
+
+// mg_chain_backtrack for one group: chain starts are visited from the highest (f, index) down; the search for
+// the next start is warp-parallel, the walk itself is done by lane 0.  Calls on_chain (all lanes, uniform
+// arguments) for every kept chain until it returns true.
+template <typename F>
+__device__ void warp_group_backtrack(int32_t n, const ChainParams &P, const int2 *fp, int32_t *t, uint32_t lane, F on_chain) {
+    for (int32_t i = lane; i < n; i += 32) t[i] = 0;
+    __syncwarp();
+    int32_t last_f = INT32_MAX, last_i = n;
+    for (;;) {
+        int32_t bf = INT32_MIN, bi = -1;
+        for (int32_t i = lane; i < n; i += 32) {
+            const int32_t fi = fp[i].x;
+            if (fi < P.min_sc || t[i] != 0) continue;
+            if (fi > last_f || (fi == last_f && i >= last_i)) continue;
+            if (fi > bf || (fi == bf && i > bi)) bf = fi, bi = i;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int32_t of = __shfl_xor_sync(0xffffffffu, bf, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || of > bf || (of == bf && oi > bi))) bf = of, bi = oi;
+        }
+        if (bi < 0) break;
+        last_f = bf, last_i = bi;
+        int32_t cnt = 0, first = bi, sc = 0;
+        if (lane == 0) {
+            // mg_chain_bk_end
+            int32_t i = bi, end_i = -1, max_i = bi, max_s = 0;
+            do {
+                int32_t s;
+                t[i] = 2;
+                end_i = i = fp[i].y;
+                s = i < 0 ? bf : bf - fp[i].x;
+                if (s > max_s) max_s = s, max_i = i;
+                else if (max_s - s > P.bw) break;
+            } while (i >= 0 && t[i] == 0);
+            for (i = bi; i >= 0 && i != end_i; i = fp[i].y) t[i] = 0;
+            end_i = max_i;
+            for (i = bi; i != end_i; i = fp[i].y) { ++cnt; t[i] = 1; first = i; }
+            sc = i < 0 ? bf : bf - fp[i].x;
+        }
+        __syncwarp();
+        cnt = __shfl_sync(0xffffffffu, cnt, 0); first = __shfl_sync(0xffffffffu, first, 0); sc = __shfl_sync(0xffffffffu, sc, 0);
+        if (sc >= P.min_sc && cnt > 0 && cnt >= P.min_cnt) {
+            ChainCoord c; c.a_first = first; c.a_last = bi; c.sc = sc; c.cnt = cnt;
+            if (on_chain(c)) return;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, ChainParams P, CountOut O) {
+    __shared__ uint8_t s_pen[2048];
+    for (int i = threadIdx.x; i <= P.bw && i < 2048; i += blockDim.x) s_pen[i] = (uint8_t)P.pen[i];
+    __syncthreads();
+    const uint32_t lane = lane_id();
+    const uint32_t c0 = T.gcount[0], c1 = c0 + T.gcount[1], c2 = c1 + T.gcount[2], total = c2 + T.gcount[3];
+    const uint64_t posmask = (1ULL << T.PB) - 1;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(T.work_ctr, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total) break;
+        uint32_t g;
+        if (w < c0) g = T.glist[w];
+        else if (w < c1) g = T.glist[(size_t)T.n_groups + (w - c0)];
+        else if (w < c2) g = T.glist[2 * (size_t)T.n_groups + (w - c1)];
+        else g = T.glist[3 * (size_t)T.n_groups + (w - c2)];
+        const uint32_t g0 = T.gstart[g];
+        const int32_t n = (int32_t)(T.gstart[g + 1] - g0);
+        const uint64_t k0 = T.akey[g0];
+        const int strand = (int)((k0 >> T.PB) & 1);
+        const uint32_t rid = (uint32_t)((k0 >> (T.PB + 1)) & ((1ULL << T.RB) - 1));
+        const uint32_t qid = T.q0 + (uint32_t)(k0 >> (T.PB + 1 + T.RB));
+        const uint2 *anc = T.anc + g0;
+        int2 *fp = T.fp + g0;
+        int32_t *t = T.t + g0;
+        warp_group_dp(anc, n, P, s_pen, fp, t, lane);
+        __syncwarp();
+        const int32_t qlen = (int32_t)O.len_q[qid], tlen = (int32_t)O.len_t[rid];
+        int kept = 0, pass = 0;
+        warp_group_backtrack(n, P, fp, t, lane, [&](const ChainCoord &c) -> bool {
+            kept = 1;
+            if (!O.remove_internal) { pass = 1; return true; }
+            const uint2 af = anc[c.a_first], al = anc[c.a_last];
+            const int32_t span0 = (int32_t)(af.y >> 24);
+            const int32_t x0 = (int32_t)af.x, x1 = (int32_t)al.x;
+            const int32_t y0 = (int32_t)(af.y & 0xffffff), y1 = (int32_t)(al.y & 0xffffff);
+            const int32_t rs = x0 + 1 > span0 ? x0 + 1 - span0 : 0, re = x1 + 1;
+            int32_t qs, qe;
+            if (!strand) { qs = y0 + 1 - span0; qe = y1 + 1; }
+            else { qs = qlen - (y1 + 1); qe = qlen - (y0 + 1 - span0); }
+            int32_t overhang;
+            if (!strand) overhang = min(qs, rs) + min(qlen - qe, tlen - re);
+            else overhang = min(qs, tlen - re) + min(qlen - qe, rs);
+            const int32_t maplen = max(qe - qs, re - rs);
+            bool drop;
+            if (O.mode == 2) drop = overhang > (int32_t)__fmul_rn((float)maplen, O.ratio);
+            else drop = __fdiv_rn((float)overhang, (float)maplen) < O.ratio;
+            if (!drop) { pass = 1; return true; }
+            return false;
+        });
+        if (lane == 0 && kept) {
+            // the two strand groups of one (query, target) pair share a slot: the forward group's
+            uint32_t slot = g;
+            if (strand && g > 0 && (T.akey[T.gstart[g - 1]] >> (T.PB + 1)) == (k0 >> (T.PB + 1))) slot = g - 1;
+            if (O.mode == 0) O.had_mapping[qid] = 1;
+            if (pass && atomicExch(&T.pflag[slot], 1u) == 0u) {
+                if (O.mode == 0) { if (O.names_unique) atomicAdd(&O.counts[qid], 1u); }
+                else if (O.mode == 1) { if (O.rank_q[qid] != O.rank_t[rid]) { atomicAdd(&O.counts[qid], 1u); atomicAdd(&O.counts[rid], 1u); } }
+                else atomicAdd(&O.counts[rid], 1u);
+            }
+        }
+        (void)posmask;
+    }
+}
+
+// K5b: sorted (key, payload) -> compact anchors + group-start flags
+__global__ void group_mark_kernel(const uint64_t *__restrict__ akey, const uint32_t *__restrict__ aval, uint64_t n, int PB,
+                                  uint2 *__restrict__ anc, uint8_t *__restrict__ flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = akey[i];
+    anc[i] = make_uint2((uint32_t)(k & ((1ULL << PB) - 1)), aval[i]);
+    flags[i] = (i == 0 || (k >> PB) != (akey[i - 1] >> PB)) ? 1 : 0;
+}
+
+// groups that can hold a chain (n >= min_cnt and n * max_span >= min_sc: f <= sum of spans) -> 4 size classes
+__global__ void group_classify_kernel(const uint32_t *__restrict__ gstart, uint32_t n_groups, int min_cnt, int min_sc,
+                                      int max_span, uint32_t *__restrict__ glist, uint32_t *__restrict__ gcount) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint32_t n = gstart[g + 1] - gstart[g];
+    if ((int)n < min_cnt || (int64_t)n * max_span < min_sc) return;
+    const int c = n >= 2048 ? 0 : n >= 256 ? 1 : n >= 48 ? 2 : 3;
+    const uint32_t slot = atomicAdd(&gcount[c], 1u);
+    glist[(size_t)c * n_groups + slot] = g;
+}
+
 }  // namespace lrge

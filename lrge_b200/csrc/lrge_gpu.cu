@@ -18,6 +18,7 @@
 #include "kernels_chain.cuh"
 
 #include <cub/cub.cuh>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
@@ -93,6 +94,8 @@ const uint8_t kNt4[256] = {
 
 thread_local std::string g_create_error;
 
+struct NcclError : std::runtime_error { using std::runtime_error::runtime_error; };
+
 struct Timer {
     cudaEvent_t a, b;
     cudaStream_t s;
@@ -137,8 +140,13 @@ struct lrge_ctx {
     // seed / anchors
     DevBuf flt, hstart, hn, acnt, aoff, qaoff;
     DevBuf akey0, akey1, aval0, aval1, flags, pstart, npairs, f, p, t, pair_res;
+    DevBuf anc, fp, glist, gmeta, pflag;
+    bool chain_v1 = false;                 // LRGE_CHAIN_V1=1: thread-per-pair debug kernel
     DevBuf rank_idx, rank_str, len_idx, len_str, pen, counts, had, counters;
     std::vector<int32_t> pen_host; int pen_k = 0, pen_bw = 0;
+    // one process per GPU: NCCL communicator for the per-read count reduction
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
 };
 
 namespace {
@@ -175,6 +183,17 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s) {
         CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + rs->off[0], s->total_bases, cudaMemcpyHostToDevice, c->stream));
     h2d(c, s->off, s->h_off.data(), s->h_off.size());
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+__global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t mul, uint32_t n,
+                                  uint32_t *__restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[(size_t)idx[i] * mul];
+}
+__global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n,
+                                  uint64_t *__restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
 }
 
 // K0 + K1: sketch a staged read set into `out`
@@ -256,12 +275,9 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         else sketch_kernel<false, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
         ++c->launches;
         // per-read minimizer offsets: woff at the first warp sub-tile of every read
-        std::vector<uint32_t> woff_h((size_t)nw + 1);
-        CUDA_CHECK(cudaMemcpyAsync(woff_h.data(), c->woff.p, ((size_t)nw + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        std::vector<uint32_t> moff(n + 1);
-        for (uint32_t i = 0; i <= n; ++i) moff[i] = woff_h[(size_t)tile_off[i] * (SK_THREADS / 32)];
-        h2d(c, out->moff, moff.data(), n + 1);
+        gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), c->tile_off.as<uint32_t>(),
+                                                                     SK_THREADS / 32, n + 1, out->moff.as<uint32_t>());
+        ++c->launches;
     } else {
         uint32_t z = 0;
         h2d(c, out->moff, &z, 1);
@@ -444,10 +460,11 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         ++c->launches;
         // anchors before each query: aoff[moff[q]]
         CUDA_CHECK(cudaMemcpyAsync(moff_h.data(), sq->moff.p, ((size_t)str->n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-        std::vector<uint64_t> aoff_h(MQ + 1);
-        CUDA_CHECK(cudaMemcpyAsync(aoff_h.data(), c->aoff.p, (MQ + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        gather_u64_kernel<<<(str->n + 1 + 255) / 256, 256, 0, c->stream>>>(c->aoff.as<uint64_t>(), sq->moff.as<uint32_t>(), str->n + 1,
+                                                                          c->qaoff.as<uint64_t>());
+        ++c->launches;
+        CUDA_CHECK(cudaMemcpyAsync(qa.data(), c->qaoff.p, ((size_t)str->n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        for (uint32_t q = 0; q <= str->n; ++q) qa[q] = aoff_h[moff_h[q]];
     }
     CUDA_CHECK(cudaGetLastError());
     S.ms_seed = tm.stop();
@@ -459,7 +476,8 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
     size_t reusable = c->akey0.cap + c->akey1.cap + c->aval0.cap + c->aval1.cap + c->flags.cap + c->pstart.cap +
                       c->f.cap + c->p.cap + c->t.cap + c->pair_res.cap;
-    uint64_t a_max = (uint64_t)((free_b + reusable) * 0.7 / 48.0);
+    reusable += c->anc.cap + c->fp.cap;
+    uint64_t a_max = (uint64_t)((free_b + reusable) * 0.7 / 56.0);
     a_max = std::min<uint64_t>(a_max, (1ull << 31) - 1024);
     const int PB = bits_for(idx->max_len ? idx->max_len - 1 : 0), RB = bits_for(idx->n ? idx->n - 1 : 0);
 
@@ -499,57 +517,128 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
             cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
                                             c->aval1.as<uint32_t>(), (int64_t)nA, 0, QB + RB + 1 + PB, c->stream);
             c->launches += 1 + (QB + RB + 1 + PB + 7) / 8;
-            // pair boundaries
-            c->flags.reserve(nA + 1);
-            c->pstart.reserve((nA + 2) * 4);
-            c->npairs.reserve(16);
-            pair_flag_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), nA, PB + 1, c->flags.as<uint8_t>());
-            cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
-                                       c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
-            cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
-                                       c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
-            c->launches += 2;
-            uint32_t n_pairs = 0;
-            CUDA_CHECK(cudaMemcpyAsync(&n_pairs, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            const uint32_t sentinel = (uint32_t)nA;
-            CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_pairs, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
-            S.ms_sort += tm.stop();
-            S.n_pairs += n_pairs;
-
-            tm.start();
-            c->f.reserve(nA * 4); c->p.reserve(nA * 4); c->t.reserve(nA * 4);
-            c->pair_res.reserve((size_t)n_pairs + 1);
-            CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
-            PairTask T{};
-            T.akey = c->akey1.as<uint64_t>(); T.aval = c->aval1.as<uint32_t>(); T.pstart = c->pstart.as<uint32_t>();
-            T.n_pairs = n_pairs; T.PB = PB; T.RB = RB; T.q0 = q0;
-            T.f = c->f.as<int32_t>(); T.p = c->p.as<int32_t>(); T.t = c->t.as<int32_t>();
             CountOut O{};
-            O.counts = c->counts.as<uint32_t>(); O.had_mapping = c->had.as<uint8_t>(); O.pair_res = c->pair_res.as<uint8_t>();
+            O.counts = c->counts.as<uint32_t>(); O.had_mapping = c->had.as<uint8_t>();
             O.len_q = K.len_q; O.len_t = K.len_t; O.rank_q = K.rank_q; O.rank_t = K.rank_t;
             O.mode = mode; O.remove_internal = opts.remove_internal; O.ratio = opts.max_overhang_ratio;
             O.names_unique = !host_dedupe;
-            chain_pair_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(T, P, O);
-            ++c->launches;
-            CUDA_CHECK(cudaGetLastError());
-            if (host_dedupe) {
-                std::vector<uint8_t> res(n_pairs);
-                std::vector<uint32_t> ps((size_t)n_pairs + 1);
-                std::vector<uint64_t> keys(nA);
-                CUDA_CHECK(cudaMemcpyAsync(res.data(), c->pair_res.p, n_pairs, cudaMemcpyDeviceToHost, c->stream));
-                CUDA_CHECK(cudaMemcpyAsync(ps.data(), c->pstart.p, ((size_t)n_pairs + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-                CUDA_CHECK(cudaMemcpyAsync(keys.data(), c->akey1.p, nA * 8, cudaMemcpyDeviceToHost, c->stream));
+            c->flags.reserve(nA + 1);
+            c->npairs.reserve(16);
+            if (c->chain_v1) {
+                // ---- v1 (debug cross-check, LRGE_CHAIN_V1=1): one thread per (query, target) pair ----
+                c->pstart.reserve((nA + 2) * 4);
+                pair_flag_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), nA, PB + 1, c->flags.as<uint8_t>());
+                cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
+                                           c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+                cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                           c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+                c->launches += 2;
+                uint32_t n_pairs = 0;
+                CUDA_CHECK(cudaMemcpyAsync(&n_pairs, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
                 CUDA_CHECK(cudaStreamSynchronize(c->stream));
-                for (uint32_t i = 0; i < n_pairs; ++i) if (res[i] & 2) {
-                    const uint64_t kk = keys[ps[i]];
-                    const uint32_t rid = (uint32_t)((kk >> (PB + 1)) & ((1ull << RB) - 1)), qid = q0 + (uint32_t)(kk >> (PB + 1 + RB));
-                    dedupe_sets[qid].push_back(rank_idx[rid]);
+                const uint32_t sentinel = (uint32_t)nA;
+                CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_pairs, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
+                S.ms_sort += tm.stop();
+                S.n_pairs += n_pairs;
+                tm.start();
+                c->f.reserve(nA * 4); c->p.reserve(nA * 4); c->t.reserve(nA * 4);
+                c->pair_res.reserve((size_t)n_pairs + 1);
+                CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
+                PairTask T{};
+                T.akey = c->akey1.as<uint64_t>(); T.aval = c->aval1.as<uint32_t>(); T.pstart = c->pstart.as<uint32_t>();
+                T.n_pairs = n_pairs; T.PB = PB; T.RB = RB; T.q0 = q0;
+                T.f = c->f.as<int32_t>(); T.p = c->p.as<int32_t>(); T.t = c->t.as<int32_t>();
+                O.pair_res = c->pair_res.as<uint8_t>();
+                Timer tk(c->stream);
+                tk.start();
+                chain_pair_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(T, P, O);
+                ++c->launches;
+                S.ms_chain_kernel += tk.stop();
+                CUDA_CHECK(cudaGetLastError());
+                if (host_dedupe) {
+                    std::vector<uint8_t> res(n_pairs);
+                    std::vector<uint32_t> ps((size_t)n_pairs + 1);
+                    std::vector<uint64_t> keys(nA);
+                    CUDA_CHECK(cudaMemcpyAsync(res.data(), c->pair_res.p, n_pairs, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaMemcpyAsync(ps.data(), c->pstart.p, ((size_t)n_pairs + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaMemcpyAsync(keys.data(), c->akey1.p, nA * 8, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                    for (uint32_t i = 0; i < n_pairs; ++i) if (res[i] & 2) {
+                        const uint64_t kk = keys[ps[i]];
+                        const uint32_t rid = (uint32_t)((kk >> (PB + 1)) & ((1ull << RB) - 1)), qid = q0 + (uint32_t)(kk >> (PB + 1 + RB));
+                        dedupe_sets[qid].push_back(rank_idx[rid]);
+                    }
+                }
+            } else {
+                // ---- v2: one warp per (query, target, strand) group --------------------------------------
+                c->anc.reserve(nA * 8);
+                c->pstart.reserve((nA + 2) * 4);
+                group_mark_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), c->aval1.as<uint32_t>(), nA, PB,
+                                                                                       c->anc.as<uint2>(), c->flags.as<uint8_t>());
+                cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
+                                           c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+                cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                           c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+                c->launches += 2;
+                uint32_t n_groups = 0;
+                CUDA_CHECK(cudaMemcpyAsync(&n_groups, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                const uint32_t sentinel = (uint32_t)nA;
+                CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_groups, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
+                c->glist.reserve((size_t)n_groups * 16 + 16);
+                c->gmeta.reserve(64);
+                c->pflag.reserve((size_t)n_groups * 4 + 4);
+                CUDA_CHECK(cudaMemsetAsync(c->gmeta.p, 0, 64, c->stream));
+                CUDA_CHECK(cudaMemsetAsync(c->pflag.p, 0, (size_t)n_groups * 4 + 4, c->stream));
+                group_classify_kernel<<<(n_groups + 255) / 256, 256, 0, c->stream>>>(c->pstart.as<uint32_t>(), n_groups, P.min_cnt, P.min_sc,
+                                                                                    o.is_hpc ? 255 : o.k, c->glist.as<uint32_t>(),
+                                                                                    c->gmeta.as<uint32_t>());
+                ++c->launches;
+                S.ms_sort += tm.stop();
+                S.n_pairs += n_groups;
+                tm.start();
+                c->fp.reserve(nA * 8); c->t.reserve(nA * 4);
+                CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
+                GroupTask T{};
+                T.anc = c->anc.as<uint2>(); T.akey = c->akey1.as<uint64_t>(); T.gstart = c->pstart.as<uint32_t>();
+                T.glist = c->glist.as<uint32_t>(); T.gcount = c->gmeta.as<uint32_t>(); T.n_groups = n_groups;
+                T.work_ctr = c->gmeta.as<uint32_t>() + 8;
+                T.fp = c->fp.as<int2>(); T.t = c->t.as<int32_t>(); T.pflag = c->pflag.as<uint32_t>();
+                T.PB = PB; T.RB = RB; T.q0 = q0;
+                Timer tk(c->stream);
+                tk.start();
+                chain_group_kernel<<<148 * (2048 / CG_THREADS), CG_THREADS, 0, c->stream>>>(T, P, O);
+                ++c->launches;
+                S.ms_chain_kernel += tk.stop();
+                CUDA_CHECK(cudaGetLastError());
+                if (host_dedupe) {
+                    std::vector<uint32_t> pf(n_groups), gs((size_t)n_groups + 1);
+                    std::vector<uint64_t> keys(nA);
+                    CUDA_CHECK(cudaMemcpyAsync(pf.data(), c->pflag.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaMemcpyAsync(gs.data(), c->pstart.p, ((size_t)n_groups + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaMemcpyAsync(keys.data(), c->akey1.p, nA * 8, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                    for (uint32_t g = 0; g < n_groups; ++g) if (pf[g]) {
+                        const uint64_t kk = keys[gs[g]];
+                        const uint32_t rid = (uint32_t)((kk >> (PB + 1)) & ((1ull << RB) - 1)), qid = q0 + (uint32_t)(kk >> (PB + 1 + RB));
+                        dedupe_sets[qid].push_back(rank_idx[rid]);
+                    }
                 }
             }
             S.ms_chain += tm.stop();
         }
         q0 = q1;
+    }
+
+    // one exchange on the query path: sum the per-read counts of all target shards over NVLink
+    if (c->comm && K.shard_count > 1) {
+        tm.start();
+        if (K.shard_count != (uint32_t)c->world || K.shard_index != (uint32_t)c->rank)
+            throw std::runtime_error("shard_index/shard_count do not match the communicator");
+        ncclResult_t r1 = ncclAllReduce(c->counts.p, c->counts.p, n_counts, ncclUint32, ncclSum, c->comm, c->stream);
+        ncclResult_t r2 = ncclAllReduce(c->had.p, c->had.p, str->n, ncclUint8, ncclMax, c->comm, c->stream);
+        if (r1 != ncclSuccess || r2 != ncclSuccess) throw NcclError(std::string("ncclAllReduce: ") + ncclGetErrorString(r1 != ncclSuccess ? r1 : r2));
+        S.ms_comm = tm.stop();
     }
 
     // results
@@ -589,6 +678,7 @@ template <typename Fn> int guarded(lrge_ctx *ctx, Fn fn) {
         fn();
         return LRGE_OK;
     } catch (const CudaError &e) { ctx->err = e.what(); cudaGetLastError(); return LRGE_ERR_CUDA; }
+    catch (const NcclError &e) { ctx->err = e.what(); return LRGE_ERR_NCCL; }
     catch (const std::domain_error &e) { ctx->err = e.what(); return LRGE_ERR_DUPLICATE_READ_ID; }
     catch (const std::invalid_argument &e) { ctx->err = e.what(); return LRGE_ERR_MAP; }
     catch (const std::length_error &e) { ctx->err = e.what(); return LRGE_ERR_UNSUPPORTED; }
@@ -633,6 +723,7 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         CUDA_CHECK(cudaSetDevice(device));
         std::unique_ptr<lrge_ctx> c(new lrge_ctx());
         c->device = device;
+        { const char *e = getenv("LRGE_CHAIN_V1"); c->chain_v1 = e && e[0] == '1'; }
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaMemcpyToSymbol(c_nt4, kNt4, 256));
         *out = c.release();
@@ -643,6 +734,7 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
 void lrge_gpu_destroy(lrge_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     delete ctx;
 }
@@ -707,6 +799,27 @@ int lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *o
         if (stats) stats->ms_h2d = ms;
         run_overlap(ctx, &sR, &sR, MODE_AVA, *opts, counts, nullptr, stats);
         if (stats) stats->ms_total += ms;
+    });
+}
+
+int lrge_gpu_comm_unique_id(uint8_t *out, size_t size) {
+    if (!out || size < sizeof(ncclUniqueId)) return LRGE_ERR_INVALID_ARG;
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return LRGE_ERR_NCCL;
+    memset(out, 0, size);
+    memcpy(out, &id, sizeof id);
+    return LRGE_OK;
+}
+
+int lrge_gpu_comm_init(lrge_ctx *ctx, int rank, int world, const uint8_t *unique_id, size_t size) {
+    if (!unique_id || size < sizeof(ncclUniqueId) || world < 1 || rank < 0 || rank >= world) return LRGE_ERR_INVALID_ARG;
+    return guarded(ctx, [&] {
+        if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+        ncclUniqueId id;
+        memcpy(&id, unique_id, sizeof id);
+        ncclResult_t r = ncclCommInitRank(&ctx->comm, world, id, rank);
+        if (r != ncclSuccess) { ctx->comm = nullptr; throw NcclError(std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); }
+        ctx->rank = rank; ctx->world = world;
     });
 }
 

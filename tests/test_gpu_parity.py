@@ -179,3 +179,17 @@ def test_strategy_estimates_match_oracle(ctx):
     assert (r.lower, r.estimate, r.upper) == (lo, md, up)
     assert r.no_mapping_count == int((had == 0).sum())
     assert abs(r.estimate - 300_000) / 300_000 < 0.5
+
+
+def test_chain_kernels_agree(ctx, monkeypatch):
+    """The warp-per-group chaining kernel against the literal thread-per-pair one (LRGE_CHAIN_V1=1)."""
+    _, platform, T, Q = readsim.make_config("C1", scale=0.5)
+    a = ctx.twoset_counts(T, Q, platform, remove_internal=True)
+    monkeypatch.setenv("LRGE_CHAIN_V1", "1")
+    c1 = lrge_b200.Context(0)
+    try:
+        b = c1.twoset_counts(T, Q, platform, remove_internal=True)
+    finally:
+        c1.close()
+    assert np.array_equal(a.counts, b.counts)
+    assert np.array_equal(a.had_mapping, b.had_mapping)
