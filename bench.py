@@ -222,6 +222,11 @@ def run_ours(args):
             pass
     # ---- CPU baseline: the oracle port on this box's cores, rank 0, N = 1 only ------------------------------
     cpu = None
+    if world > 1 and args.verify:
+        import oracle
+        oc, oh, ost = oracle.twoset_counts(T, Q, platform, threads=os.cpu_count() or 1)
+        cpu = {"verify_only": True, "counts_identical_to_gpu": bool(np.array_equal(oc, last.counts)),
+               "had_mapping_identical": bool(np.array_equal(oh, last.had_mapping))}
     if world == 1 and not args.no_cpu_baseline:
         import oracle
         threads = os.cpu_count() or 1
@@ -272,6 +277,7 @@ def main():
     ap.add_argument("--config", default=WORKLOAD)
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="N > 1: check the reduced counts against the oracle on rank 0")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     need = [os.path.join(ROOT, "lrge_b200", "csrc", "liblrge_b200.so"), os.path.join(ROOT, "lrge_b200", "csrc", "libreadsim.so"),

@@ -1,0 +1,217 @@
+// lrge_b200.hpp -- C++ host mirror of liblrge's public surface over the C ABI (lrge_b200.h).
+//
+// The reference's host language is Rust; this image has no Rust toolchain, so the host side above the
+// C ABI is C++ with the same names, argument meaning and error behaviour:
+//   lrge::Estimate            trait Estimate              (liblrge/src/estimate.rs:21-78)
+//   lrge::EstimateResult      struct EstimateResult       (estimate.rs:8-17)
+//   lrge::TwoSetStrategy      struct TwoSetStrategy       (twoset.rs:73-99) + twoset::Builder (twoset/builder.rs)
+//   lrge::AvaStrategy         struct AvaStrategy          (ava.rs:66-84)    + ava::Builder    (ava/builder.rs)
+//   lrge::Platform            enum Platform               (lib.rs:163-180)
+//   lrge::LrgeError           enum LrgeError              (error.rs:6-33)
+// The strategies take explicit read sets (what split_fastq / subsample_reads leave in target.fa / query.fa /
+// reads.fa, twoset.rs:157-186, ava.rs:139-156); the random subsampling before the hot path stays with the caller.
+#pragma once
+#include "lrge_b200.h"
+
+#include <cstdint>
+#include <fstream>
+#include <limits>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace lrge {
+
+constexpr float LOWER_QUANTILE = 0.15f;                 // estimate.rs:4
+constexpr float UPPER_QUANTILE = 0.65f;                 // estimate.rs:6
+constexpr size_t DEFAULT_TARGET_NUM_READS = 10000;      // twoset.rs:65
+constexpr size_t DEFAULT_QUERY_NUM_READS = 5000;        // twoset.rs:66
+constexpr size_t DEFAULT_AVA_NUM_READS = 25000;         // ava.rs:62
+
+enum class Platform { PacBio, Nanopore };
+
+struct LrgeError : std::runtime_error {
+    lrge_status code;
+    LrgeError(lrge_status c, const std::string &msg) : std::runtime_error(msg), code(c) {}
+};
+
+inline Platform platform_from_str(std::string s) {      // Platform::from_str (lib.rs:170-180)
+    for (auto &c : s) c = (char)tolower(c);
+    if (s == "pacbio" || s == "pb") return Platform::PacBio;
+    if (s == "nanopore" || s == "ont") return Platform::Nanopore;
+    throw LrgeError(LRGE_ERR_INVALID_PLATFORM, "Invalid platform: " + s);
+}
+
+// Reads in the layout the C ABI takes; owns its storage.
+struct ReadSet {
+    std::vector<uint8_t> bases;
+    std::vector<uint64_t> off{0};
+    std::string names;
+    std::vector<uint32_t> name_off{0};
+
+    uint32_t size() const { return (uint32_t)(off.size() - 1); }
+    uint64_t total_bases() const { return off.back(); }
+    void push(const std::string &name, const std::string &seq) {
+        bases.insert(bases.end(), seq.begin(), seq.end());
+        off.push_back(bases.size());
+        names += name;
+        name_off.push_back((uint32_t)names.size());
+    }
+    lrge_readset view() const {
+        lrge_readset v;
+        v.bases = bases.data(); v.off = off.data(); v.names = names.data(); v.name_off = name_off.data(); v.n = size();
+        return v;
+    }
+    // plain FASTA / FASTQ; the read id is the header up to the first whitespace (io.rs:192-205)
+    static ReadSet from_fastx(const std::string &path) {
+        std::ifstream in(path);
+        if (!in) throw LrgeError(LRGE_ERR_IO, "IO error: cannot open " + path);
+        ReadSet rs;
+        std::string line, name, seq;
+        bool have = false, fastq = false;
+        auto id_of = [](const std::string &h) { size_t e = h.find_first_of(" \t\r", 1); return h.substr(1, e == std::string::npos ? e : e - 1); };
+        while (std::getline(in, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            if (line.empty()) continue;
+            if (!have && line[0] == '@') fastq = true;
+            if (fastq) {
+                if (line[0] != '@') throw LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: " + path);
+                name = id_of(line);
+                std::string plus, qual;
+                if (!std::getline(in, seq) || !std::getline(in, plus) || !std::getline(in, qual))
+                    throw LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: truncated record in " + path);
+                if (!seq.empty() && seq.back() == '\r') seq.pop_back();
+                rs.push(name, seq);
+                have = true;
+            } else if (line[0] == '>') {
+                if (have) rs.push(name, seq);
+                name = id_of(line); seq.clear(); have = true;
+            } else {
+                if (!have) throw LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: " + path);
+                seq += line;
+            }
+        }
+        if (have && !fastq) rs.push(name, seq);
+        return rs;
+    }
+};
+
+struct EstimateResult {                                  // estimate.rs:8-17
+    std::optional<float> lower, estimate, upper;
+    uint32_t no_mapping_count = 0;
+};
+
+// One GPU context per process (lrge_ctx).
+class Context {
+  public:
+    explicit Context(int device = 0) {
+        const int rc = lrge_gpu_create(device, &h_);
+        if (rc != LRGE_OK) throw LrgeError((lrge_status)rc, lrge_gpu_last_error(nullptr));
+    }
+    ~Context() { lrge_gpu_destroy(h_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    lrge_ctx *get() const { return h_; }
+    void check(int rc) const { if (rc != LRGE_OK) throw LrgeError((lrge_status)rc, lrge_gpu_last_error(h_)); }
+
+  private:
+    lrge_ctx *h_ = nullptr;
+};
+
+// trait Estimate (estimate.rs:21-78)
+class Estimate {
+  public:
+    virtual ~Estimate() = default;
+    virtual std::pair<std::vector<float>, uint32_t> generate_estimates() = 0;
+    EstimateResult estimate(bool finite, std::optional<float> lower_quant, std::optional<float> upper_quant) {
+        auto [estimates, no_mapping_count] = generate_estimates();
+        float lo = 0, md = 0, up = 0;
+        const int m = lrge_estimate(estimates.data(), estimates.size(), finite ? 1 : 0, lower_quant.value_or(-1.0f),
+                                    upper_quant.value_or(-1.0f), &lo, &md, &up);
+        if (m < 0) throw std::invalid_argument("Quantile must be between 0.0 and 1.0");   // estimate.rs:118-120 panics
+        EstimateResult r;
+        if (m & 1) r.lower = lo;
+        if (m & 2) r.estimate = md;
+        if (m & 4) r.upper = up;
+        r.no_mapping_count = no_mapping_count;
+        return r;
+    }
+};
+
+class TwoSetStrategy : public Estimate {
+  public:
+    class Builder {                                      // twoset/builder.rs:22-39 defaults
+      public:
+        Builder &remove_internal(bool b) { o_.remove_internal = b; return *this; }
+        Builder &max_overhang_ratio(float r) { o_.max_overhang_ratio = r; return *this; }
+        Builder &use_min_ref(bool b) { o_.use_min_ref = b; return *this; }
+        Builder &platform(Platform p) { o_.platform = p == Platform::PacBio ? LRGE_PLATFORM_PACBIO : LRGE_PLATFORM_NANOPORE; return *this; }
+        Builder &device(int d) { device_ = d; return *this; }
+        TwoSetStrategy build(ReadSet target, ReadSet query) const { return TwoSetStrategy(std::move(target), std::move(query), o_, device_); }
+        Builder() { lrge_opts_default(&o_); }
+
+      private:
+        lrge_opts o_;
+        int device_ = 0;
+    };
+    TwoSetStrategy(ReadSet target, ReadSet query) : TwoSetStrategy(Builder().build(std::move(target), std::move(query))) {}
+    size_t target_num_reads() const { return target_.size(); }
+    size_t query_num_reads() const { return query_.size(); }
+    const lrge_stats &stats() const { return stats_; }
+
+    std::pair<std::vector<float>, uint32_t> generate_estimates() override {    // twoset.rs:587-606
+        Context ctx(device_);
+        std::vector<float> est(query_.size());
+        uint32_t no_mapping = 0;
+        const lrge_readset t = target_.view(), q = query_.view();
+        ctx.check(lrge_twoset_generate_estimates(ctx.get(), &t, &q, &opts_, est.data(), &no_mapping, &stats_));
+        return {std::move(est), no_mapping};
+    }
+
+  private:
+    TwoSetStrategy(ReadSet t, ReadSet q, lrge_opts o, int device) : target_(std::move(t)), query_(std::move(q)), opts_(o), device_(device) {}
+    ReadSet target_, query_;
+    lrge_opts opts_;
+    int device_;
+    lrge_stats stats_{};
+};
+
+class AvaStrategy : public Estimate {
+  public:
+    class Builder {                                      // ava/builder.rs:18-32 defaults
+      public:
+        Builder &remove_internal(bool b) { o_.remove_internal = b; return *this; }
+        Builder &max_overhang_ratio(float r) { o_.max_overhang_ratio = r; return *this; }
+        Builder &platform(Platform p) { o_.platform = p == Platform::PacBio ? LRGE_PLATFORM_PACBIO : LRGE_PLATFORM_NANOPORE; return *this; }
+        Builder &device(int d) { device_ = d; return *this; }
+        AvaStrategy build(ReadSet reads) const { return AvaStrategy(std::move(reads), o_, device_); }
+        Builder() { lrge_opts_default(&o_); }
+
+      private:
+        lrge_opts o_;
+        int device_ = 0;
+    };
+    explicit AvaStrategy(ReadSet reads) : AvaStrategy(Builder().build(std::move(reads))) {}
+    size_t num_reads() const { return reads_.size(); }
+    const lrge_stats &stats() const { return stats_; }
+
+    std::pair<std::vector<float>, uint32_t> generate_estimates() override {    // ava.rs:369-381
+        Context ctx(device_);
+        std::vector<float> est(reads_.size());
+        uint32_t no_mapping = 0;
+        const lrge_readset r = reads_.view();
+        ctx.check(lrge_ava_generate_estimates(ctx.get(), &r, &opts_, est.data(), &no_mapping, &stats_));
+        return {std::move(est), no_mapping};
+    }
+
+  private:
+    AvaStrategy(ReadSet r, lrge_opts o, int device) : reads_(std::move(r)), opts_(o), device_(device) {}
+    ReadSet reads_;
+    lrge_opts opts_;
+    int device_;
+    lrge_stats stats_{};
+};
+
+}  // namespace lrge

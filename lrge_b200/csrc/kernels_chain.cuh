@@ -279,14 +279,14 @@ __device__ __forceinline__ int32_t comput_sc_smem(int32_t ri, int32_t qi, int32_
 // mg_lchain_dp for one group, warp-cooperative
 __device__ void warp_group_dp(const uint2 *__restrict__ anc, int32_t n, const ChainParams &P, const uint8_t *s_pen,
                               int2 *fp, int32_t *t, uint32_t lane) {
-    int32_t st = 0, max_ii = -1, r_maxii = 0, f_maxii = 0;
+    int32_t st = 0, r_st = n > 0 ? (int32_t)anc[0].x : 0, max_ii = -1, r_maxii = 0, f_maxii = 0;
     const uint32_t le_mask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1);
     for (int32_t i = 0; i < n; ++i) {
         const uint2 ai = anc[i];
         const int32_t ri = (int32_t)ai.x, qi = (int32_t)(ai.y & 0xffffff);
         int32_t max_f = (int32_t)(ai.y >> 24), max_j = -1, n_skip = 0;
-        while (st < i && ri > (int32_t)anc[st].x + P.max_dist_x) ++st;
-        if (i - st > P.max_iter) st = i - P.max_iter;
+        while (st < i && ri > r_st + P.max_dist_x) r_st = (int32_t)anc[++st].x;
+        if (i - st > P.max_iter) { st = i - P.max_iter; r_st = (int32_t)anc[st].x; }
         int32_t end_j = st - 1;
         for (int32_t base = i - 1; base >= st; base -= 32) {
             const int32_t j = base - (int32_t)lane;
@@ -301,25 +301,41 @@ __device__ void warp_group_dp(const uint2 *__restrict__ anc, int32_t n, const Ch
                 }
             }
             const bool scored = s != INT32_MIN;
-            if (scored && pj >= 0) t[pj] = i;
+            if (pj >= 0) t[pj] = i;
             __syncwarp();
             const int32_t tj = scored ? t[j] : -1;
-            const int32_t incl = warp_prefix_max_incl(s, lane);
-            int32_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
-            if (lane == 0) excl = INT32_MIN;
-            excl = max(excl, max_f);
-            const bool improved = scored && s > excl;
+            // improved lanes: s exceeds max_f and every earlier lane's s.  Candidates are the lanes above the
+            // incoming max_f; walk them in lane order (usually one).
+            uint32_t I = 0;
+            {
+                uint32_t C = __ballot_sync(0xffffffffu, scored && s > max_f);
+                while (C) {
+                    const int c = __ffs(C) - 1;
+                    I |= 1u << c;
+                    const int32_t m = __shfl_sync(0xffffffffu, s, c);
+                    C = __ballot_sync(0xffffffffu, scored && s > m) & ~((2u << c) - 1u) & (c == 31 ? 0u : 0xffffffffu);
+                }
+            }
+            const bool improved = (I >> lane) & 1;
             const bool marked = scored && !improved && tj == i;
-            const uint32_t I = __ballot_sync(0xffffffffu, improved), M = __ballot_sync(0xffffffffu, marked);
+            const uint32_t M = __ballot_sync(0xffffffffu, marked);
             uint32_t keep = 0xffffffffu;
             int32_t brk_lane = -1;
             if (M) {
-                const int32_t N = n_skip + __popc(M & le_mask) - __popc(I & le_mask);
-                const int32_t mn = min(0, warp_prefix_min_incl(N, lane));
-                const int32_t nl = N - mn;
+                int32_t nl;
+                if (I == 0 || (31 - __clz(I)) < (__ffs(M) - 1)) {
+                    // every improvement precedes every mark: decrements first (floored), then pure increments
+                    const int32_t n1 = max(0, n_skip - __popc(I));
+                    nl = n1 + __popc(M & le_mask);
+                    n_skip = n1 + __popc(M);
+                } else {
+                    const int32_t N = n_skip + __popc(M & le_mask) - __popc(I & le_mask);
+                    const int32_t mn = min(0, warp_prefix_min_incl(N, lane));
+                    nl = N - mn;
+                    n_skip = __shfl_sync(0xffffffffu, nl, 31);
+                }
                 const uint32_t B = __ballot_sync(0xffffffffu, marked && nl > P.max_skip);
                 if (B) { brk_lane = __ffs(B) - 1; keep = (1u << brk_lane) - 1; }
-                n_skip = __shfl_sync(0xffffffffu, nl, 31);
             } else {
                 n_skip = max(0, n_skip - __popc(I));
             }
@@ -357,45 +373,88 @@ __device__ void warp_group_dp(const uint2 *__restrict__ anc, int32_t n, const Ch
     }
 }
 
+// Warp argmax of (f, index) over the group among entries with f >= min_sc, strictly below (last_f, last_i) in
+// (f, index) order and, if use_t, not yet used (t == 0).
+__device__ __forceinline__ void warp_next_start(int32_t n, const ChainParams &P, const int2 *fp, const int32_t *t, bool use_t,
+                                                int32_t last_f, int32_t last_i, uint32_t lane, int32_t &bf, int32_t &bi) {
+    bf = INT32_MIN, bi = -1;
+    for (int32_t i = lane; i < n; i += 32) {
+        const int32_t fi = fp[i].x;
+        if (fi < P.min_sc) continue;
+        if (fi > last_f || (fi == last_f && i >= last_i)) continue;
+        if (use_t && t[i] != 0) continue;
+        if (fi > bf || (fi == bf && i > bi)) bf = fi, bi = i;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int32_t of = __shfl_xor_sync(0xffffffffu, bf, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || of > bf || (of == bf && oi > bi))) bf = of, bi = oi;
+    }
+}
+
 // mg_chain_backtrack for one group: chain starts are visited from the highest (f, index) down; the search for
 // the next start is warp-parallel, the walk itself is done by lane 0.  Calls on_chain (all lanes, uniform
 // arguments) for every kept chain until it returns true.
+// The first start is walked without touching t[] (nothing is used yet, so mg_chain_bk_end's "t[i] == 0" test is
+// always true); if its chain settles the question -- the common case for counting -- no mark is ever written.
 template <typename F>
 __device__ void warp_group_backtrack(int32_t n, const ChainParams &P, const int2 *fp, int32_t *t, uint32_t lane, F on_chain) {
+    int32_t bf, bi;
+    warp_next_start(n, P, fp, t, false, INT32_MAX, n, lane, bf, bi);
+    if (bi < 0) return;
+    int32_t cnt = 0, first = bi, sc = 0, end_i = -1;
+    if (lane == 0) {
+        // mg_chain_bk_end on untouched marks: find max_i, counting the anchors above it on the way
+        int32_t i = bi, max_i = bi, max_s = 0, steps = 0, prev = bi;
+        do {
+            const int32_t cur = i;
+            i = fp[i].y;
+            ++steps;
+            const int32_t s = i < 0 ? bf : bf - fp[i].x;
+            if (s > max_s) { max_s = s; max_i = i; cnt = steps; first = cur; }
+            else if (max_s - s > P.bw) break;
+            prev = cur;
+        } while (i >= 0);
+        (void)prev;
+        end_i = max_i;
+        sc = end_i < 0 ? bf : bf - fp[end_i].x;
+        if (end_i == bi) { cnt = 0; sc = 0; }
+    }
+    cnt = __shfl_sync(0xffffffffu, cnt, 0); first = __shfl_sync(0xffffffffu, first, 0);
+    sc = __shfl_sync(0xffffffffu, sc, 0); end_i = __shfl_sync(0xffffffffu, end_i, 0);
+    if (sc >= P.min_sc && cnt > 0 && cnt >= P.min_cnt) {
+        ChainCoord c; c.a_first = first; c.a_last = bi; c.sc = sc; c.cnt = cnt;
+        if (on_chain(c)) return;
+    }
+    // general path: marks are needed from here on
     for (int32_t i = lane; i < n; i += 32) t[i] = 0;
     __syncwarp();
-    int32_t last_f = INT32_MAX, last_i = n;
+    if (lane == 0) for (int32_t i = bi; i != end_i; i = fp[i].y) t[i] = 1;
+    __syncwarp();
+    int32_t last_f = bf, last_i = bi;
     for (;;) {
-        int32_t bf = INT32_MIN, bi = -1;
-        for (int32_t i = lane; i < n; i += 32) {
-            const int32_t fi = fp[i].x;
-            if (fi < P.min_sc || t[i] != 0) continue;
-            if (fi > last_f || (fi == last_f && i >= last_i)) continue;
-            if (fi > bf || (fi == bf && i > bi)) bf = fi, bi = i;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int32_t of = __shfl_xor_sync(0xffffffffu, bf, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (oi >= 0 && (bi < 0 || of > bf || (of == bf && oi > bi))) bf = of, bi = oi;
-        }
+        warp_next_start(n, P, fp, t, true, last_f, last_i, lane, bf, bi);
         if (bi < 0) break;
         last_f = bf, last_i = bi;
-        int32_t cnt = 0, first = bi, sc = 0;
+        cnt = 0, first = bi, sc = 0;
         if (lane == 0) {
             // mg_chain_bk_end
-            int32_t i = bi, end_i = -1, max_i = bi, max_s = 0;
+            int32_t i = bi, stop_i = -1, max_i = bi, max_s = 0;
             do {
                 int32_t s;
                 t[i] = 2;
-                end_i = i = fp[i].y;
+                stop_i = i = fp[i].y;
                 s = i < 0 ? bf : bf - fp[i].x;
                 if (s > max_s) max_s = s, max_i = i;
                 else if (max_s - s > P.bw) break;
             } while (i >= 0 && t[i] == 0);
-            for (i = bi; i >= 0 && i != end_i; i = fp[i].y) t[i] = 0;
-            end_i = max_i;
-            for (i = bi; i != end_i; i = fp[i].y) { ++cnt; t[i] = 1; first = i; }
-            sc = i < 0 ? bf : bf - fp[i].x;
+            // one pass: anchors above max_i join the chain (t = 1), the rest of the walked path is released
+            bool in_chain = max_i != bi;
+            for (i = bi; i >= 0 && i != stop_i; i = fp[i].y) {
+                if (i == max_i) in_chain = false;
+                if (in_chain) { ++cnt; t[i] = 1; first = i; } else t[i] = 0;
+            }
+            sc = max_i == bi ? 0 : (max_i < 0 ? bf : bf - fp[max_i].x);
         }
         __syncwarp();
         cnt = __shfl_sync(0xffffffffu, cnt, 0); first = __shfl_sync(0xffffffffu, first, 0); sc = __shfl_sync(0xffffffffu, sc, 0);

@@ -32,6 +32,7 @@ class Opt(ctypes.Structure):
         ("min_mid_occ", ctypes.c_int32), ("max_mid_occ", ctypes.c_int32), ("mid_occ", ctypes.c_int32),
         ("max_occ", ctypes.c_int32), ("occ_dist", ctypes.c_int32), ("max_max_occ", ctypes.c_int32),
         ("seed", ctypes.c_int32), ("tie_mode", ctypes.c_int32),
+        ("shard_index", ctypes.c_int32), ("shard_count", ctypes.c_int32),
     ]
 
 
@@ -208,8 +209,10 @@ def is_internal(qlen, qs, qe, rev, tlen, ts, te, ratio) -> bool:
     return bool(lib().orc_is_internal(qlen, qs, qe, int(rev), tlen, ts, te, ratio))
 
 
-def twoset_counts(T, Q, platform="ont", remove_internal=False, max_overhang_ratio=0.2, threads=1, tie_mode=TIE_KSORT):
+def twoset_counts(T, Q, platform="ont", remove_internal=False, max_overhang_ratio=0.2, threads=1, tie_mode=TIE_KSORT,
+                  shard_index=0, shard_count=1):
     opt = options(platform, dual=True, tie_mode=tie_mode)
+    opt.shard_index, opt.shard_count = shard_index, shard_count
     counts = np.zeros(Q.n, dtype=np.uint32)
     had = np.zeros(Q.n, dtype=np.uint8)
     st = Stats()
