@@ -82,6 +82,7 @@ struct IndexView {
     const uint32_t *boff;
     uint64_t M;
     int shift;               // bucket = tx >> shift  (shift = 8 + 2k - bits)
+    const uint32_t *bl;      // sharded index only: bit i set = the run starting at i occurs > mid_occ times GLOBALLY
 };
 
 // mm_idx_get, bounded: returns the start of the run of `key` and its length capped at cap+1
@@ -100,6 +101,78 @@ __device__ __forceinline__ uint32_t index_lookup(const IndexView &I, uint64_t ke
     const uint64_t lim = (uint64_t)lo + cap + 1 < I.M ? (uint64_t)lo + cap + 1 : I.M;
     while ((uint64_t)lo + n < lim && (I.tx[lo + n] >> 8) == key) ++n;
     return n;
+}
+
+// mark the local runs of blacklisted keys (entries equal to ~0 are padding)
+__global__ void bl_mark_kernel(const uint64_t *__restrict__ keys, uint64_t n, IndexView I, uint32_t *__restrict__ bitmap) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    if (key == ~0ull) return;
+    uint32_t start;
+    if (index_lookup(I, key, 0, &start)) atomicOr(&bitmap[start >> 5], 1u << (start & 31));
+}
+
+// ---- sharded index: exact global occurrence counts across target shards ------------------------------------
+// Every rank holds the sorted minimizers of ITS targets.  Distinct keys with their local counts are sent to the
+// rank owning the key range (owner = key * W >> 2k), summed there, histogrammed (all-reduced -> the same mid_occ
+// everywhere); keys above mid_occ come back as a blacklist that each rank marks in a bitmap over its own runs.
+
+__global__ void run_flag_kernel(const uint64_t *__restrict__ tx, uint64_t M, int rshift, uint8_t *__restrict__ flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    flags[i] = (i == 0 || (tx[i] >> rshift) != (tx[i - 1] >> rshift)) ? 1 : 0;
+}
+
+// one thread per run: key and run length; starts[U] must hold M
+__global__ void rle_emit_kernel(const uint64_t *__restrict__ tx, const uint32_t *__restrict__ starts, uint32_t U,
+                                uint64_t *__restrict__ ukey, uint32_t *__restrict__ ucnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= U) return;
+    ukey[i] = tx[starts[i]] >> 8;
+    ucnt[i] = starts[i + 1] - starts[i];
+}
+
+// bounds[d] = first run whose key belongs to owner >= d, d in [0, W]
+__global__ void owner_bounds_kernel(const uint64_t *__restrict__ ukey, uint32_t U, int W, int kbits, unsigned long long *bounds) {
+    const int d = threadIdx.x;
+    if (d > W) return;
+    const uint64_t first = d == W ? ~0ull : (((uint64_t)d << kbits) + W - 1) / (uint64_t)W;
+    uint32_t lo = 0, hi = U;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ukey[mid] < first) lo = mid + 1; else hi = mid; }
+    bounds[d] = d == W ? U : lo;
+}
+
+// owner side: received (key, count) sorted by key; one thread per distinct key sums the <= W partial counts
+__global__ void owner_sum_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ scnt, const uint32_t *__restrict__ starts,
+                                 uint32_t G, uint32_t *__restrict__ gcnt, unsigned long long *hist) {
+    __shared__ unsigned int sh[OCC_BINS];
+    for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+        uint64_t n = 0;
+        for (uint32_t j = starts[g]; j < starts[g + 1]; ++j) n += scnt[j];
+        gcnt[g] = n > 0xffffffffull ? 0xffffffffu : (uint32_t)n;
+        atomicAdd(&sh[n < OCC_BINS - 1 ? n : OCC_BINS - 1], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// owner side: keys occurring more than mid_occ times -> blacklist (unordered), and overflow-bin values if asked
+__global__ void owner_select_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ gcnt,
+                                    uint32_t G, uint32_t thr, uint64_t *__restrict__ out, unsigned long long *n_out, uint64_t cap) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G || gcnt[g] <= thr) return;
+    const unsigned long long slot = atomicAdd(n_out, 1ull);
+    if (slot < cap) out[slot] = skey[starts[g]];
+}
+__global__ void owner_overflow_kernel(const uint32_t *__restrict__ gcnt, uint32_t G, uint32_t *__restrict__ out, unsigned long long *n_out, uint64_t cap) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G || gcnt[g] < OCC_BINS - 1) return;
+    const unsigned long long slot = atomicAdd(n_out, 1ull);
+    if (slot < cap) out[slot] = gcnt[g];
 }
 
 }  // namespace lrge

@@ -72,6 +72,7 @@ __global__ void seed_count_kernel(const uint64_t *__restrict__ qx, const uint64_
         const uint64_t x = qx[i];
         n = index_lookup(I, x >> 8, (uint32_t)mid_occ, &start);
         if (n > (uint32_t)mid_occ) n = 0;                     // m[i].flt = 1 (seed.c mm_collect_matches)
+        if (n && I.bl && ((I.bl[start >> 5] >> (start & 31)) & 1)) n = 0;   // > mid_occ over all target shards
         if (n) {
             if (S.check_names || S.shard_count > 1) {
                 const uint64_t y = qy[i];

@@ -15,6 +15,7 @@
 // "symmetric k-mer" skip of mm_sketch cannot occur.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 namespace lrge {
 
@@ -29,7 +30,8 @@ __constant__ uint8_t c_nt4[256];
 
 struct ReadLayout {
     const uint8_t  *asc;       // ASCII bases (HPC: run-compressed ASCII)
-    const uint64_t *off;       // n+1 offsets into asc
+    const uint64_t *off;       // n   start offset of each entry in asc
+    const uint32_t *rid_map;   // n   read id of each entry (NULL: entry index = read id); a rank sketches a subset of reads
     const uint64_t *poff;      // n   padded start (bases), multiple of PAD_BASES, >= PAD_BASES
     const uint32_t *len;       // n   number of steps (HPC: compressed length)
     const uint32_t *tile_off;  // n+1 tiles before read r (tiles computed from the uncompressed length)
@@ -92,13 +94,13 @@ __global__ void __launch_bounds__(SK_THREADS) pack_kernel(ReadLayout L) {
 // One warp per read.  Step = a run of equal unambiguous bases, or a single ambiguous base
 // (sketch.c: the HPC branch of mm_sketch). Emits the run base as ASCII, the position of the run's last
 // base, and the number of steps.
-__global__ void __launch_bounds__(256) hpc_compress_kernel(const uint8_t *asc, const uint64_t *off, uint32_t n,
+__global__ void __launch_bounds__(256) hpc_compress_kernel(const uint8_t *asc, const uint64_t *off, const uint32_t *len0, uint32_t n,
                                                            uint8_t *casc, uint32_t *cend, uint32_t *clen) {
     const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= n) return;
     const uint32_t lane = lane_id();
     const uint64_t o = off[r];
-    const uint32_t len = (uint32_t)(off[r + 1] - o);
+    const uint32_t len = len0[r];
     const char kAsc[5] = {'A', 'C', 'G', 'T', 'N'};
     uint32_t count = 0;
     for (uint32_t c0 = 0; c0 < len; c0 += 32) {
@@ -131,9 +133,9 @@ __device__ __forceinline__ uint64_t hash64_masked(uint64_t key, uint64_t mask) {
     return key;
 }
 
-template <int W>
-__device__ __forceinline__ uint64_t pick_x(const uint64_t (&xs)[W + 1], int d) {
-    uint64_t v = xs[0];
+template <int W, typename XT>
+__device__ __forceinline__ XT pick_x(const XT (&xs)[W + 1], int d) {
+    XT v = xs[0];
 #pragma unroll
     for (int i = 1; i <= W; ++i) v = d == i ? xs[i] : v;
     return v;
@@ -148,9 +150,13 @@ struct SketchArgs {
     int k;
 };
 
-template <bool HPC, bool EMIT>
+// X32: without HPC the span byte is the constant k, so windows compare the 2k <= 31 bit hash alone (32-bit lanes).
+template <bool HPC, bool EMIT, bool X32>
 __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
+    static_assert(!(HPC && X32), "HPC spans vary: 64-bit compare");
     constexpr int W = MAXW;
+    using XT = typename std::conditional<X32, uint32_t, uint64_t>::type;
+    constexpr XT XMAX = (XT)~(XT)0;
     __shared__ alignas(16) uint64_t sW[TILE_WORDS + 4];
     __shared__ alignas(16) uint32_t sN[TILE_WORDS + 4];
     __shared__ alignas(8) uint64_t bar;
@@ -187,8 +193,9 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
     const int LW = W + k;                                      // l is only compared with k, w+k-1, w+k
     const uint32_t lw_mask = LW >= 32 ? 0xffffffffu : ((1u << LW) - 1);
     const uint64_t rbase = L.off[r];
+    const uint32_t rid = L.rid_map ? L.rid_map[r] : r;
 
-    uint64_t xprev = U64MAX;
+    XT xprev = XMAX;
     uint32_t zprev = 0;
     uint32_t total = 0;
     uint32_t obase = EMIT ? A.woff[tile * (SK_THREADS / 32) + warp] : 0;
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
         const int64_t p = ws + 32 * (c - 1) + lane;            // step handled by this lane
         if (ws + 32 * (int64_t)(c - 1) >= len) break;          // warp-uniform
         const int32_t q = (int32_t)(p - s) + PAD_BASES;        // index inside the staged tile (>= 96)
-        uint64_t x = U64MAX;
+        XT x = XMAX;
         uint32_t z = 0;
         int32_t l = 0;
         if (p >= 0 && p < len) {
@@ -225,17 +232,18 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
                     const int64_t e0 = p - k >= 0 ? (int64_t)A.cend[rbase + p - k] : -1;
                     span = (uint32_t)(e1 - e0);
                 }
-                if (span < 256) x = h << 8 | span;
+                if (X32) x = (XT)h;
+                else if (span < 256) x = (XT)(h << 8 | span);
             }
         }
         // infos of steps t-d, d = 0..W, through warp shuffles (previous chunk supplies lanes < d)
-        uint64_t xs[W + 1];
+        XT xs[W + 1];
         xs[0] = x;
 #pragma unroll
         for (int d = 1; d <= W; ++d) {
             const int src = ((int)lane - d) & 31;
-            const uint64_t vc = __shfl_sync(0xffffffffu, x, src);
-            const uint64_t vp = __shfl_sync(0xffffffffu, xprev, src);
+            const XT vc = __shfl_sync(0xffffffffu, x, src);
+            const XT vp = __shfl_sync(0xffffffffu, xprev, src);
             xs[d] = (int)lane - d >= 0 ? vc : vp;
         }
         const uint32_t zb = __ballot_sync(0xffffffffu, z);
@@ -245,28 +253,28 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
         uint32_t cnt = 0;
         if (c > 0 && p < len) {
             // m[t-1]: rightmost minimum of steps t-W .. t-1;  m[t]: of steps t-W+1 .. t
-            uint64_t xm1 = xs[W]; int dm1 = W;
+            XT xm1 = xs[W]; int dm1 = W;
 #pragma unroll
             for (int d = W - 1; d >= 1; --d) if (xs[d] <= xm1) { xm1 = xs[d]; dm1 = d; }
-            uint64_t xm = xs[W - 1]; int dm = W - 1;
+            XT xm = xs[W - 1]; int dm = W - 1;
 #pragma unroll
             for (int d = W - 2; d >= 0; --d) if (xs[d] <= xm) { xm = xs[d]; dm = d; }
-            if (l == W + k - 1 && xm1 != U64MAX) {             // first full window: ties of the old minimum
+            if (l == W + k - 1 && xm1 != XMAX) {             // first full window: ties of the old minimum
 #pragma unroll
                 for (int d = W - 1; d >= 1; --d)
                     if (xs[d] == xm1 && d != dm1) { em |= (uint64_t)d << (4 * cnt); ++cnt; }
             }
             if (x <= xm1) {                                    // new minimum replaces the old one
-                if (l >= W + k && xm1 != U64MAX) { em |= (uint64_t)dm1 << (4 * cnt); ++cnt; }
+                if (l >= W + k && xm1 != XMAX) { em |= (uint64_t)dm1 << (4 * cnt); ++cnt; }
             } else if (dm1 == W) {                             // old minimum left the window
-                if (l >= W + k - 1 && xm1 != U64MAX) { em |= (uint64_t)W << (4 * cnt); ++cnt; }
-                if (l >= W + k - 1 && xm != U64MAX) {
+                if (l >= W + k - 1 && xm1 != XMAX) { em |= (uint64_t)W << (4 * cnt); ++cnt; }
+                if (l >= W + k - 1 && xm != XMAX) {
 #pragma unroll
                     for (int d = W - 1; d >= 0; --d)
                         if (xs[d] == xm && d != dm) { em |= (uint64_t)d << (4 * cnt); ++cnt; }
                 }
             }
-            if (p == len - 1 && xm != U64MAX) { em |= (uint64_t)dm << (4 * cnt); ++cnt; }   // final flush
+            if (p == len - 1 && xm != XMAX) { em |= (uint64_t)dm << (4 * cnt); ++cnt; }   // final flush
         }
         // ordered output: exclusive prefix of cnt over the warp
         uint32_t pre = cnt;
@@ -283,8 +291,9 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
                 const int64_t pt = p - d;
                 const uint64_t zz = (zcomb >> (32 + (int)lane - d)) & 1;
                 const uint64_t pos = HPC ? (uint64_t)A.cend[rbase + pt] : (uint64_t)pt;
-                A.ox[o] = pick_x<W>(xs, d);
-                A.oy[o] = (uint64_t)r << 32 | pos << 1 | zz;
+                const XT xv = pick_x<W, XT>(xs, d);
+                A.ox[o] = X32 ? ((uint64_t)xv << 8 | (uint64_t)k) : (uint64_t)xv;
+                A.oy[o] = (uint64_t)rid << 32 | pos << 1 | zz;
             }
         }
         total += chunk_total;

@@ -132,7 +132,9 @@ struct lrge_ctx {
     std::string err;
     uint32_t launches = 0;
     // layout / sketch scratch
-    DevBuf poff, len, tile_off, w2, nm, wcnt, woff, casc, cend, clen;
+    DevBuf poff, len0, sub_off, rid_map, tile_off, w2, nm, wcnt, woff, casc, cend, clen;
+    // sharded index exchange
+    DevBuf ukey, ucnt, rkey, rcnt, skey, scnt, gcnt, xmeta, blist, blall, blmap;
     DevBuf cub_tmp;
     // index
     Sketch sk_idx, sk_str;
@@ -196,18 +198,24 @@ __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32
     if (i < n) dst[i] = src[idx[i]];
 }
 
-// K0 + K1: sketch a staged read set into `out`
-void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, float *ms_pack, float *ms_sketch) {
-    const uint32_t n = s->n;
-    std::vector<uint64_t> poff(n);
-    std::vector<uint32_t> tile_off(n + 1);
+// K0 + K1: sketch a staged read set (or the reads first, first+stride, ... of it) into `out`
+void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, float *ms_pack, float *ms_sketch,
+                    uint32_t first = 0, uint32_t stride = 1) {
+    const bool subset = stride > 1;
+    const uint32_t n = s->n > first ? (s->n - first + stride - 1) / stride : 0;
+    std::vector<uint64_t> poff(n), soff(n);
+    std::vector<uint32_t> tile_off(n + 1), slen(n), rid_map(n);
     uint64_t pos = PAD_BASES;
     uint32_t tiles = 0;
     for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t r = first + i * stride;
         poff[i] = pos;
         tile_off[i] = tiles;
-        pos += ((uint64_t)s->h_len[i] + PAD_BASES - 1) / PAD_BASES * PAD_BASES;
-        tiles += (s->h_len[i] + TILE_POS - 1) / TILE_POS;
+        soff[i] = s->h_off[r];
+        slen[i] = s->h_len[r];
+        rid_map[i] = r;
+        pos += ((uint64_t)s->h_len[r] + PAD_BASES - 1) / PAD_BASES * PAD_BASES;
+        tiles += (s->h_len[r] + TILE_POS - 1) / TILE_POS;
     }
     tile_off[n] = tiles;
     const uint64_t padded_words = (pos + TILE_POS + 2 * PAD_BASES) / 32 + 8;
@@ -219,7 +227,11 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
     c->nm.reserve(padded_words * 4);
     const uint32_t *len_dev;
     ReadLayout L{};
-    L.off = s->off.as<uint64_t>();
+    h2d(c, c->sub_off, soff.data(), n);
+    h2d(c, c->len0, slen.data(), n);
+    if (subset) h2d(c, c->rid_map, rid_map.data(), n);
+    L.off = c->sub_off.as<uint64_t>();
+    L.rid_map = subset ? c->rid_map.as<uint32_t>() : nullptr;
     L.poff = c->poff.as<uint64_t>();
     L.tile_off = c->tile_off.as<uint32_t>();
     L.w2 = c->w2.as<uint64_t>();
@@ -230,7 +242,7 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         c->cend.reserve((s->total_bases + 1) * 4);
         c->clen.reserve((size_t)std::max(n, 1u) * 4);
         if (n) {
-            hpc_compress_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(s->asc.as<uint8_t>(), s->off.as<uint64_t>(), n,
+            hpc_compress_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(s->asc.as<uint8_t>(), c->sub_off.as<uint64_t>(), c->len0.as<uint32_t>(), n,
                                                                     c->casc.as<uint8_t>(), c->cend.as<uint32_t>(),
                                                                     c->clen.as<uint32_t>());
             ++c->launches;
@@ -238,9 +250,8 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         L.asc = c->casc.as<uint8_t>();
         len_dev = c->clen.as<uint32_t>();
     } else {
-        h2d(c, c->len, s->h_len.data(), n);
         L.asc = s->asc.as<uint8_t>();
-        len_dev = c->len.as<uint32_t>();
+        len_dev = c->len0.as<uint32_t>();
     }
     L.len = len_dev;
     if (tiles) { pack_kernel<<<tiles, SK_THREADS, 0, c->stream>>>(L); ++c->launches; }
@@ -257,8 +268,10 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
     out->moff.reserve(((size_t)n + 1) * 4);
     if (tiles) {
         CUDA_CHECK(cudaMemsetAsync(c->wcnt.p, 0, ((size_t)nw + 1) * 4, c->stream));
-        if (o.is_hpc) sketch_kernel<true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        else sketch_kernel<false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        const bool x32 = !o.is_hpc && 2 * o.k <= 31;
+        if (o.is_hpc) sketch_kernel<true, false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        else if (x32) sketch_kernel<false, false, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        else sketch_kernel<false, false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
         ++c->launches;
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream);
@@ -271,8 +284,9 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         out->x.reserve(((size_t)total + 1) * 8);
         out->y.reserve(((size_t)total + 1) * 8);
         A.ox = out->x.as<uint64_t>(); A.oy = out->y.as<uint64_t>();
-        if (o.is_hpc) sketch_kernel<true, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        else sketch_kernel<false, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        if (o.is_hpc) sketch_kernel<true, true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        else if (x32) sketch_kernel<false, true, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        else sketch_kernel<false, true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
         ++c->launches;
         // per-read minimizer offsets: woff at the first warp sub-tile of every read
         gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), c->tile_off.as<uint32_t>(),
@@ -303,8 +317,9 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
                                         c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
         c->launches += 4;
     }
+    // ~8 entries per bucket: the table (4 B x 2^bits) stays L2-resident, a lookup bisects <= 3 steps
     int bits = 8;
-    while (bits < 2 * o.k && bits < 28 && (1ull << bits) < M) ++bits;
+    while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
     const uint32_t nb = 1u << bits;
     const int shift = 8 + 2 * o.k - bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
@@ -346,7 +361,170 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     if (mid_occ < o.min_mid_occ) mid_occ = o.min_mid_occ;
     if (o.max_mid_occ > o.min_mid_occ && mid_occ > o.max_mid_occ) mid_occ = o.max_mid_occ;
     B.view.tx = c->tx.as<uint64_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
-    B.view.M = M; B.view.shift = shift;
+    B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
+    B.mid_occ = mid_occ; B.n_keys = n_keys;
+    return B;
+}
+
+#define NCCL_CHECK(x) do { ncclResult_t _r = (x); if (_r != ncclSuccess) throw NcclError(std::string(#x) + ": " + ncclGetErrorString(_r)); } while (0)
+
+// K2 + K3 with the index sharded over ranks: `sk` holds the minimizers of THIS rank's targets only.
+// Exact global occurrence counts: distinct local keys (key, count) go to the rank owning their key range,
+// are summed there, the occurrence histogram is all-reduced (=> the same mid_occ on every rank), and the keys
+// above mid_occ come back as a blacklist marked in a bitmap over the local runs.
+BuiltIndex build_index_sharded(lrge_ctx *c, const Sketch &sk, const MapOpt &o, lrge_stats *S) {
+    BuiltIndex B{};
+    const int W = c->world, me = c->rank;
+    const uint64_t M = sk.M;
+    if (M >= (1ull << 32) - 2) throw std::length_error("more than 2^32 target minimizers per GPU are not supported");
+    c->tx.reserve((M + 1) * 8);
+    c->ty.reserve((M + 1) * 8);
+    size_t tb = 0;
+    if (M) {
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
+        cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
+        c->launches += 4;
+    }
+    int bits = 8;
+    while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
+    const uint32_t nb = 1u << bits;
+    const int shift = 8 + 2 * o.k - bits;
+    c->boff.reserve(((size_t)nb + 2) * 4);
+    bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>());
+    ++c->launches;
+
+    // local run-length encoding: (key, count) per distinct local key
+    c->flags.reserve(M + 1);
+    c->pstart.reserve((M + 2) * 4);
+    c->npairs.reserve(16);
+    uint32_t U = 0;
+    if (M) {
+        run_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, 8, c->flags.as<uint8_t>());
+        cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
+                                   c->npairs.as<uint32_t>(), (int64_t)M, c->stream);
+        cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                   c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)M, c->stream);
+        c->launches += 3;
+        CUDA_CHECK(cudaMemcpyAsync(&U, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        const uint32_t sentinel = (uint32_t)M;
+        CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + U, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->ukey.reserve(((size_t)U + 1) * 8);
+    c->ucnt.reserve(((size_t)U + 1) * 4);
+    if (U) { rle_emit_kernel<<<(U + 255) / 256, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), c->pstart.as<uint32_t>(), U, c->ukey.as<uint64_t>(), c->ucnt.as<uint32_t>()); ++c->launches; }
+
+    // who owns what: bounds[W+1] over the local runs, then the W x W matrix of send counts
+    c->xmeta.reserve((size_t)(W + 1) * 8 + (size_t)W * W * 8 + (OCC_BINS + 8) * 8 + 64);
+    unsigned long long *bounds_d = c->xmeta.as<unsigned long long>();
+    unsigned long long *mat_d = bounds_d + (W + 1);
+    unsigned long long *hist_d = mat_d + (size_t)W * W;            // OCC_BINS bins + [OCC_BINS] n_keys + [OCC_BINS+1] minimizers + scratch
+    owner_bounds_kernel<<<1, 32, 0, c->stream>>>(c->ukey.as<uint64_t>(), U, W, 2 * o.k, bounds_d);
+    ++c->launches;
+    std::vector<unsigned long long> bounds(W + 1), mat((size_t)W * W), sendc(W);
+    CUDA_CHECK(cudaMemcpyAsync(bounds.data(), bounds_d, (W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < W; ++d) sendc[d] = bounds[d + 1] - bounds[d];
+    CUDA_CHECK(cudaMemcpyAsync(hist_d + OCC_BINS + 8, sendc.data(), W * 8, cudaMemcpyHostToDevice, c->stream));   // staging slot
+    NCCL_CHECK(ncclAllGather(hist_d + OCC_BINS + 8, mat_d, W, ncclUint64, c->comm, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(mat.data(), mat_d, (size_t)W * W * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    std::vector<uint64_t> roff(W + 1, 0);
+    for (int s2 = 0; s2 < W; ++s2) roff[s2 + 1] = roff[s2] + mat[(size_t)s2 * W + me];
+    const uint64_t R = roff[W];
+    if (R >= (1ull << 32) - 2) throw std::length_error("too many distinct keys per owner rank");
+    c->rkey.reserve((R + 1) * 8); c->rcnt.reserve((R + 1) * 4);
+    c->skey.reserve((R + 1) * 8); c->scnt.reserve((R + 1) * 4);
+    NCCL_CHECK(ncclGroupStart());
+    for (int d = 0; d < W; ++d) if (sendc[d]) {
+        NCCL_CHECK(ncclSend(c->ukey.as<uint64_t>() + bounds[d], sendc[d], ncclUint64, d, c->comm, c->stream));
+        NCCL_CHECK(ncclSend(c->ucnt.as<uint32_t>() + bounds[d], sendc[d], ncclUint32, d, c->comm, c->stream));
+    }
+    for (int s2 = 0; s2 < W; ++s2) if (roff[s2 + 1] > roff[s2]) {
+        NCCL_CHECK(ncclRecv(c->rkey.as<uint64_t>() + roff[s2], roff[s2 + 1] - roff[s2], ncclUint64, s2, c->comm, c->stream));
+        NCCL_CHECK(ncclRecv(c->rcnt.as<uint32_t>() + roff[s2], roff[s2 + 1] - roff[s2], ncclUint32, s2, c->comm, c->stream));
+    }
+    NCCL_CHECK(ncclGroupEnd());
+
+    // owner: sort the received partial counts by key, sum per key, histogram
+    uint32_t G = 0;
+    CUDA_CHECK(cudaMemsetAsync(hist_d, 0, (OCC_BINS + 8) * 8, c->stream));
+    if (R) {
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, c->rkey.as<uint64_t>(), c->skey.as<uint64_t>(), c->rcnt.as<uint32_t>(),
+                                        c->scnt.as<uint32_t>(), (int64_t)R, 0, 2 * o.k, c->stream);
+        cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->rkey.as<uint64_t>(), c->skey.as<uint64_t>(), c->rcnt.as<uint32_t>(),
+                                        c->scnt.as<uint32_t>(), (int64_t)R, 0, 2 * o.k, c->stream);
+        c->flags.reserve(R + 1);
+        c->pstart.reserve((R + 2) * 4);      // NB: the local run starts are no longer needed
+        run_flag_kernel<<<(unsigned)((R + 255) / 256), 256, 0, c->stream>>>(c->skey.as<uint64_t>(), R, 0, c->flags.as<uint8_t>());
+        cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
+                                   c->npairs.as<uint32_t>(), (int64_t)R, c->stream);
+        cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                   c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)R, c->stream);
+        c->launches += 8;
+        CUDA_CHECK(cudaMemcpyAsync(&G, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        const uint32_t sentinel = (uint32_t)R;
+        CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + G, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
+        c->gcnt.reserve(((size_t)G + 1) * 4);
+        owner_sum_kernel<<<148 * 4, 256, 0, c->stream>>>(c->skey.as<uint64_t>(), c->scnt.as<uint32_t>(), c->pstart.as<uint32_t>(), G,
+                                                       c->gcnt.as<uint32_t>(), hist_d);
+        ++c->launches;
+    }
+    const unsigned long long extra[2] = {G, M};
+    CUDA_CHECK(cudaMemcpyAsync(hist_d + OCC_BINS, extra, 16, cudaMemcpyHostToDevice, c->stream));
+    NCCL_CHECK(ncclAllReduce(hist_d, hist_d, OCC_BINS + 2, ncclUint64, ncclSum, c->comm, c->stream));
+    std::vector<unsigned long long> h(OCC_BINS + 2);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), hist_d, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const uint64_t n_keys = h[OCC_BINS];
+    if (S) S->n_target_minimizers = h[OCC_BINS + 1];
+    int mid_occ;
+    if (n_keys == 0) mid_occ = INT32_MAX;
+    else {
+        const uint64_t rank = (uint32_t)((1. - (double)o.mid_occ_frac) * (double)n_keys);
+        uint64_t cum = 0; int64_t val = -1;
+        for (int b = 0; b < OCC_BINS - 1; ++b) { cum += h[b]; if (cum > rank) { val = b; break; } }
+        if (val < 0) {
+            // the rank lies among keys occurring >= OCC_BINS-1 times: gather those counts from all owners (padded)
+            const uint64_t cap = h[OCC_BINS - 1];
+            DevBuf mine, all;
+            mine.reserve((cap + 1) * 4); all.reserve((cap + 1) * 4 * W);
+            CUDA_CHECK(cudaMemsetAsync(mine.p, 0xff, (cap + 1) * 4, c->stream));
+            CUDA_CHECK(cudaMemsetAsync(hist_d + OCC_BINS + 4, 0, 8, c->stream));
+            if (G) owner_overflow_kernel<<<(G + 255) / 256, 256, 0, c->stream>>>(c->gcnt.as<uint32_t>(), G, mine.as<uint32_t>(), hist_d + OCC_BINS + 4, cap);
+            NCCL_CHECK(ncclAllGather(mine.p, all.p, cap, ncclUint32, c->comm, c->stream));
+            std::vector<uint32_t> ov(cap * W);
+            CUDA_CHECK(cudaMemcpyAsync(ov.data(), all.p, cap * W * 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            std::sort(ov.begin(), ov.end());                       // padding (0xffffffff) sorts last
+            val = ov[rank - cum];
+        }
+        mid_occ = (int)val + 1;
+    }
+    if (mid_occ < o.min_mid_occ) mid_occ = o.min_mid_occ;
+    if (o.max_mid_occ > o.min_mid_occ && mid_occ > o.max_mid_occ) mid_occ = o.max_mid_occ;
+
+    // blacklist: owned keys above mid_occ -> everyone
+    uint64_t n_above = 0;
+    for (int b = std::min(mid_occ + 1, OCC_BINS - 1); b < OCC_BINS; ++b) n_above += h[b];   // global upper bound on the blacklist length
+    const uint64_t cap = n_above + 1;
+    c->blist.reserve(cap * 8); c->blall.reserve(cap * 8 * W);
+    CUDA_CHECK(cudaMemsetAsync(c->blist.p, 0xff, cap * 8, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(hist_d + OCC_BINS + 4, 0, 8, c->stream));
+    if (G) { owner_select_kernel<<<(G + 255) / 256, 256, 0, c->stream>>>(c->skey.as<uint64_t>(), c->pstart.as<uint32_t>(), c->gcnt.as<uint32_t>(), G,
+                                                                          (uint32_t)mid_occ, c->blist.as<uint64_t>(), hist_d + OCC_BINS + 4, cap); ++c->launches; }
+    NCCL_CHECK(ncclAllGather(c->blist.p, c->blall.p, cap, ncclUint64, c->comm, c->stream));
+    c->blmap.reserve((M / 32 + 2) * 4);
+    CUDA_CHECK(cudaMemsetAsync(c->blmap.p, 0, (M / 32 + 2) * 4, c->stream));
+    B.view.tx = c->tx.as<uint64_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
+    bl_mark_kernel<<<(unsigned)((cap * W + 255) / 256), 256, 0, c->stream>>>(c->blall.as<uint64_t>(), cap * W, B.view, c->blmap.as<uint32_t>());
+    ++c->launches;
+    CUDA_CHECK(cudaGetLastError());
+    B.view.bl = c->blmap.as<uint32_t>();
     B.mid_occ = mid_occ; B.n_keys = n_keys;
     return B;
 }
@@ -402,16 +580,30 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     if (mode == MODE_INVERSE && !R.a_unique) throw std::domain_error("DuplicateReadIdentifier");
     const std::vector<uint32_t> &rank_idx = R.a, &rank_str = mode == MODE_AVA ? R.a : R.b;
 
-    // K0/K1 on the indexed set, K2/K3
-    sketch_readset(c, idx, o, &c->sk_idx, &S.ms_pack, &S.ms_sketch);
-    tm.start();
-    BuiltIndex B = build_index(c, c->sk_idx, o);
-    S.ms_index = tm.stop();
-    S.n_target_minimizers = c->sk_idx.M; S.n_keys = B.n_keys; S.mid_occ = B.mid_occ;
+    // K0/K1 on the indexed set, K2/K3.  With a communicator the index itself is sharded: this rank sketches only
+    // its targets (rid % world == rank) and the occurrence filter is made exact by build_index_sharded.
+    const int world = std::max(opts.shard_count, 1);
+    const bool sharded_index = c->comm != nullptr && world > 1;
+    if (sharded_index && (world != c->world || opts.shard_index != c->rank))
+        throw std::runtime_error("shard_index/shard_count do not match the communicator");
+    BuiltIndex B;
+    if (sharded_index) {
+        sketch_readset(c, idx, o, &c->sk_idx, &S.ms_pack, &S.ms_sketch, (uint32_t)c->rank, (uint32_t)world);
+        tm.start();
+        B = build_index_sharded(c, c->sk_idx, o, &S);
+        S.ms_index = tm.stop();
+    } else {
+        sketch_readset(c, idx, o, &c->sk_idx, &S.ms_pack, &S.ms_sketch);
+        tm.start();
+        B = build_index(c, c->sk_idx, o);
+        S.ms_index = tm.stop();
+        S.n_target_minimizers = c->sk_idx.M;
+    }
+    S.n_keys = B.n_keys; S.mid_occ = B.mid_occ;
 
     // K1 on the streamed set
     Sketch *sq = &c->sk_idx;
-    if (mode != MODE_AVA) { sketch_readset(c, str, o, &c->sk_str, &S.ms_pack, &S.ms_sketch); sq = &c->sk_str; }
+    if (mode != MODE_AVA || sharded_index) { sketch_readset(c, str, o, &c->sk_str, &S.ms_pack, &S.ms_sketch); sq = &c->sk_str; }
     const uint64_t MQ = sq->M;
     S.n_query_minimizers = MQ;
 
@@ -428,7 +620,8 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     K.len_q = c->len_str.as<uint32_t>(); K.len_t = c->len_idx.as<uint32_t>();
     K.no_dual = mode == MODE_AVA;                                      // aligner.rs:93-103, ava.rs:378
     K.check_names = mode == MODE_AVA || R.shared;                      // NO_DIAG only matters for equal names
-    K.shard_index = (uint32_t)opts.shard_index; K.shard_count = (uint32_t)std::max(opts.shard_count, 1);
+    K.shard_index = (uint32_t)opts.shard_index; K.shard_count = (uint32_t)world;
+    if (sharded_index) K.shard_count = 1;                              // every local hit already belongs to this shard
 
     c->counts.reserve(((size_t)n_counts + 1) * 4);
     c->had.reserve((size_t)str->n + 1);
@@ -631,10 +824,8 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     }
 
     // one exchange on the query path: sum the per-read counts of all target shards over NVLink
-    if (c->comm && K.shard_count > 1) {
+    if (sharded_index) {
         tm.start();
-        if (K.shard_count != (uint32_t)c->world || K.shard_index != (uint32_t)c->rank)
-            throw std::runtime_error("shard_index/shard_count do not match the communicator");
         ncclResult_t r1 = ncclAllReduce(c->counts.p, c->counts.p, n_counts, ncclUint32, ncclSum, c->comm, c->stream);
         ncclResult_t r2 = ncclAllReduce(c->had.p, c->had.p, str->n, ncclUint8, ncclMax, c->comm, c->stream);
         if (r1 != ncclSuccess || r2 != ncclSuccess) throw NcclError(std::string("ncclAllReduce: ") + ncclGetErrorString(r1 != ncclSuccess ? r1 : r2));
