@@ -43,34 +43,55 @@ def workload(name: str, n_gpus: int, scale: float):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md), sampled through NVML so that no
+    nvidia-smi process is spawned next to the measurement; falls back to nvidia-smi if NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.samples.append((float(sm), float(mx), [k for k, b in bits.items() if r & b]))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.samples.append((float(f[0]), float(f[1]), [names[i] for i in range(4) if f[3 + i].lower().startswith("active")]))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05 if self.nvml else 0.5)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=3)
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i].lower().startswith("active")})
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({r for s in self.samples for r in s[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "via": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def measured_peak():
@@ -162,13 +183,14 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     barrier()
-    ev_ms, chain_ms, launches = 0.0, 0.0, 0
+    ev_ms, chain_ms, launches, step_ms = 0.0, 0.0, 0, []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
         torch.cuda.synchronize()
         last = ctx.twoset_counts(sT, sQ, platform, **shard)
         ev_ms += last.stats["ms_total"]
+        step_ms.append(round(last.stats["ms_total"], 3))
         chain_ms += last.stats["ms_chain_kernel"]
         launches += last.stats["n_kernel_launches"]
     barrier()
@@ -245,7 +267,7 @@ def run_ours(args):
         "overlaps_per_step": overlaps,
         "gbases_per_s": (T.total_bases + Q.total_bases) / 1e9 / (ms_per_step / 1e3),
         "candidate_pairs_per_s": T.n * Q.n / (ms_per_step / 1e3),
-        "wall_ms_per_step": wall_ms / args.steps,
+        "wall_ms_per_step": wall_ms / args.steps, "step_ms": step_ms,
         "stage_ms": {k: st[k] for k in st if k.startswith("ms_")},
         "counts": {k: st[k] for k in ("n_target_minimizers", "n_query_minimizers", "n_keys", "n_seeds", "n_hits", "n_anchors",
                                       "n_pairs", "mid_occ", "n_batches")},
@@ -271,7 +293,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=WORKLOAD)

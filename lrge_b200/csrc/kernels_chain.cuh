@@ -27,6 +27,7 @@ namespace lrge {
 struct ChainParams {
     int max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc;
     const int32_t *pen;          // bw+1 entries
+    int span_bound_ok;           // every anchor span is the constant k and k * (min_cnt-1) < min_sc (no HPC)
 };
 
 struct PairTask {
@@ -276,9 +277,10 @@ __device__ __forceinline__ int32_t comput_sc_smem(int32_t ri, int32_t qi, int32_
     return sc;
 }
 
-// mg_lchain_dp for one group, warp-cooperative
-__device__ void warp_group_dp(const uint2 *__restrict__ anc, int32_t n, const ChainParams &P, const uint8_t *s_pen,
-                              int2 *fp, int32_t *t, uint32_t lane) {
+// mg_lchain_dp for one group, warp-cooperative.  Returns the first anchor whose score reaches stop_sc (the DP is
+// causal, so f[0..i] are final at that point), or -1 after the whole group.
+__device__ int32_t warp_group_dp(const uint2 *__restrict__ anc, int32_t n, const ChainParams &P, const uint8_t *s_pen,
+                                 int2 *fp, int32_t *t, uint32_t lane, int32_t stop_sc) {
     int32_t st = 0, r_st = n > 0 ? (int32_t)anc[0].x : 0, max_ii = -1, r_maxii = 0, f_maxii = 0;
     const uint32_t le_mask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1);
     for (int32_t i = 0; i < n; ++i) {
@@ -369,8 +371,10 @@ __device__ void warp_group_dp(const uint2 *__restrict__ anc, int32_t n, const Ch
         }
         if (lane == 0) fp[i] = make_int2(max_f, max_j);
         __syncwarp();
+        if (max_f >= stop_sc) return i;
         if (max_ii < 0 || (ri - r_maxii <= P.max_dist_x && f_maxii < max_f)) { max_ii = i; r_maxii = ri; f_maxii = max_f; }
     }
+    return -1;
 }
 
 // Warp argmax of (f, index) over the group among entries with f >= min_sc, strictly below (last_f, last_i) in
@@ -491,31 +495,57 @@ __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, Ch
         const uint2 *anc = T.anc + g0;
         int2 *fp = T.fp + g0;
         int32_t *t = T.t + g0;
-        warp_group_dp(anc, n, P, s_pen, fp, t, lane);
-        __syncwarp();
         const int32_t qlen = (int32_t)O.len_q[qid], tlen = (int32_t)O.len_t[rid];
         int kept = 0, pass = 0;
-        warp_group_backtrack(n, P, fp, t, lane, [&](const ChainCoord &c) -> bool {
-            kept = 1;
-            if (!O.remove_internal) { pass = 1; return true; }
-            const uint2 af = anc[c.a_first], al = anc[c.a_last];
-            const int32_t span0 = (int32_t)(af.y >> 24);
-            const int32_t x0 = (int32_t)af.x, x1 = (int32_t)al.x;
-            const int32_t y0 = (int32_t)(af.y & 0xffffff), y1 = (int32_t)(al.y & 0xffffff);
-            const int32_t rs = x0 + 1 > span0 ? x0 + 1 - span0 : 0, re = x1 + 1;
-            int32_t qs, qe;
-            if (!strand) { qs = y0 + 1 - span0; qe = y1 + 1; }
-            else { qs = qlen - (y1 + 1); qe = qlen - (y0 + 1 - span0); }
-            int32_t overhang;
-            if (!strand) overhang = min(qs, rs) + min(qlen - qe, tlen - re);
-            else overhang = min(qs, tlen - re) + min(qlen - qe, rs);
-            const int32_t maplen = max(qe - qs, re - rs);
-            bool drop;
-            if (O.mode == 2) drop = overhang > (int32_t)__fmul_rn((float)maplen, O.ratio);
-            else drop = __fdiv_rn((float)overhang, (float)maplen) < O.ratio;
-            if (!drop) { pass = 1; return true; }
-            return false;
-        });
+        bool full = true;
+        if (!O.remove_internal) {
+            // Counting only needs "does this group yield a kept chain".  The chain extracted first starts at the group's
+            // highest f; nothing is used yet and no predecessor scores above the start, so mg_chain_bk_end keeps
+            // sc >= min(f_max, max_drop) -- and with every span <= (min_sc-1)/(min_cnt-1) a score >= min_sc needs
+            // >= min_cnt anchors.  Hence: kept chain exists <=> some f[i] >= min_sc, and the DP can stop there.
+            const int32_t hit = warp_group_dp(anc, n, P, s_pen, fp, t, lane, P.min_sc);
+            full = false;
+            if (hit >= 0) {
+                int32_t mspan = 0;
+                if (P.span_bound_ok) mspan = 0;                         // constant span k (no HPC): bound holds by construction
+                else {
+                    for (int32_t i = lane; i < n; i += 32) mspan = max(mspan, (int32_t)(anc[i].y >> 24));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mspan = max(mspan, __shfl_xor_sync(0xffffffffu, mspan, o));
+                }
+                if (P.span_bound_ok || (mspan * (P.min_cnt - 1) < P.min_sc && P.bw >= P.min_sc)) kept = pass = 1;
+                else {                                                  // HPC group with a very long span: literal path
+                    for (int32_t i = lane; i < n; i += 32) t[i] = 0;
+                    __syncwarp();
+                    full = true;
+                }
+            }
+        }
+        if (full) {
+            warp_group_dp(anc, n, P, s_pen, fp, t, lane, INT32_MAX);
+            __syncwarp();
+            warp_group_backtrack(n, P, fp, t, lane, [&](const ChainCoord &c) -> bool {
+                kept = 1;
+                if (!O.remove_internal) { pass = 1; return true; }
+                const uint2 af = anc[c.a_first], al = anc[c.a_last];
+                const int32_t span0 = (int32_t)(af.y >> 24);
+                const int32_t x0 = (int32_t)af.x, x1 = (int32_t)al.x;
+                const int32_t y0 = (int32_t)(af.y & 0xffffff), y1 = (int32_t)(al.y & 0xffffff);
+                const int32_t rs = x0 + 1 > span0 ? x0 + 1 - span0 : 0, re = x1 + 1;
+                int32_t qs, qe;
+                if (!strand) { qs = y0 + 1 - span0; qe = y1 + 1; }
+                else { qs = qlen - (y1 + 1); qe = qlen - (y0 + 1 - span0); }
+                int32_t overhang;
+                if (!strand) overhang = min(qs, rs) + min(qlen - qe, tlen - re);
+                else overhang = min(qs, tlen - re) + min(qlen - qe, rs);
+                const int32_t maplen = max(qe - qs, re - rs);
+                bool drop;
+                if (O.mode == 2) drop = overhang > (int32_t)__fmul_rn((float)maplen, O.ratio);
+                else drop = __fdiv_rn((float)overhang, (float)maplen) < O.ratio;
+                if (!drop) { pass = 1; return true; }
+                return false;
+            });
+        }
         if (lane == 0 && kept) {
             // the two strand groups of one (query, target) pair share a slot: the forward group's
             uint32_t slot = g;

@@ -119,6 +119,9 @@ struct lrge_staged {
     std::vector<uint32_t> h_len;
     std::string names;
     std::vector<uint32_t> name_off;
+    std::vector<std::pair<uint64_t, uint32_t>> name_hash;   // (FNV-1a of the name, read), sorted: cheap equality joins
+    bool names_unique = true;
+    std::vector<uint32_t> lex_rank;                        // lazily: lexicographic rank of each name (AVA's strcmp order)
 };
 
 struct Sketch {                            // minimizers of a read set, (rid, position) order
@@ -144,6 +147,7 @@ struct lrge_ctx {
     DevBuf akey0, akey1, aval0, aval1, flags, pstart, npairs, f, p, t, pair_res;
     DevBuf anc, fp, glist, gmeta, pflag;
     bool chain_v1 = false;                 // LRGE_CHAIN_V1=1: thread-per-pair debug kernel
+    lrge_staged tmp_a, tmp_b;              // device staging of the host-buffer entry points (reused across calls)
     DevBuf rank_idx, rank_str, len_idx, len_str, pen, counts, had, counters;
     std::vector<int32_t> pen_host; int pen_k = 0, pen_bw = 0;
     // one process per GPU: NCCL communicator for the per-read count reduction
@@ -162,8 +166,12 @@ template <typename T> void h2d(lrge_ctx *c, DevBuf &d, const T *src, size_t n) {
 
 void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s) {
     s->n = rs->n;
-    s->h_off.assign(rs->off, rs->off + rs->n + 1);
     s->total_bases = rs->n ? rs->off[rs->n] - rs->off[0] : 0;
+    // start the big copy first; the host-side bookkeeping below overlaps with it
+    s->asc.reserve(s->total_bases + 64);
+    if (s->total_bases)
+        CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + rs->off[0], s->total_bases, cudaMemcpyHostToDevice, c->stream));
+    s->h_off.assign(rs->off, rs->off + rs->n + 1);
     if (rs->n && rs->off[0] != 0) {
         const uint64_t b = rs->off[0];
         for (auto &o : s->h_off) o -= b;
@@ -172,17 +180,30 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s) {
     s->max_len = 0;
     for (uint32_t i = 0; i < rs->n; ++i) {
         const uint64_t l = s->h_off[i + 1] - s->h_off[i];
-        if (l == 0) throw std::invalid_argument("MapError: Sequence is empty");          // aligner.rs:214-216
-        if (l >= (1u << 24)) throw std::length_error("reads of 16 Mbases or more are not supported");
+        if (l == 0) { cudaStreamSynchronize(c->stream); throw std::invalid_argument("MapError: Sequence is empty"); }   // aligner.rs:214-216
+        if (l >= (1u << 24)) { cudaStreamSynchronize(c->stream); throw std::length_error("reads of 16 Mbases or more are not supported"); }
         s->h_len[i] = (uint32_t)l;
         s->max_len = std::max(s->max_len, (uint32_t)l);
     }
     s->name_off.assign(rs->name_off, rs->name_off + rs->n + 1);
     s->names.assign(rs->names + rs->name_off[0], rs->names + rs->name_off[rs->n]);
     if (rs->n && rs->name_off[0] != 0) { const uint32_t b = rs->name_off[0]; for (auto &o : s->name_off) o -= b; }
-    s->asc.reserve(s->total_bases + 64);
-    if (s->total_bases)
-        CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + rs->off[0], s->total_bases, cudaMemcpyHostToDevice, c->stream));
+    // name hashes: equal names <=> equal hashes (verified); the usual case "all names distinct" needs no string sort
+    s->name_hash.resize(rs->n);
+    for (uint32_t i = 0; i < rs->n; ++i) {
+        uint64_t h = 1469598103934665603ull;
+        for (uint32_t j = s->name_off[i]; j < s->name_off[i + 1]; ++j) h = (h ^ (uint8_t)s->names[j]) * 1099511628211ull;
+        s->name_hash[i] = {h, i};
+    }
+    std::sort(s->name_hash.begin(), s->name_hash.end());
+    s->names_unique = true;
+    s->lex_rank.clear();
+    for (uint32_t i = 1; i < rs->n && s->names_unique; ++i)
+        if (s->name_hash[i].first == s->name_hash[i - 1].first) {
+            const uint32_t a = s->name_hash[i - 1].second, b = s->name_hash[i].second;
+            const uint32_t la = s->name_off[a + 1] - s->name_off[a], lb = s->name_off[b + 1] - s->name_off[b];
+            if (la == lb && memcmp(s->names.data() + s->name_off[a], s->names.data() + s->name_off[b], la) == 0) s->names_unique = false;
+        }
     h2d(c, s->off, s->h_off.data(), s->h_off.size());
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
@@ -574,10 +595,36 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     S.n_target_bases = idx->total_bases; S.n_query_bases = str->total_bases;
     const uint32_t launches0 = c->launches;
 
-    // names -> ranks
-    NameRanks R = rank_names(idx, mode == MODE_AVA ? nullptr : str);
-    if (mode == MODE_AVA && !R.a_unique) throw std::domain_error("DuplicateReadIdentifier");
-    if (mode == MODE_INVERSE && !R.a_unique) throw std::domain_error("DuplicateReadIdentifier");
+    // names -> ranks.  Only equality (two-set: NO_DIAG, HashSet<name>) or strcmp order (AVA: NO_DUAL) is ever used.
+    if ((mode == MODE_AVA || mode == MODE_INVERSE) && !idx->names_unique) throw std::domain_error("DuplicateReadIdentifier");
+    NameRanks R;
+    if (mode == MODE_AVA) {
+        if (idx->lex_rank.empty() && idx->n) idx->lex_rank = rank_names(idx, nullptr).a;
+        R.a = idx->lex_rank;
+    } else {
+        // do the two sets share a name?  (sorted hash lists, equal hashes verified on the bytes)
+        bool shared = false;
+        size_t i = 0, j = 0;
+        while (i < idx->name_hash.size() && j < str->name_hash.size() && !shared) {
+            const uint64_t ha = idx->name_hash[i].first, hb = str->name_hash[j].first;
+            if (ha < hb) ++i;
+            else if (hb < ha) ++j;
+            else {
+                size_t j2 = j;
+                for (; j2 < str->name_hash.size() && str->name_hash[j2].first == ha && !shared; ++j2) {
+                    const uint32_t a = idx->name_hash[i].second, b = str->name_hash[j2].second;
+                    const uint32_t la = idx->name_off[a + 1] - idx->name_off[a], lb = str->name_off[b + 1] - str->name_off[b];
+                    if (la == lb && memcmp(idx->names.data() + idx->name_off[a], str->names.data() + str->name_off[b], la) == 0) shared = true;
+                }
+                ++i;
+            }
+        }
+        if (!shared && idx->names_unique && str->names_unique) {   // all names distinct: any injective numbering will do
+            R.a.resize(idx->n); R.b.resize(str->n);
+            std::iota(R.a.begin(), R.a.end(), 0u);
+            std::iota(R.b.begin(), R.b.end(), idx->n);
+        } else R = rank_names(idx, str);
+    }
     const std::vector<uint32_t> &rank_idx = R.a, &rank_str = mode == MODE_AVA ? R.a : R.b;
 
     // K0/K1 on the indexed set, K2/K3.  With a communicator the index itself is sharded: this rank sketches only
@@ -678,6 +725,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     P.max_dist_x = std::max(o.max_gap, o.bw); P.max_dist_y = std::max(o.max_gap, o.bw);
     P.bw = o.bw; P.max_skip = o.max_chain_skip; P.max_iter = o.max_chain_iter; P.min_cnt = o.min_cnt; P.min_sc = o.min_chain_score;
     P.pen = c->pen.as<int32_t>();
+    P.span_bound_ok = !o.is_hpc && o.k * (o.min_cnt - 1) < o.min_chain_score && o.bw >= o.min_chain_score;
 
     const bool host_dedupe = mode == MODE_TWOSET && !R.a_unique;      // duplicate target names: HashSet<name> semantics
     std::vector<std::vector<uint32_t>> dedupe_sets;
@@ -968,7 +1016,7 @@ int lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_read
     return guarded(ctx, [&] {
         Timer tm(ctx->stream);
         tm.start();
-        lrge_staged sT, sQ;
+        lrge_staged &sT = ctx->tmp_a, &sQ = ctx->tmp_b;
         stage_readset(ctx, T, &sT);
         stage_readset(ctx, Q, &sQ);
         const float ms = tm.stop();
@@ -984,7 +1032,7 @@ int lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *o
     return guarded(ctx, [&] {
         Timer tm(ctx->stream);
         tm.start();
-        lrge_staged sR;
+        lrge_staged &sR = ctx->tmp_a;
         stage_readset(ctx, R, &sR);
         const float ms = tm.stop();
         if (stats) stats->ms_h2d = ms;

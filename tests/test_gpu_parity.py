@@ -181,15 +181,38 @@ def test_strategy_estimates_match_oracle(ctx):
     assert abs(r.estimate - 300_000) / 300_000 < 0.5
 
 
-def test_chain_kernels_agree(ctx, monkeypatch):
-    """The warp-per-group chaining kernel against the literal thread-per-pair one (LRGE_CHAIN_V1=1)."""
-    _, platform, T, Q = readsim.make_config("C1", scale=0.5)
-    a = ctx.twoset_counts(T, Q, platform, remove_internal=True)
+@pytest.mark.parametrize("platform,F", [("ont", True), ("ont", False), ("pb", False), ("pb", True)])
+def test_chain_kernels_agree(ctx, monkeypatch, platform, F):
+    """The warp-per-group chaining kernel (early-exit counting when F is off, full DP + backtrack when on) against
+    the literal thread-per-pair one (LRGE_CHAIN_V1=1: always full DP + backtrack)."""
+    T, Q = small_sets(nt=400, nq=150, mean=5000, gsize=250_000, err=readsim.ONT if platform == "ont" else readsim.HIFI)
+    a = ctx.twoset_counts(T, Q, platform, remove_internal=F)
     monkeypatch.setenv("LRGE_CHAIN_V1", "1")
     c1 = lrge_b200.Context(0)
     try:
-        b = c1.twoset_counts(T, Q, platform, remove_internal=True)
+        b = c1.twoset_counts(T, Q, platform, remove_internal=F)
     finally:
         c1.close()
     assert np.array_equal(a.counts, b.counts)
     assert np.array_equal(a.had_mapping, b.had_mapping)
+    assert a.counts.sum() > 0
+
+
+def test_long_span_hpc_group_takes_literal_path(ctx):
+    """ava-pb reads with long homopolymers: minimizer spans above (min_sc-1)/(min_cnt-1) disable the counting
+    shortcut for their groups; results must still equal the oracle."""
+    rng = np.random.default_rng(11)
+    def hp_seq(n):
+        out = []
+        for _ in range(n):
+            out.append(bytes([rng.choice(list(b"ACGT"))]) * int(rng.choice([1, 1, 1, 2, 3, 9, 14])))
+        return b"".join(out)
+    g = hp_seq(6000)
+    recs_t = [("t%d" % i, g[s:s + 6000]) for i, s in enumerate(range(0, len(g) - 6000, 700))]
+    recs_q = [("q%d" % i, g[s:s + 5000]) for i, s in enumerate(range(350, len(g) - 5000, 900))]
+    T, Q = ReadSet.from_records(recs_t), ReadSet.from_records(recs_q)
+    res = ctx.twoset_counts(T, Q, "pb")
+    want, had, _ = oracle.twoset_counts(T, Q, "pb", threads=4)
+    assert np.array_equal(res.counts, want)
+    assert np.array_equal(res.had_mapping, had)
+    assert want.sum() > 0
