@@ -129,6 +129,19 @@ int  lrge_gpu_ava_counts_staged(lrge_ctx *ctx, lrge_staged *R, const lrge_opts *
 int  lrge_gpu_comm_unique_id(uint8_t *out, size_t size);
 int  lrge_gpu_comm_init(lrge_ctx *ctx, int rank, int world, const uint8_t *unique_id, size_t size);
 
+/* Per-kernel device times of the LAST *_counts call on this context (CUDA events on the context's stream, no
+ * host syncs in between). Off by default; lrge_gpu_set_profiling(ctx, 1) turns the per-kernel events on.
+ * lrge_gpu_kernel_times fills up to cap records and returns the number of distinct kernels (or < 0). */
+typedef struct lrge_kernel_time {
+    char     name[64];
+    double   ms;                  /* summed over the launches of this kernel in the call */
+    double   algorithmic_bytes;   /* summed algorithmic bytes of those launches */
+    uint32_t launches;
+    uint32_t reserved;
+} lrge_kernel_time;
+int  lrge_gpu_set_profiling(lrge_ctx *ctx, int on);
+int  lrge_gpu_kernel_times(lrge_ctx *ctx, lrge_kernel_time *out, int cap);
+
 /* Pinned host memory for the caller's read buffers (optional; pageable memory works, slower). */
 int  lrge_gpu_host_alloc(size_t bytes, void **out);
 void lrge_gpu_host_free(void *p);

@@ -35,6 +35,7 @@ C_API = [
     "lrge_gpu_twoset_counts_staged", "lrge_gpu_ava_counts_staged", "lrge_gpu_host_alloc", "lrge_gpu_host_free",
     "lrge_gpu_dump_minimizers", "lrge_gpu_dump_mid_occ", "lrge_per_read_estimate", "lrge_estimate", "lrge_is_internal",
     "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates", "lrge_gpu_comm_unique_id", "lrge_gpu_comm_init",
+    "lrge_gpu_set_profiling", "lrge_gpu_kernel_times",
 ]
 
 
@@ -51,6 +52,11 @@ class Opts(ctypes.Structure):
         ("use_min_ref", ctypes.c_int32), ("shard_index", ctypes.c_int32), ("shard_count", ctypes.c_int32),
         ("reserved", ctypes.c_int32 * 6),
     ]
+
+
+class KernelTime(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 64), ("ms", ctypes.c_double), ("algorithmic_bytes", ctypes.c_double),
+                ("launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class Stats(ctypes.Structure):
@@ -105,6 +111,8 @@ def lib():
         L.lrge_gpu_ava_counts_staged.argtypes = [vp, vp, P(Opts), vp, P(Stats)]
         L.lrge_gpu_comm_unique_id.argtypes = [vp, ctypes.c_size_t]
         L.lrge_gpu_comm_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_size_t]
+        L.lrge_gpu_set_profiling.argtypes = [vp, ctypes.c_int]
+        L.lrge_gpu_kernel_times.argtypes = [vp, P(KernelTime), ctypes.c_int]
         L.lrge_gpu_host_alloc.argtypes = [ctypes.c_size_t, P(vp)]
         L.lrge_gpu_host_free.argtypes = [vp]
         L.lrge_gpu_host_free.restype = None
@@ -227,6 +235,16 @@ class Context:
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(lib().lrge_gpu_comm_init(self.h, rank, world, buf, 128))
         self.rank, self.world = rank, world
+
+    def set_profiling(self, on: bool):
+        self._check(lib().lrge_gpu_set_profiling(self.h, int(on)))
+
+    def kernel_times(self):
+        """Per-kernel device time of the last *_counts call (needs set_profiling(True))."""
+        buf = (KernelTime * 64)()
+        n = lib().lrge_gpu_kernel_times(self.h, buf, 64)
+        return [dict(name=buf[i].name.decode(), ms=buf[i].ms, algorithmic_bytes=buf[i].algorithmic_bytes, launches=buf[i].launches)
+                for i in range(max(0, min(n, 64)))]
 
     def stage(self, rs: ReadSet) -> Staged:
         return Staged(self, rs)

@@ -96,6 +96,53 @@ thread_local std::string g_create_error;
 
 struct NcclError : std::runtime_error { using std::runtime_error::runtime_error; };
 
+// Event-based profiler: spans are recorded on the stream without host syncs and resolved after the run.
+enum Stage { ST_PACK, ST_SKETCH, ST_INDEX, ST_SEED, ST_SORT, ST_CHAIN, ST_D2H, ST_TOTAL, ST_COMM, ST_COUNT };
+struct Prof {
+    cudaStream_t s = nullptr;
+    bool kernels = false;                              // per-kernel spans (lrge_gpu_set_profiling)
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Span { int id; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<std::string> names;                    // kernel spans: id = ST_COUNT + index into names
+    std::vector<double> ms, bytes;
+    std::vector<uint32_t> count;
+    int open_kernel = -1;
+    cudaEvent_t open_ev = nullptr;
+    cudaEvent_t stage_ev[ST_COUNT] = {};
+    ~Prof() { for (auto e : pool) cudaEventDestroy(e); }
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+    void reset() {
+        used = 0; spans.clear(); open_kernel = -1;
+        ms.assign(ST_COUNT + names.size(), 0.0); bytes.assign(ST_COUNT + names.size(), 0.0); count.assign(ST_COUNT + names.size(), 0);
+    }
+    int kid(const char *name) {
+        for (size_t i = 0; i < names.size(); ++i) if (names[i] == name) return ST_COUNT + (int)i;
+        names.emplace_back(name); ms.push_back(0); bytes.push_back(0); count.push_back(0);
+        return ST_COUNT + (int)names.size() - 1;
+    }
+    void sbegin(Stage st) { stage_ev[st] = get(); cudaEventRecord(stage_ev[st], s); }
+    void send(Stage st) { cudaEvent_t b = get(); cudaEventRecord(b, s); spans.push_back({(int)st, stage_ev[st], b}); }
+    void kbegin(const char *name, double nbytes) {
+        if (!kernels) return;
+        open_kernel = kid(name); bytes[open_kernel] += nbytes;
+        open_ev = get(); cudaEventRecord(open_ev, s);
+    }
+    void kend() {
+        if (!kernels || open_kernel < 0) return;
+        cudaEvent_t b = get(); cudaEventRecord(b, s); spans.push_back({open_kernel, open_ev, b}); open_kernel = -1;
+    }
+    void resolve() {                                   // the stream must be idle
+        for (auto &sp : spans) { float t = 0; cudaEventElapsedTime(&t, sp.a, sp.b); ms[sp.id] += t; ++count[sp.id]; }
+        spans.clear();
+    }
+};
+#define KLAUNCH(c, name, nbytes, ...) do { (c)->prof.kbegin(name, (double)(nbytes)); __VA_ARGS__; (c)->prof.kend(); ++(c)->launches; } while (0)
+
 struct Timer {
     cudaEvent_t a, b;
     cudaStream_t s;
@@ -134,6 +181,7 @@ struct lrge_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint32_t launches = 0;
+    Prof prof;
     // layout / sketch scratch
     DevBuf poff, len0, sub_off, rid_map, tile_off, w2, nm, wcnt, woff, casc, cend, clen;
     // sharded index exchange
@@ -147,6 +195,7 @@ struct lrge_ctx {
     DevBuf akey0, akey1, aval0, aval1, flags, pstart, npairs, f, p, t, pair_res;
     DevBuf anc, fp, glist, gmeta, pflag;
     bool chain_v1 = false;                 // LRGE_CHAIN_V1=1: thread-per-pair debug kernel
+    uint64_t max_anchors = 0;              // LRGE_MAX_ANCHORS=n: cap anchors per query batch
     lrge_staged tmp_a, tmp_b;              // device staging of the host-buffer entry points (reused across calls)
     DevBuf rank_idx, rank_str, len_idx, len_str, pen, counts, had, counters;
     std::vector<int32_t> pen_host; int pen_k = 0, pen_bw = 0;
@@ -220,8 +269,7 @@ __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32
 }
 
 // K0 + K1: sketch a staged read set (or the reads first, first+stride, ... of it) into `out`
-void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, float *ms_pack, float *ms_sketch,
-                    uint32_t first = 0, uint32_t stride = 1) {
+void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first = 0, uint32_t stride = 1) {
     const bool subset = stride > 1;
     const uint32_t n = s->n > first ? (s->n - first + stride - 1) / stride : 0;
     std::vector<uint64_t> poff(n), soff(n);
@@ -240,8 +288,9 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
     }
     tile_off[n] = tiles;
     const uint64_t padded_words = (pos + TILE_POS + 2 * PAD_BASES) / 32 + 8;
-    Timer tm(c->stream);
-    tm.start();
+    c->prof.sbegin(ST_PACK);
+    uint64_t nbases = 0;
+    for (uint32_t i = 0; i < n; ++i) nbases += slen[i];
     h2d(c, c->poff, poff.data(), n);
     h2d(c, c->tile_off, tile_off.data(), n + 1);
     c->w2.reserve(padded_words * 8);
@@ -263,10 +312,9 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         c->cend.reserve((s->total_bases + 1) * 4);
         c->clen.reserve((size_t)std::max(n, 1u) * 4);
         if (n) {
-            hpc_compress_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(s->asc.as<uint8_t>(), c->sub_off.as<uint64_t>(), c->len0.as<uint32_t>(), n,
-                                                                    c->casc.as<uint8_t>(), c->cend.as<uint32_t>(),
-                                                                    c->clen.as<uint32_t>());
-            ++c->launches;
+            KLAUNCH(c, "hpc_compress_kernel", 6 * nbases,
+                    hpc_compress_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(s->asc.as<uint8_t>(), c->sub_off.as<uint64_t>(), c->len0.as<uint32_t>(), n,
+                                                                            c->casc.as<uint8_t>(), c->cend.as<uint32_t>(), c->clen.as<uint32_t>()));
         }
         L.asc = c->casc.as<uint8_t>();
         len_dev = c->clen.as<uint32_t>();
@@ -275,11 +323,11 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         len_dev = c->len0.as<uint32_t>();
     }
     L.len = len_dev;
-    if (tiles) { pack_kernel<<<tiles, SK_THREADS, 0, c->stream>>>(L); ++c->launches; }
+    if (tiles) KLAUNCH(c, "pack_kernel", nbases + nbases * 3 / 8, pack_kernel<<<tiles, SK_THREADS, 0, c->stream>>>(L));
     CUDA_CHECK(cudaGetLastError());
-    if (ms_pack) *ms_pack += tm.stop();
+    c->prof.send(ST_PACK);
 
-    tm.start();
+    c->prof.sbegin(ST_SKETCH);
     const uint32_t nw = tiles * (SK_THREADS / 32);
     c->wcnt.reserve(((size_t)nw + 1) * 4);
     c->woff.reserve(((size_t)nw + 1) * 4);
@@ -290,14 +338,15 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
     if (tiles) {
         CUDA_CHECK(cudaMemsetAsync(c->wcnt.p, 0, ((size_t)nw + 1) * 4, c->stream));
         const bool x32 = !o.is_hpc && 2 * o.k <= 31;
-        if (o.is_hpc) sketch_kernel<true, false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        else if (x32) sketch_kernel<false, false, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        else sketch_kernel<false, false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        ++c->launches;
+        KLAUNCH(c, "sketch_kernel<count>", nbases * 3 / 8, {
+            if (o.is_hpc) sketch_kernel<true, false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+            else if (x32) sketch_kernel<false, false, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+            else sketch_kernel<false, false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        });
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream);
-        cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream);
-        ++c->launches;
+        KLAUNCH(c, "cub::DeviceScan(u32)", 8.0 * nw,
+                cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream));
         uint32_t total = 0;
         CUDA_CHECK(cudaMemcpyAsync(&total, c->woff.as<uint32_t>() + nw, 4, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -305,20 +354,21 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         out->x.reserve(((size_t)total + 1) * 8);
         out->y.reserve(((size_t)total + 1) * 8);
         A.ox = out->x.as<uint64_t>(); A.oy = out->y.as<uint64_t>();
-        if (o.is_hpc) sketch_kernel<true, true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        else if (x32) sketch_kernel<false, true, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        else sketch_kernel<false, true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        ++c->launches;
+        KLAUNCH(c, "sketch_kernel<emit>", nbases * 3 / 8 + 16.0 * total, {
+            if (o.is_hpc) sketch_kernel<true, true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+            else if (x32) sketch_kernel<false, true, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+            else sketch_kernel<false, true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        });
         // per-read minimizer offsets: woff at the first warp sub-tile of every read
-        gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), c->tile_off.as<uint32_t>(),
-                                                                     SK_THREADS / 32, n + 1, out->moff.as<uint32_t>());
-        ++c->launches;
+        KLAUNCH(c, "gather_kernel", 12.0 * n,
+                gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), c->tile_off.as<uint32_t>(),
+                                                                             SK_THREADS / 32, n + 1, out->moff.as<uint32_t>()));
     } else {
         uint32_t z = 0;
         h2d(c, out->moff, &z, 1);
     }
     CUDA_CHECK(cudaGetLastError());
-    if (ms_sketch) *ms_sketch += tm.stop();
+    c->prof.send(ST_SKETCH);
 }
 
 struct BuiltIndex { IndexView view; int mid_occ; uint64_t n_keys; };
@@ -334,9 +384,10 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
         size_t tb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
                                         c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
-        cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
-                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
-        c->launches += 4;
+        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", ((2 * o.k + 7) / 8) * 32.0 * M + 8.0 * M,
+                cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                                c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
+        c->launches += (2 * o.k + 7) / 8;
     }
     // ~8 entries per bucket: the table (4 B x 2^bits) stays L2-resident, a lookup bisects <= 3 steps
     int bits = 8;
@@ -344,15 +395,14 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     const uint32_t nb = 1u << bits;
     const int shift = 8 + 2 * o.k - bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
-    bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>());
-    ++c->launches;
+    KLAUNCH(c, "bucket_bounds_kernel", 8.0 * M + 4.0 * nb,
+            bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>()));
     // occurrence histogram -> mid_occ (mm_idx_cal_max_occ + mm_mapopt_update)
     c->hist.reserve((OCC_BINS + 2) * 8);
     CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));
     unsigned long long *hist = c->hist.as<unsigned long long>();
     if (M) {
-        occ_hist_kernel<<<148 * 4, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, hist, hist + OCC_BINS);
-        ++c->launches;
+        KLAUNCH(c, "occ_hist_kernel", 8.0 * M, occ_hist_kernel<<<148 * 4, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, hist, hist + OCC_BINS));
     }
     std::vector<unsigned long long> h(OCC_BINS + 2);
     CUDA_CHECK(cudaMemcpyAsync(h.data(), hist, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -404,17 +454,18 @@ BuiltIndex build_index_sharded(lrge_ctx *c, const Sketch &sk, const MapOpt &o, l
     if (M) {
         cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
                                         c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
-        cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
-                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
-        c->launches += 4;
+        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", ((2 * o.k + 7) / 8) * 32.0 * M + 8.0 * M,
+                cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                                c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
+        c->launches += (2 * o.k + 7) / 8;
     }
     int bits = 8;
     while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
     const uint32_t nb = 1u << bits;
     const int shift = 8 + 2 * o.k - bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
-    bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>());
-    ++c->launches;
+    KLAUNCH(c, "bucket_bounds_kernel", 8.0 * M + 4.0 * nb,
+            bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>()));
 
     // local run-length encoding: (key, count) per distinct local key
     c->flags.reserve(M + 1);
@@ -422,7 +473,7 @@ BuiltIndex build_index_sharded(lrge_ctx *c, const Sketch &sk, const MapOpt &o, l
     c->npairs.reserve(16);
     uint32_t U = 0;
     if (M) {
-        run_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, 8, c->flags.as<uint8_t>());
+        KLAUNCH(c, "run_flag_kernel", 9.0 * M, run_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, 8, c->flags.as<uint8_t>()));
         cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
                                    c->npairs.as<uint32_t>(), (int64_t)M, c->stream);
         cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
@@ -589,8 +640,8 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
                  uint32_t *counts_out, uint8_t *had_out, lrge_stats *st) {
     const MapOpt o = preset_for(opts.platform);
     const uint32_t n_counts = mode == MODE_TWOSET ? str->n : idx->n;
-    Timer total(c->stream), tm(c->stream);
-    total.start();
+    c->prof.reset();
+    c->prof.sbegin(ST_TOTAL);
     lrge_stats S{};
     S.n_target_bases = idx->total_bases; S.n_query_bases = str->total_bases;
     const uint32_t launches0 = c->launches;
@@ -635,26 +686,26 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         throw std::runtime_error("shard_index/shard_count do not match the communicator");
     BuiltIndex B;
     if (sharded_index) {
-        sketch_readset(c, idx, o, &c->sk_idx, &S.ms_pack, &S.ms_sketch, (uint32_t)c->rank, (uint32_t)world);
-        tm.start();
+        sketch_readset(c, idx, o, &c->sk_idx, (uint32_t)c->rank, (uint32_t)world);
+        c->prof.sbegin(ST_INDEX);
         B = build_index_sharded(c, c->sk_idx, o, &S);
-        S.ms_index = tm.stop();
+        c->prof.send(ST_INDEX);
     } else {
-        sketch_readset(c, idx, o, &c->sk_idx, &S.ms_pack, &S.ms_sketch);
-        tm.start();
+        sketch_readset(c, idx, o, &c->sk_idx);
+        c->prof.sbegin(ST_INDEX);
         B = build_index(c, c->sk_idx, o);
-        S.ms_index = tm.stop();
+        c->prof.send(ST_INDEX);
         S.n_target_minimizers = c->sk_idx.M;
     }
     S.n_keys = B.n_keys; S.mid_occ = B.mid_occ;
 
     // K1 on the streamed set
     Sketch *sq = &c->sk_idx;
-    if (mode != MODE_AVA || sharded_index) { sketch_readset(c, str, o, &c->sk_str, &S.ms_pack, &S.ms_sketch); sq = &c->sk_str; }
+    if (mode != MODE_AVA || sharded_index) { sketch_readset(c, str, o, &c->sk_str); sq = &c->sk_str; }
     const uint64_t MQ = sq->M;
     S.n_query_minimizers = MQ;
 
-    tm.start();
+    c->prof.sbegin(ST_SEED);
     h2d(c, c->rank_idx, rank_idx.data(), idx->n);
     h2d(c, c->rank_str, rank_str.data(), str->n);
     h2d(c, c->len_idx, idx->h_len.data(), idx->n);
@@ -688,26 +739,27 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     std::vector<uint64_t> qa((size_t)str->n + 1, 0);
     std::vector<uint32_t> moff_h((size_t)str->n + 1, 0);
     if (MQ) {
-        mz_flt_kernel<<<str->n, 256, 0, c->stream>>>(sq->x.as<uint64_t>(), sq->moff.as<uint32_t>(), B.mid_occ, o.q_occ_frac, c->flt.as<uint8_t>());
-        seed_count_kernel<<<(unsigned)((MQ + 255) / 256), 256, 0, c->stream>>>(
-            sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->flt.as<uint8_t>(), MQ, B.view, B.mid_occ, K,
-            c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(), ctr, ctr + 1);
-        c->launches += 2;
+        KLAUNCH(c, "mz_flt_kernel", 16.0 * MQ,
+                mz_flt_kernel<<<str->n, 256, 0, c->stream>>>(sq->x.as<uint64_t>(), sq->moff.as<uint32_t>(), B.mid_occ, o.q_occ_frac, c->flt.as<uint8_t>()));
+        KLAUNCH(c, "seed_count_kernel", 28.0 * MQ,
+                seed_count_kernel<<<(unsigned)((MQ + 255) / 256), 256, 0, c->stream>>>(
+                    sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->flt.as<uint8_t>(), MQ, B.view, B.mid_occ, K,
+                    c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(), ctr, ctr + 1));
         size_t tb = 0;
         cub::TransformInputIterator<uint64_t, WidenU32, const uint32_t *> in(c->acnt.as<uint32_t>(), WidenU32());
         cub::DeviceScan::ExclusiveSum(nullptr, tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream);
-        cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream);
-        ++c->launches;
+        KLAUNCH(c, "cub::DeviceScan(u64)", 12.0 * MQ,
+                cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream));
         // anchors before each query: aoff[moff[q]]
         CUDA_CHECK(cudaMemcpyAsync(moff_h.data(), sq->moff.p, ((size_t)str->n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-        gather_u64_kernel<<<(str->n + 1 + 255) / 256, 256, 0, c->stream>>>(c->aoff.as<uint64_t>(), sq->moff.as<uint32_t>(), str->n + 1,
-                                                                          c->qaoff.as<uint64_t>());
-        ++c->launches;
+        KLAUNCH(c, "gather_kernel", 20.0 * str->n,
+                gather_u64_kernel<<<(str->n + 1 + 255) / 256, 256, 0, c->stream>>>(c->aoff.as<uint64_t>(), sq->moff.as<uint32_t>(), str->n + 1,
+                                                                                  c->qaoff.as<uint64_t>()));
         CUDA_CHECK(cudaMemcpyAsync(qa.data(), c->qaoff.p, ((size_t)str->n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
     }
     CUDA_CHECK(cudaGetLastError());
-    S.ms_seed = tm.stop();
+    c->prof.send(ST_SEED);
     const uint64_t A_total = qa[str->n];
     S.n_anchors = A_total;
 
@@ -719,6 +771,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     reusable += c->anc.cap + c->fp.cap;
     uint64_t a_max = (uint64_t)((free_b + reusable) * 0.7 / 56.0);
     a_max = std::min<uint64_t>(a_max, (1ull << 31) - 1024);
+    if (c->max_anchors) a_max = std::min<uint64_t>(a_max, c->max_anchors);   // LRGE_MAX_ANCHORS: force small batches (tests)
     const int PB = bits_for(idx->max_len ? idx->max_len - 1 : 0), RB = bits_for(idx->n ? idx->n - 1 : 0);
 
     ChainParams P{};
@@ -741,23 +794,25 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         if (QB + RB + 1 + PB > 64) throw std::length_error("sort key does not fit 64 bits (too many reads x read length)");
         if (nA) {
             ++S.n_batches;
-            tm.start();
+            c->prof.sbegin(ST_SEED);
             c->akey0.reserve(nA * 8); c->akey1.reserve(nA * 8); c->aval0.reserve(nA * 4); c->aval1.reserve(nA * 4);
             const uint64_t m0 = moff_h[q0], m1 = moff_h[q1];
             KeyLayout KL{PB, RB};
-            anchor_fill_kernel<<<(unsigned)((m1 - m0 + 255) / 256), 256, 0, c->stream>>>(
-                sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
-                c->aoff.as<uint64_t>(), m0, m1, qa[q0], q0, B.view, K, KL, c->akey0.as<uint64_t>(), c->aval0.as<uint32_t>());
-            ++c->launches;
-            S.ms_seed += tm.stop();
+            KLAUNCH(c, "anchor_fill_kernel", 20.0 * nA + 28.0 * (m1 - m0),
+                    anchor_fill_kernel<<<(unsigned)((m1 - m0 + 255) / 256), 256, 0, c->stream>>>(
+                        sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
+                        c->aoff.as<uint64_t>(), m0, m1, qa[q0], q0, B.view, K, KL, c->akey0.as<uint64_t>(), c->aval0.as<uint32_t>()));
+            c->prof.send(ST_SEED);
 
-            tm.start();
+            c->prof.sbegin(ST_SORT);
             size_t tb = 0;
+            const int sort_bits = QB + RB + 1 + PB;
             cub::DeviceRadixSort::SortPairs(nullptr, tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
-                                            c->aval1.as<uint32_t>(), (int64_t)nA, 0, QB + RB + 1 + PB, c->stream);
-            cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
-                                            c->aval1.as<uint32_t>(), (int64_t)nA, 0, QB + RB + 1 + PB, c->stream);
-            c->launches += 1 + (QB + RB + 1 + PB + 7) / 8;
+                                            c->aval1.as<uint32_t>(), (int64_t)nA, 0, sort_bits, c->stream);
+            KLAUNCH(c, "cub::DeviceRadixSort(anchors: u64 key, u32 value)", ((sort_bits + 7) / 8) * 24.0 * nA + 8.0 * nA,
+                    cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
+                                                    c->aval1.as<uint32_t>(), (int64_t)nA, 0, sort_bits, c->stream));
+            c->launches += (sort_bits + 7) / 8;
             CountOut O{};
             O.counts = c->counts.as<uint32_t>(); O.had_mapping = c->had.as<uint8_t>();
             O.len_q = K.len_q; O.len_t = K.len_t; O.rank_q = K.rank_q; O.rank_t = K.rank_t;
@@ -768,7 +823,8 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
             if (c->chain_v1) {
                 // ---- v1 (debug cross-check, LRGE_CHAIN_V1=1): one thread per (query, target) pair ----
                 c->pstart.reserve((nA + 2) * 4);
-                pair_flag_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), nA, PB + 1, c->flags.as<uint8_t>());
+                KLAUNCH(c, "pair_flag_kernel", 9.0 * nA,
+                        pair_flag_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), nA, PB + 1, c->flags.as<uint8_t>()));
                 cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
                                            c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
                 cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
@@ -779,9 +835,9 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
                 CUDA_CHECK(cudaStreamSynchronize(c->stream));
                 const uint32_t sentinel = (uint32_t)nA;
                 CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_pairs, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
-                S.ms_sort += tm.stop();
+                c->prof.send(ST_SORT);
                 S.n_pairs += n_pairs;
-                tm.start();
+                c->prof.sbegin(ST_CHAIN);
                 c->f.reserve(nA * 4); c->p.reserve(nA * 4); c->t.reserve(nA * 4);
                 c->pair_res.reserve((size_t)n_pairs + 1);
                 CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
@@ -790,11 +846,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
                 T.n_pairs = n_pairs; T.PB = PB; T.RB = RB; T.q0 = q0;
                 T.f = c->f.as<int32_t>(); T.p = c->p.as<int32_t>(); T.t = c->t.as<int32_t>();
                 O.pair_res = c->pair_res.as<uint8_t>();
-                Timer tk(c->stream);
-                tk.start();
-                chain_pair_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(T, P, O);
-                ++c->launches;
-                S.ms_chain_kernel += tk.stop();
+                KLAUNCH(c, "chain_pair_kernel", 16.0 * nA + 4.0 * str->n, chain_pair_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(T, P, O));
                 CUDA_CHECK(cudaGetLastError());
                 if (host_dedupe) {
                     std::vector<uint8_t> res(n_pairs);
@@ -814,13 +866,14 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
                 // ---- v2: one warp per (query, target, strand) group --------------------------------------
                 c->anc.reserve(nA * 8);
                 c->pstart.reserve((nA + 2) * 4);
-                group_mark_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), c->aval1.as<uint32_t>(), nA, PB,
-                                                                                       c->anc.as<uint2>(), c->flags.as<uint8_t>());
+                KLAUNCH(c, "group_mark_kernel", 21.0 * nA,
+                        group_mark_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), c->aval1.as<uint32_t>(), nA, PB,
+                                                                                               c->anc.as<uint2>(), c->flags.as<uint8_t>()));
                 cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
                                            c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
-                cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
-                                           c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
-                c->launches += 2;
+                KLAUNCH(c, "cub::DeviceSelect(group starts)", 1.0 * nA,
+                        cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                                   c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream));
                 uint32_t n_groups = 0;
                 CUDA_CHECK(cudaMemcpyAsync(&n_groups, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
                 CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -831,13 +884,13 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
                 c->pflag.reserve((size_t)n_groups * 4 + 4);
                 CUDA_CHECK(cudaMemsetAsync(c->gmeta.p, 0, 64, c->stream));
                 CUDA_CHECK(cudaMemsetAsync(c->pflag.p, 0, (size_t)n_groups * 4 + 4, c->stream));
-                group_classify_kernel<<<(n_groups + 255) / 256, 256, 0, c->stream>>>(c->pstart.as<uint32_t>(), n_groups, P.min_cnt, P.min_sc,
-                                                                                    o.is_hpc ? 255 : o.k, c->glist.as<uint32_t>(),
-                                                                                    c->gmeta.as<uint32_t>());
-                ++c->launches;
-                S.ms_sort += tm.stop();
+                KLAUNCH(c, "group_classify_kernel", 8.0 * n_groups,
+                        group_classify_kernel<<<(n_groups + 255) / 256, 256, 0, c->stream>>>(c->pstart.as<uint32_t>(), n_groups, P.min_cnt, P.min_sc,
+                                                                                            o.is_hpc ? 255 : o.k, c->glist.as<uint32_t>(),
+                                                                                            c->gmeta.as<uint32_t>()));
+                c->prof.send(ST_SORT);
                 S.n_pairs += n_groups;
-                tm.start();
+                c->prof.sbegin(ST_CHAIN);
                 c->fp.reserve(nA * 8); c->t.reserve(nA * 4);
                 CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
                 GroupTask T{};
@@ -846,11 +899,8 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
                 T.work_ctr = c->gmeta.as<uint32_t>() + 8;
                 T.fp = c->fp.as<int2>(); T.t = c->t.as<int32_t>(); T.pflag = c->pflag.as<uint32_t>();
                 T.PB = PB; T.RB = RB; T.q0 = q0;
-                Timer tk(c->stream);
-                tk.start();
-                chain_group_kernel<<<148 * (2048 / CG_THREADS), CG_THREADS, 0, c->stream>>>(T, P, O);
-                ++c->launches;
-                S.ms_chain_kernel += tk.stop();
+                KLAUNCH(c, "chain_group_kernel", 16.0 * nA + 4.0 * str->n,
+                        chain_group_kernel<<<148 * (2048 / CG_THREADS), CG_THREADS, 0, c->stream>>>(T, P, O));
                 CUDA_CHECK(cudaGetLastError());
                 if (host_dedupe) {
                     std::vector<uint32_t> pf(n_groups), gs((size_t)n_groups + 1);
@@ -866,30 +916,37 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
                     }
                 }
             }
-            S.ms_chain += tm.stop();
+            c->prof.send(ST_CHAIN);
         }
         q0 = q1;
     }
 
     // one exchange on the query path: sum the per-read counts of all target shards over NVLink
     if (sharded_index) {
-        tm.start();
+        c->prof.sbegin(ST_COMM);
         ncclResult_t r1 = ncclAllReduce(c->counts.p, c->counts.p, n_counts, ncclUint32, ncclSum, c->comm, c->stream);
         ncclResult_t r2 = ncclAllReduce(c->had.p, c->had.p, str->n, ncclUint8, ncclMax, c->comm, c->stream);
         if (r1 != ncclSuccess || r2 != ncclSuccess) throw NcclError(std::string("ncclAllReduce: ") + ncclGetErrorString(r1 != ncclSuccess ? r1 : r2));
-        S.ms_comm = tm.stop();
+        c->prof.send(ST_COMM);
     }
 
     // results
-    tm.start();
+    c->prof.sbegin(ST_D2H);
     std::vector<uint32_t> counts(n_counts);
     std::vector<uint8_t> had(str->n);
     unsigned long long ctr_h[2] = {0, 0};
     if (n_counts) CUDA_CHECK(cudaMemcpyAsync(counts.data(), c->counts.p, (size_t)n_counts * 4, cudaMemcpyDeviceToHost, c->stream));
     if (str->n) CUDA_CHECK(cudaMemcpyAsync(had.data(), c->had.p, str->n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(ctr_h, ctr, 16, cudaMemcpyDeviceToHost, c->stream));
+    c->prof.send(ST_D2H);
+    c->prof.send(ST_TOTAL);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    S.ms_d2h = tm.stop();
+    c->prof.resolve();
+    S.ms_pack = (float)c->prof.ms[ST_PACK]; S.ms_sketch = (float)c->prof.ms[ST_SKETCH]; S.ms_index = (float)c->prof.ms[ST_INDEX];
+    S.ms_seed = (float)c->prof.ms[ST_SEED]; S.ms_sort = (float)c->prof.ms[ST_SORT]; S.ms_chain = (float)c->prof.ms[ST_CHAIN];
+    S.ms_d2h = (float)c->prof.ms[ST_D2H]; S.ms_comm = (float)c->prof.ms[ST_COMM]; S.ms_total = (float)c->prof.ms[ST_TOTAL];
+    for (size_t i = 0; i < c->prof.names.size(); ++i)
+        if (c->prof.names[i] == "chain_group_kernel" || c->prof.names[i] == "chain_pair_kernel") S.ms_chain_kernel += (float)c->prof.ms[ST_COUNT + i];
     if (host_dedupe)
         for (uint32_t q = 0; q < str->n; ++q) {
             auto &v = dedupe_sets[q];
@@ -906,7 +963,6 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     if (counts_out && n_counts) memcpy(counts_out, counts.data(), (size_t)n_counts * 4);
     if (had_out && mode == MODE_TWOSET && str->n) memcpy(had_out, had.data(), str->n);
     S.n_kernel_launches = c->launches - launches0;
-    S.ms_total = total.stop();
     if (st) { const float h2d_ms = st->ms_h2d; *st = S; st->ms_h2d = h2d_ms; }
 }
 
@@ -963,7 +1019,10 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         std::unique_ptr<lrge_ctx> c(new lrge_ctx());
         c->device = device;
         { const char *e = getenv("LRGE_CHAIN_V1"); c->chain_v1 = e && e[0] == '1'; }
+        { const char *e = getenv("LRGE_MAX_ANCHORS"); c->max_anchors = e ? strtoull(e, nullptr, 10) : 0; }
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->prof.s = c->stream;
+        c->prof.reset();
         CUDA_CHECK(cudaMemcpyToSymbol(c_nt4, kNt4, 256));
         *out = c.release();
         return LRGE_OK;
@@ -1062,6 +1121,25 @@ int lrge_gpu_comm_init(lrge_ctx *ctx, int rank, int world, const uint8_t *unique
     });
 }
 
+int lrge_gpu_set_profiling(lrge_ctx *ctx, int on) {
+    if (!ctx) return LRGE_ERR_INVALID_ARG;
+    ctx->prof.kernels = on != 0;
+    return LRGE_OK;
+}
+
+int lrge_gpu_kernel_times(lrge_ctx *ctx, lrge_kernel_time *out, int cap) {
+    if (!ctx || (!out && cap > 0)) return -1;
+    const int n = (int)ctx->prof.names.size();
+    for (int i = 0; i < n && i < cap; ++i) {
+        memset(&out[i], 0, sizeof(out[i]));
+        strncpy(out[i].name, ctx->prof.names[i].c_str(), sizeof(out[i].name) - 1);
+        out[i].ms = ctx->prof.ms[ST_COUNT + i];
+        out[i].algorithmic_bytes = ctx->prof.bytes[ST_COUNT + i];
+        out[i].launches = ctx->prof.count[ST_COUNT + i];
+    }
+    return n;
+}
+
 int lrge_gpu_host_alloc(size_t bytes, void **out) {
     if (!out) return LRGE_ERR_INVALID_ARG;
     cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
@@ -1077,7 +1155,7 @@ int lrge_gpu_dump_minimizers(lrge_ctx *ctx, const lrge_readset *rs, int32_t plat
         lrge_staged s;
         stage_readset(ctx, rs, &s);
         const MapOpt o = preset_for(platform);
-        sketch_readset(ctx, &s, o, &ctx->sk_str, nullptr, nullptr);
+        sketch_readset(ctx, &s, o, &ctx->sk_str);
         const uint64_t M = ctx->sk_str.M;
         *n_out = M;
         const uint64_t m = std::min(M, cap);
@@ -1099,7 +1177,7 @@ int lrge_gpu_dump_mid_occ(lrge_ctx *ctx, const lrge_readset *T, int32_t platform
         lrge_staged s;
         stage_readset(ctx, T, &s);
         const MapOpt o = preset_for(platform);
-        sketch_readset(ctx, &s, o, &ctx->sk_idx, nullptr, nullptr);
+        sketch_readset(ctx, &s, o, &ctx->sk_idx);
         BuiltIndex B = build_index(ctx, ctx->sk_idx, o);
         *mid_occ = B.mid_occ;
         if (n_keys) *n_keys = B.n_keys;

@@ -216,3 +216,24 @@ def test_long_span_hpc_group_takes_literal_path(ctx):
     assert np.array_equal(res.counts, want)
     assert np.array_equal(res.had_mapping, had)
     assert want.sum() > 0
+
+
+def test_query_batching(ctx, monkeypatch):
+    """Anchors are processed in query batches sized from device memory; force many small batches."""
+    T, Q = small_sets()
+    full = ctx.twoset_counts(T, Q, "ont")
+    monkeypatch.setenv("LRGE_MAX_ANCHORS", "6000")
+    c1 = lrge_b200.Context(0)
+    try:
+        b = c1.twoset_counts(T, Q, "ont")
+        g = readsim.genome(200_000)
+        R = readsim.reads(g, 250, 4000, readsim.ONT, readsim.SEED_AVA, "r")
+        av = c1.ava_counts(R, "ont")
+    finally:
+        c1.close()
+    assert b.stats["n_batches"] > 5
+    assert np.array_equal(full.counts, b.counts)
+    assert np.array_equal(full.had_mapping, b.had_mapping)
+    want, _ = oracle.ava_counts(R, "ont", threads=8)
+    assert av.stats["n_batches"] > 5
+    assert np.array_equal(av.counts, want)
