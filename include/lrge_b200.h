@@ -114,6 +114,28 @@ int  lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_rea
 int  lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts,
                          uint32_t *counts, lrge_stats *stats);
 
+/* Every overlap minimap2 would report for the pair of sets (one record per kept chain = one PAF row / mm_reg1_t as
+ * liblrge copies it out, aligner.rs:244-290; with MM_F_ALL_CHAINS every chain is reported, tp:A:S, mapq 0), in no
+ * particular order.  query/target are read indices into Q / T.  Not restated yet: dv (mm_est_err) and rl (rep_len).
+ * Up to cap records are written; *n_out receives the number found (call again with a larger buffer if > cap).
+ * counts / had_mapping (optional) are filled as by lrge_gpu_twoset_counts. */
+typedef struct lrge_overlap {
+    uint32_t query, target;
+    int32_t  rev;                 /* 0 '+', 1 '-' */
+    int32_t  qs, qe, ts, te;      /* PafRecord query_start/query_end/target_start/target_end */
+    int32_t  score, cnt;          /* s1:i, cm:i */
+    int32_t  mlen, blen;          /* match_len, block_len */
+} lrge_overlap;
+int  lrge_gpu_twoset_overlaps(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,
+                              lrge_overlap *out, uint64_t cap, uint64_t *n_out,
+                              uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats);
+int  lrge_gpu_ava_overlaps(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts,
+                           lrge_overlap *out, uint64_t cap, uint64_t *n_out, uint32_t *counts, lrge_stats *stats);
+/* One PAF line (no newline) for an overlap, formatted as liblrge's PafRecord serialises it (mapping.rs:81-177):
+ * 12 columns, then tp:A:S cm:i s1:i dv:f rl:i.  dv < 0 prints as 0. Returns the length written (truncated to cap-1). */
+int  lrge_paf_format(const lrge_overlap *o, const char *qname, int qname_len, int32_t qlen,
+                     const char *tname, int tname_len, int32_t tlen, float dv, int32_t rl, char *buf, size_t cap);
+
 /* Same computation with the read sets already resident in HBM (what bench.py times as `value`). */
 int  lrge_gpu_stage(lrge_ctx *ctx, const lrge_readset *rs, lrge_staged **out);
 void lrge_gpu_unstage(lrge_ctx *ctx, lrge_staged *s);

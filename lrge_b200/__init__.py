@@ -35,7 +35,7 @@ C_API = [
     "lrge_gpu_twoset_counts_staged", "lrge_gpu_ava_counts_staged", "lrge_gpu_host_alloc", "lrge_gpu_host_free",
     "lrge_gpu_dump_minimizers", "lrge_gpu_dump_mid_occ", "lrge_per_read_estimate", "lrge_estimate", "lrge_is_internal",
     "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates", "lrge_gpu_comm_unique_id", "lrge_gpu_comm_init",
-    "lrge_gpu_set_profiling", "lrge_gpu_kernel_times",
+    "lrge_gpu_set_profiling", "lrge_gpu_kernel_times", "lrge_gpu_twoset_overlaps", "lrge_gpu_ava_overlaps", "lrge_paf_format",
 ]
 
 
@@ -52,6 +52,10 @@ class Opts(ctypes.Structure):
         ("use_min_ref", ctypes.c_int32), ("shard_index", ctypes.c_int32), ("shard_count", ctypes.c_int32),
         ("reserved", ctypes.c_int32 * 6),
     ]
+
+
+OVERLAP_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("rev", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("ts", "<i4"),
+                          ("te", "<i4"), ("score", "<i4"), ("cnt", "<i4"), ("mlen", "<i4"), ("blen", "<i4")])
 
 
 class KernelTime(ctypes.Structure):
@@ -113,6 +117,10 @@ def lib():
         L.lrge_gpu_comm_init.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_size_t]
         L.lrge_gpu_set_profiling.argtypes = [vp, ctypes.c_int]
         L.lrge_gpu_kernel_times.argtypes = [vp, P(KernelTime), ctypes.c_int]
+        L.lrge_gpu_twoset_overlaps.argtypes = [vp, P(CReadSet), P(CReadSet), P(Opts), vp, ctypes.c_uint64, P(ctypes.c_uint64), vp, vp, P(Stats)]
+        L.lrge_gpu_ava_overlaps.argtypes = [vp, P(CReadSet), P(Opts), vp, ctypes.c_uint64, P(ctypes.c_uint64), vp, P(Stats)]
+        L.lrge_paf_format.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int, ctypes.c_int32,
+                                      ctypes.c_float, ctypes.c_int32, ctypes.c_char_p, ctypes.c_size_t]
         L.lrge_gpu_host_alloc.argtypes = [ctypes.c_size_t, P(vp)]
         L.lrge_gpu_host_free.argtypes = [vp]
         L.lrge_gpu_host_free.restype = None
@@ -276,6 +284,37 @@ class Context:
             self._check(lib().lrge_gpu_ava_counts(self.h, ctypes.byref(cr), ctypes.byref(o), counts.ctypes.data, ctypes.byref(st)))
         return Counts(counts, None, st.as_dict())
 
+    def twoset_overlaps(self, T: ReadSet, Q: ReadSet, platform="ont", cap: int = 0, **kw):
+        """Every overlap (kept chain) as a structured array (OVERLAP_DTYPE) plus the Counts of the same run."""
+        o = make_opts(platform, **kw)
+        cap = cap or max(1024, 64 * Q.n)
+        while True:
+            out = np.zeros(cap, OVERLAP_DTYPE)
+            n = ctypes.c_uint64()
+            counts, had = np.zeros(Q.n, np.uint32), np.zeros(Q.n, np.uint8)
+            st = Stats()
+            ct, cq = as_c(T), as_c(Q)
+            self._check(lib().lrge_gpu_twoset_overlaps(self.h, ctypes.byref(ct), ctypes.byref(cq), ctypes.byref(o), out.ctypes.data, cap,
+                                                       ctypes.byref(n), counts.ctypes.data, had.ctypes.data, ctypes.byref(st)))
+            if n.value <= cap:
+                return out[:n.value], Counts(counts, had, st.as_dict())
+            cap = int(n.value)
+
+    def ava_overlaps(self, R: ReadSet, platform="ont", cap: int = 0, **kw):
+        o = make_opts(platform, **kw)
+        cap = cap or max(1024, 64 * R.n)
+        while True:
+            out = np.zeros(cap, OVERLAP_DTYPE)
+            n = ctypes.c_uint64()
+            counts = np.zeros(R.n, np.uint32)
+            st = Stats()
+            cr = as_c(R)
+            self._check(lib().lrge_gpu_ava_overlaps(self.h, ctypes.byref(cr), ctypes.byref(o), out.ctypes.data, cap, ctypes.byref(n),
+                                                    counts.ctypes.data, ctypes.byref(st)))
+            if n.value <= cap:
+                return out[:n.value], Counts(counts, None, st.as_dict())
+            cap = int(n.value)
+
     def dump_minimizers(self, rs: ReadSet, platform="ont"):
         cap = rs.total_bases + 16
         x, y = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
@@ -291,6 +330,17 @@ class Context:
         c = as_c(T)
         self._check(lib().lrge_gpu_dump_mid_occ(self.h, ctypes.byref(c), platform_code(platform), ctypes.byref(m), ctypes.byref(nk)))
         return m.value, nk.value
+
+
+def paf_line(ov, Q: ReadSet, T: ReadSet, dv: float = -1.0, rl: int = 0) -> bytes:
+    """One PAF row as PafRecord serialises it (mapping.rs:81-177)."""
+    rec = np.zeros(1, OVERLAP_DTYPE)
+    rec[0] = ov
+    qn, tn = Q.name(int(ov["query"])), T.name(int(ov["target"]))
+    buf = ctypes.create_string_buffer(1024)
+    n = lib().lrge_paf_format(rec.ctypes.data, qn, len(qn), int(Q.off[int(ov["query"]) + 1] - Q.off[int(ov["query"])]), tn, len(tn),
+                              int(T.off[int(ov["target"]) + 1] - T.off[int(ov["target"])]), dv, rl, buf, 1024)
+    return buf.raw[:n]
 
 
 # ---- host-side mirror of liblrge's estimator surface -----------------------------------------------

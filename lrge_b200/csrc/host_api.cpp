@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <vector>
@@ -66,6 +67,19 @@ int lrge_is_internal(int32_t qlen, int32_t qs, int32_t qe, int32_t rev, int32_t 
     const int32_t maplen = std::max(qe - qs, te - ts);
     volatile float r = (float)overhang / (float)maplen;
     return r < ratio;
+}
+
+int lrge_paf_format(const lrge_overlap *o, const char *qname, int qname_len, int32_t qlen, const char *tname, int tname_len,
+                    int32_t tlen, float dv, int32_t rl, char *buf, size_t cap) {
+    if (!o || !buf || cap == 0) return -1;
+    // serialize_dv (mapping.rs:135-147): "0" below f32::EPSILON, else 4 decimals
+    char dvs[32];
+    if (dv < 1.1920929e-07f) snprintf(dvs, sizeof dvs, "0");
+    else snprintf(dvs, sizeof dvs, "%.4f", (double)dv);
+    const int n = snprintf(buf, cap, "%.*s\t%d\t%d\t%d\t%c\t%.*s\t%d\t%d\t%d\t%d\t%d\t0\ttp:A:S\tcm:i:%d\ts1:i:%d\tdv:f:%s\trl:i:%d",
+                           qname_len, qname, qlen, o->qs, o->qe, o->rev ? '-' : '+', tname_len, tname, tlen, o->ts, o->te, o->mlen,
+                           o->blen, o->cnt, o->score, dvs, rl);
+    return n < 0 ? -1 : (n >= (int)cap ? (int)cap - 1 : n);
 }
 
 int lrge_twoset_generate_estimates(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,

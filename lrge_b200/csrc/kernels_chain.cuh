@@ -40,7 +40,13 @@ struct PairTask {
     int32_t *f, *p, *t;          // per-anchor scratch (batch sized); t zeroed before launch
 };
 
+// one kept chain = one mm_reg1_t as liblrge reads it (aligner.rs:244-290); same layout as lrge_overlap
+struct RegOut { uint32_t qid, rid; int32_t rev, qs, qe, rs, re, score, cnt, mlen, blen; };
+
 struct CountOut {
+    RegOut *regs;                // optional: every kept chain (full DP + full backtrack, no counting shortcut)
+    unsigned long long *n_regs;
+    uint64_t regs_cap;
     uint32_t *counts;            // two-set: per query; ava: per read
     uint8_t  *had_mapping;       // two-set: any kept chain (before -F)
     uint8_t  *pair_res;          // per pair: bit0 kept chain, bit1 kept chain passing -F
@@ -498,7 +504,7 @@ __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, Ch
         const int32_t qlen = (int32_t)O.len_q[qid], tlen = (int32_t)O.len_t[rid];
         int kept = 0, pass = 0;
         bool full = true;
-        if (!O.remove_internal) {
+        if (!O.remove_internal && !O.regs) {
             // Counting only needs "does this group yield a kept chain".  The chain extracted first starts at the group's
             // highest f; nothing is used yet and no predecessor scores above the start, so mg_chain_bk_end keeps
             // sc >= min(f_max, max_drop) -- and with every span <= (min_sc-1)/(min_cnt-1) a score >= min_sc needs
@@ -507,8 +513,7 @@ __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, Ch
             full = false;
             if (hit >= 0) {
                 int32_t mspan = 0;
-                if (P.span_bound_ok) mspan = 0;                         // constant span k (no HPC): bound holds by construction
-                else {
+                if (!P.span_bound_ok) {
                     for (int32_t i = lane; i < n; i += 32) mspan = max(mspan, (int32_t)(anc[i].y >> 24));
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) mspan = max(mspan, __shfl_xor_sync(0xffffffffu, mspan, o));
@@ -526,7 +531,8 @@ __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, Ch
             __syncwarp();
             warp_group_backtrack(n, P, fp, t, lane, [&](const ChainCoord &c) -> bool {
                 kept = 1;
-                if (!O.remove_internal) { pass = 1; return true; }
+                if (!O.remove_internal && !O.regs) { pass = 1; return true; }
+                // mm_reg_set_coor (hit.c)
                 const uint2 af = anc[c.a_first], al = anc[c.a_last];
                 const int32_t span0 = (int32_t)(af.y >> 24);
                 const int32_t x0 = (int32_t)af.x, x1 = (int32_t)al.x;
@@ -535,15 +541,39 @@ __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, Ch
                 int32_t qs, qe;
                 if (!strand) { qs = y0 + 1 - span0; qe = y1 + 1; }
                 else { qs = qlen - (y1 + 1); qe = qlen - (y0 + 1 - span0); }
-                int32_t overhang;
-                if (!strand) overhang = min(qs, rs) + min(qlen - qe, tlen - re);
-                else overhang = min(qs, tlen - re) + min(qlen - qe, rs);
-                const int32_t maplen = max(qe - qs, re - rs);
-                bool drop;
-                if (O.mode == 2) drop = overhang > (int32_t)__fmul_rn((float)maplen, O.ratio);
-                else drop = __fdiv_rn((float)overhang, (float)maplen) < O.ratio;
-                if (!drop) { pass = 1; return true; }
-                return false;
+                bool drop = false;
+                if (O.remove_internal) {                                // PafRecord::is_internal / the inverse path's inline test
+                    int32_t overhang;
+                    if (!strand) overhang = min(qs, rs) + min(qlen - qe, tlen - re);
+                    else overhang = min(qs, tlen - re) + min(qlen - qe, rs);
+                    const int32_t maplen = max(qe - qs, re - rs);
+                    if (O.mode == 2) drop = overhang > (int32_t)__fmul_rn((float)maplen, O.ratio);
+                    else drop = __fdiv_rn((float)overhang, (float)maplen) < O.ratio;
+                }
+                if (!drop) pass = 1;
+                if (O.regs) {
+                    if (lane == 0) {
+                        // mm_cal_fuzzy_len (hit.c): walk the chain once more, last anchor -> first
+                        int32_t mlen = span0, blen = span0;
+                        for (int32_t i = c.a_last; i != c.a_first;) {
+                            const int32_t pi = fp[i].y;
+                            const uint2 a1 = anc[i], a0 = anc[pi];
+                            const int32_t span = (int32_t)(a1.y >> 24);
+                            const int32_t tl = (int32_t)a1.x - (int32_t)a0.x, ql = (int32_t)(a1.y & 0xffffff) - (int32_t)(a0.y & 0xffffff);
+                            blen += tl > ql ? tl : ql;
+                            mlen += (tl > span && ql > span) ? span : (tl < ql ? tl : ql);
+                            i = pi;
+                        }
+                        const unsigned long long slot = atomicAdd(O.n_regs, 1ull);
+                        if (slot < O.regs_cap) {
+                            RegOut r; r.qid = qid; r.rid = rid; r.rev = strand; r.qs = qs; r.qe = qe; r.rs = rs; r.re = re;
+                            r.score = c.sc; r.cnt = c.cnt; r.mlen = mlen; r.blen = blen;
+                            O.regs[slot] = r;
+                        }
+                    }
+                    return false;                                       // every chain of the group is reported
+                }
+                return !drop;
             });
         }
         if (lane == 0 && kept) {

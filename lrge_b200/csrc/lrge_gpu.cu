@@ -193,7 +193,7 @@ struct lrge_ctx {
     // seed / anchors
     DevBuf flt, hstart, hn, acnt, aoff, qaoff;
     DevBuf akey0, akey1, aval0, aval1, flags, pstart, npairs, f, p, t, pair_res;
-    DevBuf anc, fp, glist, gmeta, pflag;
+    DevBuf anc, fp, glist, gmeta, pflag, regs;
     bool chain_v1 = false;                 // LRGE_CHAIN_V1=1: thread-per-pair debug kernel
     uint64_t max_anchors = 0;              // LRGE_MAX_ANCHORS=n: cap anchors per query batch
     lrge_staged tmp_a, tmp_b;              // device staging of the host-buffer entry points (reused across calls)
@@ -636,8 +636,11 @@ struct WidenU32 { __host__ __device__ uint64_t operator()(uint32_t v) const { re
 
 // The whole hot path: `idx` is the indexed read set, `str` the streamed one (the same object for AVA).
 // counts_out: MODE_TWOSET -> per streamed read; MODE_AVA -> per read; MODE_INVERSE -> per indexed read.
+struct RegsRequest { lrge_overlap *out = nullptr; uint64_t cap = 0; uint64_t *n_out = nullptr; };
+
 void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, const lrge_opts &opts,
-                 uint32_t *counts_out, uint8_t *had_out, lrge_stats *st) {
+                 uint32_t *counts_out, uint8_t *had_out, lrge_stats *st, const RegsRequest *rq = nullptr) {
+    static_assert(sizeof(lrge_overlap) == sizeof(RegOut), "lrge_overlap and the device record must share a layout");
     const MapOpt o = preset_for(opts.platform);
     const uint32_t n_counts = mode == MODE_TWOSET ? str->n : idx->n;
     c->prof.reset();
@@ -727,7 +730,9 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     CUDA_CHECK(cudaMemsetAsync(c->counts.p, 0, ((size_t)n_counts + 1) * 4, c->stream));
     CUDA_CHECK(cudaMemsetAsync(c->had.p, 0, (size_t)str->n + 1, c->stream));
     CUDA_CHECK(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
-    unsigned long long *ctr = c->counters.as<unsigned long long>();   // [0] seeds [1] hits
+    unsigned long long *ctr = c->counters.as<unsigned long long>();   // [0] seeds [1] hits [2] overlap records
+    const bool want_regs = rq && rq->n_out;
+    if (want_regs) c->regs.reserve(std::max<uint64_t>(rq->cap, 1) * sizeof(RegOut));
 
     // K4 part 1: filter + lookup + count
     c->flt.reserve(MQ + 1);
@@ -818,6 +823,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
             O.len_q = K.len_q; O.len_t = K.len_t; O.rank_q = K.rank_q; O.rank_t = K.rank_t;
             O.mode = mode; O.remove_internal = opts.remove_internal; O.ratio = opts.max_overhang_ratio;
             O.names_unique = !host_dedupe;
+            if (want_regs) { O.regs = c->regs.as<RegOut>(); O.n_regs = ctr + 2; O.regs_cap = rq->cap; }
             c->flags.reserve(nA + 1);
             c->npairs.reserve(16);
             if (c->chain_v1) {
@@ -934,10 +940,17 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     c->prof.sbegin(ST_D2H);
     std::vector<uint32_t> counts(n_counts);
     std::vector<uint8_t> had(str->n);
-    unsigned long long ctr_h[2] = {0, 0};
+    unsigned long long ctr_h[3] = {0, 0, 0};
     if (n_counts) CUDA_CHECK(cudaMemcpyAsync(counts.data(), c->counts.p, (size_t)n_counts * 4, cudaMemcpyDeviceToHost, c->stream));
     if (str->n) CUDA_CHECK(cudaMemcpyAsync(had.data(), c->had.p, str->n, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(ctr_h, ctr, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctr_h, ctr, 24, cudaMemcpyDeviceToHost, c->stream));
+    if (want_regs) {
+        if (c->chain_v1) throw std::runtime_error("overlap records need the warp-per-group kernel (unset LRGE_CHAIN_V1)");
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        *rq->n_out = ctr_h[2];
+        const uint64_t m = std::min<uint64_t>(ctr_h[2], rq->cap);
+        if (m && rq->out) CUDA_CHECK(cudaMemcpyAsync(rq->out, c->regs.p, m * sizeof(RegOut), cudaMemcpyDeviceToHost, c->stream));
+    }
     c->prof.send(ST_D2H);
     c->prof.send(ST_TOTAL);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1083,6 +1096,39 @@ int lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_read
         if (opts->use_min_ref && sT.total_bases > sQ.total_bases) run_overlap(ctx, &sQ, &sT, MODE_INVERSE, *opts, counts, nullptr, stats);
         else run_overlap(ctx, &sT, &sQ, MODE_TWOSET, *opts, counts, had_mapping, stats);
         if (stats) stats->ms_total += ms;
+    });
+}
+
+int lrge_gpu_twoset_overlaps(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,
+                             lrge_overlap *out, uint64_t cap, uint64_t *n_out, uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats) {
+    if (!T || !Q || !n_out || (!out && cap) || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
+    return guarded(ctx, [&] {
+        lrge_staged &sT = ctx->tmp_a, &sQ = ctx->tmp_b;
+        stage_readset(ctx, T, &sT);
+        stage_readset(ctx, Q, &sQ);
+        RegsRequest rq; rq.out = out; rq.cap = cap; rq.n_out = n_out;
+        std::vector<uint32_t> tmp_counts;
+        if (opts->use_min_ref && sT.total_bases > sQ.total_bases) {
+            // inverse direction: records carry query = streamed (target-set) read, target = indexed (query-set) read
+            if (!counts) { tmp_counts.resize(Q->n); counts = tmp_counts.data(); }
+            run_overlap(ctx, &sQ, &sT, MODE_INVERSE, *opts, counts, nullptr, stats, &rq);
+        } else {
+            if (!counts) { tmp_counts.resize(Q->n); counts = tmp_counts.data(); }
+            run_overlap(ctx, &sT, &sQ, MODE_TWOSET, *opts, counts, had_mapping, stats, &rq);
+        }
+    });
+}
+
+int lrge_gpu_ava_overlaps(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts, lrge_overlap *out, uint64_t cap, uint64_t *n_out,
+                          uint32_t *counts, lrge_stats *stats) {
+    if (!R || !n_out || (!out && cap) || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
+    return guarded(ctx, [&] {
+        lrge_staged &sR = ctx->tmp_a;
+        stage_readset(ctx, R, &sR);
+        RegsRequest rq; rq.out = out; rq.cap = cap; rq.n_out = n_out;
+        std::vector<uint32_t> tmp_counts;
+        if (!counts) { tmp_counts.resize(R->n); counts = tmp_counts.data(); }
+        run_overlap(ctx, &sR, &sR, MODE_AVA, *opts, counts, nullptr, stats, &rq);
     });
 }
 

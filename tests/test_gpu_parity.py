@@ -237,3 +237,43 @@ def test_query_batching(ctx, monkeypatch):
     want, _ = oracle.ava_counts(R, "ont", threads=8)
     assert av.stats["n_batches"] > 5
     assert np.array_equal(av.counts, want)
+
+
+def _reg_set(regs, qidx=None):
+    if qidx is None:
+        return sorted(zip(regs["query"].tolist(), regs["target"].tolist(), regs["rev"].tolist(), regs["qs"].tolist(), regs["qe"].tolist(),
+                          regs["ts"].tolist(), regs["te"].tolist(), regs["score"].tolist(), regs["cnt"].tolist(), regs["mlen"].tolist(),
+                          regs["blen"].tolist()))
+    return sorted(zip(qidx.tolist(), regs["rid"].tolist(), regs["rev"].tolist(), regs["qs"].tolist(), regs["qe"].tolist(),
+                      regs["rs"].tolist(), regs["re"].tolist(), regs["score"].tolist(), regs["cnt"].tolist(), regs["mlen"].tolist(),
+                      regs["blen"].tolist()))
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_overlap_records_parity(ctx, platform):
+    """Every kept chain (PAF row: coordinates, score, cm, match/block length) against the oracle's mm_gen_regs output."""
+    T, Q = small_sets(nt=300, nq=120, mean=4000, gsize=250_000, err=readsim.ONT if platform == "ont" else readsim.HIFI)
+    ov, cnt = ctx.twoset_overlaps(T, Q, platform)
+    regs, qidx, _ = oracle.twoset_regs(T, Q, platform, threads=8, tie_mode=oracle.TIE_STABLE)
+    assert ov.shape[0] == regs.shape[0] > 0
+    assert _reg_set(ov) == _reg_set(regs, qidx)
+    plain = ctx.twoset_counts(T, Q, platform)
+    assert np.array_equal(cnt.counts, plain.counts) and np.array_equal(cnt.had_mapping, plain.had_mapping)
+    # the literal (unstable ksort) tie order gives the same rows here
+    regs2, qidx2, _ = oracle.twoset_regs(T, Q, platform, threads=8, tie_mode=oracle.TIE_KSORT)
+    assert _reg_set(regs2, qidx2) == _reg_set(regs, qidx)
+    # a small buffer reports how many records exist
+    small, _ = ctx.twoset_overlaps(T, Q, platform, cap=8)
+    assert small.shape[0] == ov.shape[0]
+    line = lrge_b200.paf_line(ov[0], Q, T)
+    assert line.count(b"\t") == 16 and b"tp:A:S" in line
+
+
+def test_ava_overlap_records_parity(ctx):
+    g = readsim.genome(150_000)
+    R = readsim.reads(g, 200, 3000, readsim.ONT, readsim.SEED_AVA, "r")
+    ov, cnt = ctx.ava_overlaps(R, "ont")
+    regs, qidx, _ = oracle.twoset_regs(R, R, "ont", threads=8, tie_mode=oracle.TIE_STABLE, dual=False)
+    assert _reg_set(ov) == _reg_set(regs, qidx)
+    want, _ = oracle.ava_counts(R, "ont", threads=8)
+    assert np.array_equal(cnt.counts, want)

@@ -97,3 +97,15 @@ def test_host_estimator_equals_oracle_bitwise():
     v = rng.uniform(1e5, 1e7, size=4999).astype(np.float32)
     v[::17] = np.inf
     assert lrge_b200.estimate_from(v, True, 0.15, 0.65) == oracle.estimate(v, True, 0.15, 0.65)
+
+
+def test_paf_format_golden():   # mapping.rs:197-420: the serialised record of the reference's own test
+    ov = np.zeros(1, lrge_b200.OVERLAP_DTYPE)
+    ov[0] = (0, 0, 1, 40, 237, 41, 238, 190, 59, 190, 197)
+    buf = ctypes.create_string_buffer(512)
+    q, t = b"SRR28370649.1", b"SRR28370649.7311"
+    n = lrge_b200.lib().lrge_paf_format(ov.ctypes.data, q, len(q), 4402, t, len(t), 5094, 0.0022, 56, buf, 512)
+    assert buf.raw[:n] == (b"SRR28370649.1\t4402\t40\t237\t-\tSRR28370649.7311\t5094\t41\t238\t190\t197\t0\t"
+                           b"tp:A:S\tcm:i:59\ts1:i:190\tdv:f:0.0022\trl:i:56")
+    n = lrge_b200.lib().lrge_paf_format(ov.ctypes.data, q, len(q), 4402, t, len(t), 5094, 0.0, 56, buf, 512)
+    assert buf.raw[:n].endswith(b"dv:f:0\trl:i:56")   # mapping.rs:415-419
