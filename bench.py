@@ -204,6 +204,20 @@ def run_ours(args):
     overlaps = int(last.counts.sum())          # counts are already reduced over all shards
     value = overlaps / (ms_per_step / 1e3)
 
+    # ---- per-kernel CUDA-event pass (EVERY rank: the sharded path contains NCCL collectives) ------------------
+    ctx.set_profiling(True)
+    prof_steps = 3
+    acc = {}
+    for i in range(prof_steps + 1):
+        flush.zero_()
+        torch.cuda.synchronize()
+        ctx.twoset_counts(sT, sQ, platform, **shard)
+        if i == 0:
+            continue                                   # first pass creates the events
+        for kt in ctx.kernel_times():
+            a = acc.setdefault(kt["name"], dict(ms=0.0, bytes=0.0, launches=0))
+            a["ms"] += kt["ms"]; a["bytes"] += kt["algorithmic_bytes"]; a["launches"] += kt["launches"]
+    ctx.set_profiling(False)
     # ---- e2e: host buffers through the C-ABI, H2D + D2H inside ------------------------------------------
     pT, bT = lrge_b200.pinned_copy(T)
     pQ, bQ = lrge_b200.pinned_copy(Q)
@@ -228,21 +242,8 @@ def run_ours(args):
         dist.destroy_process_group()
         return
     st = last.stats
-    # ---- roofline of the dominant kernel: one extra pass with per-kernel CUDA events (same stream, no host syncs) ----
+    # ---- roofline of the dominant kernel (rank 0) ----------------------------------------------------------------------
     peak, peak_src = measured_peak()
-    ctx.set_profiling(True)
-    prof_steps = 3
-    acc = {}
-    for i in range(prof_steps + 1):
-        flush.zero_()
-        torch.cuda.synchronize()
-        ctx.twoset_counts(sT, sQ, platform, **shard)
-        if i == 0:
-            continue                                   # first pass creates the events
-        for kt in ctx.kernel_times():
-            a = acc.setdefault(kt["name"], dict(ms=0.0, bytes=0.0, launches=0))
-            a["ms"] += kt["ms"]; a["bytes"] += kt["algorithmic_bytes"]; a["launches"] += kt["launches"]
-    ctx.set_profiling(False)
     kernels = []
     for name, a in acc.items():
         ms = a["ms"] / prof_steps

@@ -1,6 +1,7 @@
 // common.cuh -- shared device/host helpers for liblrge_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -23,6 +24,9 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
 }
 #define CUDA_CHECK(x) ::lrge::cuda_check((x), #x, __FILE__, __LINE__)
 
+// bytes currently held by DevBufs of this process (cudaMemGetInfo costs ~0.5 ms per call, so budgets use this instead)
+inline std::atomic<size_t> &dev_bytes_in_use() { static std::atomic<size_t> v{0}; return v; }
+
 // RAII device buffer (raw bytes); grows on demand, never shrinks while the context lives.
 struct DevBuf {
     void *p = nullptr;
@@ -32,7 +36,7 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) { cudaFree(p); dev_bytes_in_use() -= cap; }
         p = nullptr; cap = 0;
     }
     void reserve(size_t bytes) {
@@ -48,6 +52,7 @@ struct DevBuf {
             throw CudaError(buf);
         }
         cap = want;
+        dev_bytes_in_use() += cap;
     }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };

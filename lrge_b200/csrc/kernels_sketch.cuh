@@ -25,6 +25,7 @@ constexpr int SK_THREADS = 256;           // 8 warps x 1024 steps
 constexpr int WARP_POS = TILE_POS / (SK_THREADS / 32);
 constexpr int TILE_WORDS = (TILE_POS + PAD_BASES) / 32;   // 260 u64 of bases / u32 of mask
 constexpr int MAXW = 5;                   // minimizer window of both presets
+constexpr uint32_t SK_CAP = 768;          // single-pass staging: minimizers per 1024-step sub-tile (density 1/3 expected)
 
 __constant__ uint8_t c_nt4[256];
 
@@ -122,6 +123,18 @@ __global__ void __launch_bounds__(256) hpc_compress_kernel(const uint8_t *asc, c
 
 // ---- K1: sketch ---------------------------------------------------------------------------------
 
+// the same mix in 32-bit lanes: for 2k <= 32 every step only needs the low 2k bits of its operands
+__device__ __forceinline__ uint32_t hash32_masked(uint32_t key, uint32_t mask) {
+    key = (~key + (key << 21)) & mask;
+    key = key ^ key >> 24;
+    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = key ^ key >> 14;
+    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = key ^ key >> 28;
+    key = (key + (key << 31)) & mask;
+    return key;
+}
+
 __device__ __forceinline__ uint64_t hash64_masked(uint64_t key, uint64_t mask) {
     key = (~key + (key << 21)) & mask;
     key = key ^ key >> 24;
@@ -146,13 +159,19 @@ struct SketchArgs {
     const uint32_t *cend;     // HPC: original position of the last base of each step (indexed off[r] + t)
     const uint32_t *woff;     // EMIT: exclusive scan of wcnt (one entry per warp sub-tile)
     uint32_t *wcnt;           // COUNT: emissions per warp sub-tile
-    uint64_t *ox, *oy;        // EMIT: minimizers, (rid, position) order
+    uint64_t *ox, *oy;        // EMIT: minimizers, (rid, position) order (MODE 2: the staging arrays)
+    uint32_t cap;             // MODE 2: staging capacity per warp sub-tile
+    uint32_t *overflow;       // MODE 2: set when a sub-tile does not fit its slot
     int k;
 };
 
 // X32: without HPC the span byte is the constant k, so windows compare the 2k <= 31 bit hash alone (32-bit lanes).
-template <bool HPC, bool EMIT, bool X32>
+// MODE 0: count the pushes of every warp sub-tile (wcnt).  MODE 1: emit at the scanned offsets (woff).
+// MODE 2: single pass -- emit into a fixed-capacity staging slot per sub-tile and record wcnt; compact_kernel
+// then packs the slots.  A sub-tile that would exceed its slot raises *overflow (the host falls back to 0 + 1).
+template <bool HPC, int MODE, bool X32>
 __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
+    constexpr bool EMIT = MODE >= 1;
     static_assert(!(HPC && X32), "HPC spans vary: 64-bit compare");
     constexpr int W = MAXW;
     using XT = typename std::conditional<X32, uint32_t, uint64_t>::type;
@@ -177,7 +196,7 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const int64_t ws = s + (int64_t)warp * WARP_POS;          // first step of this warp's sub-tile
     if (s >= len) {                                            // HPC: tile lies past the compressed length
-        if (!EMIT && lane == 0) A.wcnt[tile * (SK_THREADS / 32) + warp] = 0;
+        if (MODE != 1 && lane == 0) A.wcnt[tile * (SK_THREADS / 32) + warp] = 0;
         return;
     }
     if (threadIdx.x == 0) {
@@ -198,7 +217,8 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
     XT xprev = XMAX;
     uint32_t zprev = 0;
     uint32_t total = 0;
-    uint32_t obase = EMIT ? A.woff[tile * (SK_THREADS / 32) + warp] : 0;
+    const uint64_t obase = MODE == 1 ? (uint64_t)A.woff[tile * (SK_THREADS / 32) + warp]
+                         : MODE == 2 ? (uint64_t)(tile * (SK_THREADS / 32) + warp) * A.cap : 0;
     const int n_chunks = WARP_POS / 32 + 1;                    // chunk 0 is warm-up (steps ws-32 .. ws-1)
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t p = ws + 32 * (c - 1) + lane;            // step handled by this lane
@@ -221,11 +241,21 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
                 const uint64_t hi = sW[wi], lo = sW[wi + 1];
                 const uint64_t v = sh ? (hi << sh) | (lo >> (64 - sh)) : hi;
                 const uint64_t fwd = v >> (64 - 2 * k);
-                uint64_t t = __brevll(~fwd);
-                t = ((t & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((t & 0x5555555555555555ULL) << 1);
-                const uint64_t rc = t >> (64 - 2 * k);
-                z = fwd < rc ? 0 : 1;
-                const uint64_t h = hash64_masked(z ? rc : fwd, kmask);
+                uint64_t h;
+                if (X32) {
+                    const uint32_t f32 = (uint32_t)fwd;
+                    uint32_t t = __brev(~f32);
+                    t = ((t & 0xAAAAAAAAu) >> 1) | ((t & 0x55555555u) << 1);
+                    const uint32_t rc = t >> (32 - 2 * k);
+                    z = f32 < rc ? 0 : 1;
+                    h = hash32_masked(z ? rc : f32, (uint32_t)kmask);
+                } else {
+                    uint64_t t = __brevll(~fwd);
+                    t = ((t & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((t & 0x5555555555555555ULL) << 1);
+                    const uint64_t rc = t >> (64 - 2 * k);
+                    z = fwd < rc ? 0 : 1;
+                    h = hash64_masked(z ? rc : fwd, kmask);
+                }
                 uint32_t span = k;
                 if (HPC) {
                     const int64_t e1 = A.cend[rbase + p];
@@ -285,8 +315,9 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
         }
         const uint32_t chunk_total = __shfl_sync(0xffffffffu, pre, 31);
         if (EMIT) {
-            uint32_t o = obase + total + pre - cnt;
+            uint64_t o = obase + total + pre - cnt;
             for (uint32_t e = 0; e < cnt; ++e, ++o) {
+                if (MODE == 2 && o - obase >= A.cap) break;            // slot full: overflow is flagged at the end
                 const int d = (int)((em >> (4 * e)) & 15);
                 const int64_t pt = p - d;
                 const uint64_t zz = (zcomb >> (32 + (int)lane - d)) & 1;
@@ -300,7 +331,21 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
         xprev = x;
         zprev = zb;
     }
-    if (!EMIT && lane == 0) A.wcnt[tile * (SK_THREADS / 32) + warp] = total;
+    if (MODE != 1 && lane == 0) {
+        A.wcnt[tile * (SK_THREADS / 32) + warp] = total;
+        if (MODE == 2 && total > A.cap) *A.overflow = 1;
+    }
+}
+
+// MODE 2 follow-up: pack the staging slots into the contiguous (rid, position)-ordered arrays. One warp per sub-tile.
+__global__ void __launch_bounds__(256) compact_kernel(const uint64_t *__restrict__ sx, const uint64_t *__restrict__ sy,
+                                                      const uint32_t *__restrict__ wcnt, const uint32_t *__restrict__ woff, uint32_t nw,
+                                                      uint32_t cap, uint64_t *__restrict__ ox, uint64_t *__restrict__ oy) {
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= nw) return;
+    const uint32_t n = wcnt[w], o = woff[w];
+    const uint64_t b = (uint64_t)w * cap;
+    for (uint32_t e = lane_id(); e < n; e += 32) { ox[o + e] = sx[b + e]; oy[o + e] = sy[b + e]; }
 }
 
 }  // namespace lrge

@@ -196,6 +196,9 @@ struct lrge_ctx {
     DevBuf anc, fp, glist, gmeta, pflag, regs;
     bool chain_v1 = false;                 // LRGE_CHAIN_V1=1: thread-per-pair debug kernel
     uint64_t max_anchors = 0;              // LRGE_MAX_ANCHORS=n: cap anchors per query batch
+    bool sketch_two_pass = false;          // LRGE_SKETCH_TWO_PASS=1: count + emit instead of stage + compact
+    size_t free_at_create = 0, held_at_create = 0;
+    DevBuf stg_x, stg_y, xflag;
     lrge_staged tmp_a, tmp_b;              // device staging of the host-buffer entry points (reused across calls)
     DevBuf rank_idx, rank_str, len_idx, len_str, pen, counts, had, counters;
     std::vector<int32_t> pen_host; int pen_k = 0, pen_bw = 0;
@@ -205,6 +208,13 @@ struct lrge_ctx {
 };
 
 namespace {
+
+// device memory still available to this context: what was free at creation minus what the process holds since
+size_t free_estimate(const lrge_ctx *c) {
+    const size_t used = dev_bytes_in_use().load();
+    const size_t base = c->free_at_create + c->held_at_create;
+    return base > used + (1ull << 30) ? base - used - (1ull << 30) : 0;
+}
 
 void *cub_temp(lrge_ctx *c, size_t bytes) { c->cub_tmp.reserve(bytes ? bytes : 16); return c->cub_tmp.p; }
 
@@ -338,27 +348,59 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
     if (tiles) {
         CUDA_CHECK(cudaMemsetAsync(c->wcnt.p, 0, ((size_t)nw + 1) * 4, c->stream));
         const bool x32 = !o.is_hpc && 2 * o.k <= 31;
-        KLAUNCH(c, "sketch_kernel<count>", nbases * 3 / 8, {
-            if (o.is_hpc) sketch_kernel<true, false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-            else if (x32) sketch_kernel<false, false, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-            else sketch_kernel<false, false, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        });
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream);
-        KLAUNCH(c, "cub::DeviceScan(u32)", 8.0 * nw,
-                cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream));
+        // single pass when the staging slots (SK_CAP minimizers per 1024-step sub-tile) fit comfortably
+        const uint64_t stage_bytes = (uint64_t)nw * SK_CAP * 16;
+        const size_t free_b = free_estimate(c);
+        bool single = !c->sketch_two_pass && stage_bytes <= (8ull << 30) && stage_bytes <= (free_b + c->stg_x.cap + c->stg_y.cap) / 4;
         uint32_t total = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&total, c->woff.as<uint32_t>() + nw, 4, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        out->M = total;
-        out->x.reserve(((size_t)total + 1) * 8);
-        out->y.reserve(((size_t)total + 1) * 8);
-        A.ox = out->x.as<uint64_t>(); A.oy = out->y.as<uint64_t>();
-        KLAUNCH(c, "sketch_kernel<emit>", nbases * 3 / 8 + 16.0 * total, {
-            if (o.is_hpc) sketch_kernel<true, true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-            else if (x32) sketch_kernel<false, true, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-            else sketch_kernel<false, true, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
-        });
+        if (single) {
+            c->stg_x.reserve(stage_bytes / 2 + 64); c->stg_y.reserve(stage_bytes / 2 + 64);
+            c->xflag.reserve(16);
+            CUDA_CHECK(cudaMemsetAsync(c->xflag.p, 0, 16, c->stream));
+            A.ox = c->stg_x.as<uint64_t>(); A.oy = c->stg_y.as<uint64_t>(); A.cap = SK_CAP; A.overflow = c->xflag.as<uint32_t>();
+            KLAUNCH(c, "sketch_kernel<stage>", nbases * 3 / 8 + 16.0 * nbases / 3, {
+                if (o.is_hpc) sketch_kernel<true, 2, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+                else if (x32) sketch_kernel<false, 2, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+                else sketch_kernel<false, 2, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+            });
+            KLAUNCH(c, "cub::DeviceScan(u32)", 8.0 * nw,
+                    cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream));
+            uint32_t ovf = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&total, c->woff.as<uint32_t>() + nw, 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(&ovf, c->xflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            if (ovf) single = false;                          // a very dense sub-tile: redo with the two-pass path
+            else {
+                out->M = total;
+                out->x.reserve(((size_t)total + 1) * 8);
+                out->y.reserve(((size_t)total + 1) * 8);
+                KLAUNCH(c, "compact_kernel", 32.0 * total,
+                        compact_kernel<<<(nw + 7) / 8, 256, 0, c->stream>>>(c->stg_x.as<uint64_t>(), c->stg_y.as<uint64_t>(), c->wcnt.as<uint32_t>(),
+                                                                           c->woff.as<uint32_t>(), nw, SK_CAP, out->x.as<uint64_t>(), out->y.as<uint64_t>()));
+            }
+        }
+        if (!single) {
+            KLAUNCH(c, "sketch_kernel<count>", nbases * 3 / 8, {
+                if (o.is_hpc) sketch_kernel<true, 0, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+                else if (x32) sketch_kernel<false, 0, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+                else sketch_kernel<false, 0, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+            });
+            KLAUNCH(c, "cub::DeviceScan(u32)", 8.0 * nw,
+                    cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(&total, c->woff.as<uint32_t>() + nw, 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            out->M = total;
+            out->x.reserve(((size_t)total + 1) * 8);
+            out->y.reserve(((size_t)total + 1) * 8);
+            A.ox = out->x.as<uint64_t>(); A.oy = out->y.as<uint64_t>();
+            KLAUNCH(c, "sketch_kernel<emit>", nbases * 3 / 8 + 16.0 * total, {
+                if (o.is_hpc) sketch_kernel<true, 1, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+                else if (x32) sketch_kernel<false, 1, true><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+                else sketch_kernel<false, 1, false><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+            });
+        }
         // per-read minimizer offsets: woff at the first warp sub-tile of every read
         KLAUNCH(c, "gather_kernel", 12.0 * n,
                 gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), c->tile_off.as<uint32_t>(),
@@ -769,8 +811,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     S.n_anchors = A_total;
 
     // batches of queries bounded by anchor memory
-    size_t free_b = 0, total_b = 0;
-    CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t free_b = free_estimate(c);
     size_t reusable = c->akey0.cap + c->akey1.cap + c->aval0.cap + c->aval1.cap + c->flags.cap + c->pstart.cap +
                       c->f.cap + c->p.cap + c->t.cap + c->pair_res.cap;
     reusable += c->anc.cap + c->fp.cap;
@@ -1033,9 +1074,11 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         c->device = device;
         { const char *e = getenv("LRGE_CHAIN_V1"); c->chain_v1 = e && e[0] == '1'; }
         { const char *e = getenv("LRGE_MAX_ANCHORS"); c->max_anchors = e ? strtoull(e, nullptr, 10) : 0; }
+        { const char *e = getenv("LRGE_SKETCH_TWO_PASS"); c->sketch_two_pass = e && e[0] == '1'; }
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->prof.s = c->stream;
         c->prof.reset();
+        { size_t f = 0, t = 0; CUDA_CHECK(cudaMemGetInfo(&f, &t)); c->free_at_create = f; c->held_at_create = dev_bytes_in_use().load(); }
         CUDA_CHECK(cudaMemcpyToSymbol(c_nt4, kNt4, 256));
         *out = c.release();
         return LRGE_OK;

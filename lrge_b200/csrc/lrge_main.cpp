@@ -1,0 +1,163 @@
+// lrge-b200 -- command-line driver with the lrge CLI's flags (lrge/src/cli.rs:9-87, main.rs:32-121) over liblrge_b200.so.
+//
+// Differences, on purpose: plain FASTA/FASTQ only (no gz/BAM: io.rs is out of scope); the random subsample uses this
+// file's own generator, so `-s SEED` is repeatable here but does not pick the reads the Rust `rand` crate would
+// (lib.rs:189-204); `-t`, `-C`, `-D` are accepted and ignored (no threads, no temp files on this path); and
+// `--platform` IS forwarded (the reference CLI parses it but never passes it on, main.rs:56-85).
+#include "../../include/lrge_b200.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Args {
+    std::string input, output = "-", platform = "ont";
+    size_t target = lrge::DEFAULT_TARGET_NUM_READS, query = lrge::DEFAULT_QUERY_NUM_READS, num = 0;
+    bool filter_contained = false, with_infinity = false, precise = false, use_min_ref = false, seeded = false;
+    uint64_t seed = 0;
+    float q1 = lrge::LOWER_QUANTILE, q3 = lrge::UPPER_QUANTILE, max_overhang_ratio = 0.2f;
+    int device = 0, quiet = 0;
+};
+
+[[noreturn]] void usage(int rc) {
+    fprintf(rc ? stderr : stdout,
+            "Usage: lrge-b200 [OPTIONS] <INPUT>\n"
+            "  -o, --output <OUTPUT>        output file for the estimate [default: -]\n"
+            "  -T, --target <INT>           target number of reads (two-set strategy) [default: 10000]\n"
+            "  -Q, --query <INT>            query number of reads (two-set strategy) [default: 5000]\n"
+            "  -n, --num <INT>              number of reads (all-vs-all strategy)\n"
+            "  -P, --platform <ont|pb>      sequencing platform [default: ont]\n"
+            "  -F, --filter-contained       exclude overlaps for internal matches\n"
+            "  -s, --seed <INT>             random seed\n"
+            "  -8, --inf                    median over all estimates, including infinite ones\n"
+            "  -f, --float-my-boat          print the estimate as a floating point number\n"
+            "      --q1 <FLOAT> --q3 <FLOAT>  quantiles of the reported range [default: 0.15 0.65]\n"
+            "      --max-overhang-ratio <FLOAT> [default: 0.2]\n"
+            "      --use-min-ref            index the smaller of the two sets\n"
+            "      --device <INT>           CUDA device [default: 0]\n"
+            "  -t/-C/-D                     accepted for compatibility, ignored\n");
+    exit(rc);
+}
+
+Args parse(int argc, char **argv) {
+    Args a;
+    auto need = [&](int &i) -> const char * { if (i + 1 >= argc) usage(2); return argv[++i]; };
+    for (int i = 1; i < argc; ++i) {
+        const std::string s = argv[i];
+        if (s == "-h" || s == "--help") usage(0);
+        else if (s == "-o" || s == "--output") a.output = need(i);
+        else if (s == "-T" || s == "--target") a.target = strtoull(need(i), nullptr, 10);
+        else if (s == "-Q" || s == "--query") a.query = strtoull(need(i), nullptr, 10);
+        else if (s == "-n" || s == "--num") a.num = strtoull(need(i), nullptr, 10);
+        else if (s == "-P" || s == "--platform") a.platform = need(i);
+        else if (s == "-F" || s == "--filter-contained") a.filter_contained = true;
+        else if (s == "-s" || s == "--seed") { a.seed = strtoull(need(i), nullptr, 10); a.seeded = true; }
+        else if (s == "-8" || s == "--inf") a.with_infinity = true;
+        else if (s == "-f" || s == "--float-my-boat") a.precise = true;
+        else if (s == "--q1") a.q1 = strtof(need(i), nullptr);
+        else if (s == "--q3") a.q3 = strtof(need(i), nullptr);
+        else if (s == "--max-overhang-ratio") a.max_overhang_ratio = strtof(need(i), nullptr);
+        else if (s == "--use-min-ref") a.use_min_ref = true;
+        else if (s == "--device") a.device = atoi(need(i));
+        else if (s == "-t" || s == "--threads" || s == "-D" || s == "--temp") need(i);
+        else if (s == "-C" || s == "--keep-temp") {}
+        else if (s.rfind("-q", 0) == 0) a.quiet = (int)s.size() - 1;
+        else if (s.rfind("-v", 0) == 0) {}
+        else if (!s.empty() && s[0] == '-' && s != "-") { fprintf(stderr, "error: unexpected argument '%s'\n", s.c_str()); usage(2); }
+        else a.input = s;
+    }
+    if (a.input.empty()) usage(2);
+    // cli.rs: --q1 in [0, 0.5], --q3 in [0.5, 1], ratio in [0, 1]
+    if (!(a.q1 >= 0.0f && a.q1 <= 0.5f) || !(a.q3 >= 0.5f && a.q3 <= 1.0f) || !(a.max_overhang_ratio >= 0.0f && a.max_overhang_ratio <= 1.0f)) {
+        fprintf(stderr, "error: quantile or ratio out of range\n");
+        exit(2);
+    }
+    return a;
+}
+
+// k unique indices out of [0, n), in random order (stands in for lib.rs:189-204)
+std::vector<uint32_t> unique_random_set(size_t k, uint32_t n, uint64_t seed) {
+    std::vector<uint32_t> idx(n);
+    std::iota(idx.begin(), idx.end(), 0u);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ULL + 0xD1B54A32D192ED03ULL;
+    auto next = [&]() { uint64_t z = (x += 0x9E3779B97F4A7C15ULL); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; return z ^ (z >> 31); };
+    for (size_t i = 0; i < k; ++i) { const size_t j = i + (size_t)(next() % (n - i)); std::swap(idx[i], idx[j]); }
+    idx.resize(k);
+    return idx;
+}
+
+std::string format_estimate(float est) {                 // utils.rs:18-47
+    if (std::isinf(est)) return "\xE2\x88\x9E bp";
+    const char *units[] = {"bp", "kbp", "Mbp", "Gbp", "Tbp", "Pbp"};
+    float value = est; const char *suffix = "bp";
+    for (int p = 0; p < 6; ++p) {
+        const float thr = std::pow(10.0f, (float)(p * 3));
+        if (est >= thr) { value = est / thr; suffix = units[p]; } else break;
+    }
+    char buf[64]; snprintf(buf, sizeof buf, "%.2f %s", value, suffix);
+    return buf;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    const Args a = parse(argc, argv);
+    try {
+        const lrge::Platform platform = lrge::platform_from_str(a.platform);
+        lrge::ReadSet all = lrge::ReadSet::from_fastx(a.input);
+        const uint32_t n_fq = all.size();
+        const uint64_t seed = a.seeded ? a.seed : (uint64_t)time(nullptr);
+        auto take = [&](const std::vector<uint32_t> &sorted_idx) {
+            lrge::ReadSet rs;
+            for (uint32_t i : sorted_idx)
+                rs.push(all.names.substr(all.name_off[i], all.name_off[i + 1] - all.name_off[i]),
+                        std::string(all.bases.begin() + all.off[i], all.bases.begin() + all.off[i + 1]));
+            return rs;
+        };
+        lrge::EstimateResult res;
+        if (a.num) {                                              // AvaStrategy (ava.rs:108-161)
+            size_t n = a.num;
+            if (n_fq < n) { if (a.quiet < 1) fprintf(stderr, "[WARN] only %u reads in input, using all\n", n_fq); n = n_fq; }
+            auto idx = unique_random_set(n, n_fq, seed);
+            std::sort(idx.begin(), idx.end());
+            auto strat = lrge::AvaStrategy::Builder().platform(platform).remove_internal(a.filter_contained)
+                             .max_overhang_ratio(a.max_overhang_ratio).device(a.device).build(take(idx));
+            res = strat.estimate(!a.with_infinity, a.q1, a.q3);
+        } else {                                                  // TwoSetStrategy (twoset.rs:122-201)
+            size_t T = a.target, Q = a.query;
+            if (n_fq <= Q) throw lrge::LrgeError(LRGE_ERR_TOO_FEW_READS, "Too few reads requested: input has <= query number of reads");
+            if (n_fq < T + Q) { T = n_fq - Q; if (a.quiet < 1) fprintf(stderr, "[WARN] using %zu target reads\n", T); }
+            auto idx = unique_random_set(T + Q, n_fq, seed);
+            // split_into_hashsets pops from the END: the last T indices are the targets (twoset.rs:632-652)
+            std::vector<uint32_t> t(idx.end() - T, idx.end()), q(idx.begin(), idx.end() - T);
+            std::sort(t.begin(), t.end()); std::sort(q.begin(), q.end());
+            auto strat = lrge::TwoSetStrategy::Builder().platform(platform).remove_internal(a.filter_contained)
+                             .max_overhang_ratio(a.max_overhang_ratio).use_min_ref(a.use_min_ref).device(a.device).build(take(t), take(q));
+            res = strat.estimate(!a.with_infinity, a.q1, a.q3);
+        }
+        if (!res.estimate) {
+            fprintf(stderr, "Error: %s\n", a.with_infinity ? "No estimates were generated" : "No finite estimates were generated");
+            return 1;
+        }
+        if (a.quiet < 1) {
+            std::string msg = "Estimated genome size: " + format_estimate(*res.estimate);
+            if (res.lower && res.upper) msg += " (IQR: " + format_estimate(*res.lower) + " - " + format_estimate(*res.upper) + ")";
+            fprintf(stderr, "[INFO] %s\n", msg.c_str());
+        }
+        FILE *out = a.output == "-" ? stdout : fopen(a.output.c_str(), "w");
+        if (!out) throw lrge::LrgeError(LRGE_ERR_IO, "IO error: cannot open " + a.output);
+        if (a.precise) fprintf(out, "%g\n", (double)*res.estimate); else fprintf(out, "%.0f\n", (double)*res.estimate);
+        if (out != stdout) fclose(out);
+        return 0;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+}

@@ -52,6 +52,21 @@ def test_sketch_parity_ambiguous_and_short(ctx, platform):
     recs += [("tile%d" % L, bytes(rng.choice(list(b"ACGT"), size=L).tolist())) for L in (1023, 1024, 1025, 8191, 8192, 8193, 16384, 20000)]
     recs += [("rep", b"ACGTTGCA" * 300)]
     check_minimizers(ctx, ReadSet.from_records(recs), platform)
+    # periodic reads emit a minimizer at (almost) every step: the single-pass staging slots overflow and the
+    # library must fall back to its count + emit passes
+    recs += [("dense2", b"AC" * 3000), ("dense3", b"ACG" * 2500), ("polyA", b"A" * 4000), ("polyAC", (b"AAA" + b"CC") * 1500)]
+    check_minimizers(ctx, ReadSet.from_records(recs), platform)
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_sketch_two_pass_path(monkeypatch, platform):
+    monkeypatch.setenv("LRGE_SKETCH_TWO_PASS", "1")
+    c1 = lrge_b200.Context(0)
+    try:
+        T, _ = small_sets(err=readsim.ONT if platform == "ont" else readsim.HIFI)
+        check_minimizers(c1, T, platform)
+    finally:
+        c1.close()
 
 
 @pytest.mark.parametrize("platform", ["ont", "pb"])
