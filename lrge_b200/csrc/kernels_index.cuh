@@ -56,6 +56,66 @@ __global__ void occ_hist_kernel(const uint64_t *__restrict__ tx, uint64_t M, uns
     if ((threadIdx.x & 31) == 0 && my_keys) atomicAdd(n_keys, (unsigned long long)my_keys);
 }
 
+// K2b + K3 fused: one coalesced pass over the sorted keys writes the bucket table and the occurrence histogram.
+// Run lengths come from the warp's run-start ballot; only the last run of each warp may continue into the next
+// warp's elements and is finished by galloping.  hist[OCC_BINS] bins + hist[OCC_BINS] = number of keys.
+__global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restrict__ tx, uint64_t M, int shift, uint32_t nb,
+                                                         uint32_t *__restrict__ boff, unsigned long long *hist) {
+    __shared__ unsigned int sh[OCC_BINS];
+    for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned int my_keys = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (M + 1 + stride - 1) / stride;
+    for (uint64_t r = 0; r < rounds; ++r) {
+        const uint64_t i = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // warp-contiguous
+        const bool in = i < M;
+        const uint64_t x = in ? tx[i] : 0;
+        uint64_t xp = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0 && i > 0 && i <= M) xp = tx[i - 1];
+        // bucket table: boff[b] = first i with bucket >= b
+        if (i <= M) {
+            const int64_t b_prev = i == 0 ? -1 : (int64_t)(xp >> shift);
+            const int64_t b_cur = i == M ? (int64_t)nb : (int64_t)(x >> shift);
+            for (int64_t b = b_prev + 1; b <= b_cur; ++b) boff[b] = (uint32_t)i;
+        }
+        // occurrence of every key that STARTS in this warp
+        const bool start = in && (i == 0 || (xp >> 8) != (x >> 8));
+        const uint32_t S = __ballot_sync(0xffffffffu, start);
+        const uint32_t valid = __ballot_sync(0xffffffffu, in);
+        uint64_t n = 0;
+        if (start) {
+            const uint32_t above = lane == 31 ? 0u : (S >> (lane + 1)) << (lane + 1);
+            if (above) n = (uint32_t)(__ffs(above) - 1) - lane;
+            else {
+                // the run reaches the end of this warp's elements: finish it by galloping
+                const uint32_t nvalid = __popc(valid);
+                uint64_t lo = i + (nvalid - 1 - lane);                 // last element of the warp, same key
+                const uint64_t key = x >> 8;
+                uint64_t step = 1;
+                while (lo + step < M && (tx[lo + step] >> 8) == key) { lo += step; step <<= 1; }
+                uint64_t hi = lo + step < M ? lo + step : M;
+                while (hi - lo > 1) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if ((tx[mid] >> 8) == key) lo = mid; else hi = mid;
+                }
+                n = hi - i;
+            }
+            ++my_keys;
+        }
+        // most keys occur once or twice: add those bins once per warp instead of 32 same-address atomics
+        const uint32_t n1 = __ballot_sync(0xffffffffu, n == 1), n2 = __ballot_sync(0xffffffffu, n == 2);
+        if (lane == 0) { if (n1) atomicAdd(&sh[1], (unsigned)__popc(n1)); if (n2) atomicAdd(&sh[2], (unsigned)__popc(n2)); }
+        if (n > 2) atomicAdd(&sh[n < OCC_BINS - 1 ? n : OCC_BINS - 1], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+    for (int o = 16; o > 0; o >>= 1) my_keys += __shfl_down_sync(0xffffffffu, my_keys, o);
+    if (lane == 0 && my_keys) atomicAdd(&hist[OCC_BINS], (unsigned long long)my_keys);
+}
+
 // Run lengths that fell into the overflow bin, collected for an exact order statistic on the host
 // (only reached when the mid_occ rank lands among keys occurring >= OCC_BINS-1 times).
 __global__ void occ_overflow_kernel(const uint64_t *__restrict__ tx, uint64_t M, uint32_t *out, unsigned long long *n_out,
@@ -90,6 +150,19 @@ struct IndexView {
 __device__ __forceinline__ uint32_t index_lookup(const IndexView &I, uint64_t key, uint32_t cap, uint32_t *start) {
     const uint64_t b = (key << 8) >> I.shift;
     uint32_t lo = I.boff[b], hi = I.boff[b + 1];
+    if (hi - lo <= 8) {
+        // small bucket (the usual case, ~6 entries): fetch it with independent loads -- one memory round trip instead
+        // of a chain of dependent probes -- and match in registers.  tx is allocated with >= 32 entries of slack.
+        uint64_t e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = I.tx[lo + j];
+        uint32_t n = 0, first = 0;
+#pragma unroll
+        for (int j = 7; j >= 0; --j)
+            if (lo + j < hi && (e[j] >> 8) == key) { ++n; first = j; }
+        *start = lo + first;
+        return n > cap + 1 ? cap + 1 : n;
+    }
     // lower bound of key in [lo, hi)
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;

@@ -437,15 +437,12 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     const uint32_t nb = 1u << bits;
     const int shift = 8 + 2 * o.k - bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
-    KLAUNCH(c, "bucket_bounds_kernel", 8.0 * M + 4.0 * nb,
-            bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>()));
-    // occurrence histogram -> mid_occ (mm_idx_cal_max_occ + mm_mapopt_update)
+    // bucket table + occurrence histogram -> mid_occ (mm_idx_cal_max_occ + mm_mapopt_update), one pass over the keys
     c->hist.reserve((OCC_BINS + 2) * 8);
     CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));
     unsigned long long *hist = c->hist.as<unsigned long long>();
-    if (M) {
-        KLAUNCH(c, "occ_hist_kernel", 8.0 * M, occ_hist_kernel<<<148 * 4, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, hist, hist + OCC_BINS));
-    }
+    KLAUNCH(c, "index_post_kernel", 8.0 * M + 4.0 * nb,
+            index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), hist));
     std::vector<unsigned long long> h(OCC_BINS + 2);
     CUDA_CHECK(cudaMemcpyAsync(h.data(), hist, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
