@@ -60,7 +60,8 @@ __global__ void occ_hist_kernel(const uint64_t *__restrict__ tx, uint64_t M, uns
 // Run lengths come from the warp's run-start ballot; only the last run of each warp may continue into the next
 // warp's elements and is finished by galloping.  hist[OCC_BINS] bins + hist[OCC_BINS] = number of keys.
 __global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restrict__ tx, uint64_t M, int shift, uint32_t nb,
-                                                         uint32_t *__restrict__ boff, unsigned long long *hist) {
+                                                         uint32_t *__restrict__ boff, uint32_t *__restrict__ tk32,
+                                                         unsigned long long *hist) {
     __shared__ unsigned int sh[OCC_BINS];
     for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -72,35 +73,43 @@ __global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restr
         const uint64_t i = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // warp-contiguous
         const bool in = i < M;
         const uint64_t x = in ? tx[i] : 0;
+        // the element after the warp's last one, fetched together with the main load (ends most boundary runs)
+        const uint64_t xnext = (lane == 31 && i + 1 < M) ? tx[i + 1] : 0;
         uint64_t xp = __shfl_up_sync(0xffffffffu, x, 1);
         if (lane == 0 && i > 0 && i <= M) xp = tx[i - 1];
+        if (in) tk32[i] = (uint32_t)(x >> 8);                     // compact lookup keys (low 32 bits of the hash)
         // bucket table: boff[b] = first i with bucket >= b
         if (i <= M) {
-            const int64_t b_prev = i == 0 ? -1 : (int64_t)(xp >> shift);
-            const int64_t b_cur = i == M ? (int64_t)nb : (int64_t)(x >> shift);
-            for (int64_t b = b_prev + 1; b <= b_cur; ++b) boff[b] = (uint32_t)i;
+            const int32_t b_prev = i == 0 ? -1 : (int32_t)(xp >> shift);
+            const int32_t b_cur = i == M ? (int32_t)nb : (int32_t)(x >> shift);
+            for (int32_t b = b_prev + 1; b <= b_cur; ++b) boff[b] = (uint32_t)i;
         }
         // occurrence of every key that STARTS in this warp
         const bool start = in && (i == 0 || (xp >> 8) != (x >> 8));
         const uint32_t S = __ballot_sync(0xffffffffu, start);
         const uint32_t valid = __ballot_sync(0xffffffffu, in);
+        const uint64_t key_next = __shfl_sync(0xffffffffu, xnext, 31) >> 8;
+        const bool full_warp = valid == 0xffffffffu;
         uint64_t n = 0;
         if (start) {
             const uint32_t above = lane == 31 ? 0u : (S >> (lane + 1)) << (lane + 1);
             if (above) n = (uint32_t)(__ffs(above) - 1) - lane;
             else {
-                // the run reaches the end of this warp's elements: finish it by galloping
                 const uint32_t nvalid = __popc(valid);
-                uint64_t lo = i + (nvalid - 1 - lane);                 // last element of the warp, same key
+                const uint64_t last = i + (nvalid - 1 - lane);         // last element of the warp, same key
                 const uint64_t key = x >> 8;
-                uint64_t step = 1;
-                while (lo + step < M && (tx[lo + step] >> 8) == key) { lo += step; step <<= 1; }
-                uint64_t hi = lo + step < M ? lo + step : M;
-                while (hi - lo > 1) {
-                    const uint64_t mid = (lo + hi) >> 1;
-                    if ((tx[mid] >> 8) == key) lo = mid; else hi = mid;
+                if (!full_warp || last + 1 >= M || key_next != key) n = last - i + 1;
+                else {
+                    // the run continues past the prefetched element: finish it by galloping
+                    uint64_t lo = last + 1, step = 1;
+                    while (lo + step < M && (tx[lo + step] >> 8) == key) { lo += step; step <<= 1; }
+                    uint64_t hi = lo + step < M ? lo + step : M;
+                    while (hi - lo > 1) {
+                        const uint64_t mid = (lo + hi) >> 1;
+                        if ((tx[mid] >> 8) == key) lo = mid; else hi = mid;
+                    }
+                    n = hi - i;
                 }
-                n = hi - i;
             }
             ++my_keys;
         }
@@ -114,6 +123,12 @@ __global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restr
         if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
     for (int o = 16; o > 0; o >>= 1) my_keys += __shfl_down_sync(0xffffffffu, my_keys, o);
     if (lane == 0 && my_keys) atomicAdd(&hist[OCC_BINS], (unsigned long long)my_keys);
+}
+
+// sharded path: the compact lookup keys alone
+__global__ void tk32_kernel(const uint64_t *__restrict__ tx, uint64_t M, uint32_t *__restrict__ tk32) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) tk32[i] = (uint32_t)(tx[i] >> 8);
 }
 
 // Run lengths that fell into the overflow bin, collected for an exact order statistic on the host
@@ -138,6 +153,8 @@ __global__ void occ_overflow_kernel(const uint64_t *__restrict__ tx, uint64_t M,
 
 struct IndexView {
     const uint64_t *tx;      // sorted by tx>>8
+    const uint32_t *tk32;    // low 32 bits of tx>>8: inside a bucket (top hash bits equal, 2k - bits <= 32) they order and
+                             // identify keys exactly, at half the bytes per probe
     const uint64_t *ty;
     const uint32_t *boff;
     uint64_t M;
@@ -150,29 +167,31 @@ struct IndexView {
 __device__ __forceinline__ uint32_t index_lookup(const IndexView &I, uint64_t key, uint32_t cap, uint32_t *start) {
     const uint64_t b = (key << 8) >> I.shift;
     uint32_t lo = I.boff[b], hi = I.boff[b + 1];
+    const uint32_t k32 = (uint32_t)key;
     if (hi - lo <= 8) {
         // small bucket (the usual case, ~6 entries): fetch it with independent loads -- one memory round trip instead
-        // of a chain of dependent probes -- and match in registers.  tx is allocated with >= 32 entries of slack.
-        uint64_t e[8];
+        // of a chain of dependent probes -- and match in registers.  tk32 is allocated with >= 64 entries of slack.
+        uint32_t e[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = I.tx[lo + j];
+        for (int j = 0; j < 8; ++j) e[j] = I.tk32[lo + j];
         uint32_t n = 0, first = 0;
 #pragma unroll
         for (int j = 7; j >= 0; --j)
-            if (lo + j < hi && (e[j] >> 8) == key) { ++n; first = j; }
+            if (lo + j < hi && e[j] == k32) { ++n; first = j; }
         *start = lo + first;
         return n > cap + 1 ? cap + 1 : n;
     }
     // lower bound of key in [lo, hi)
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
-        if ((I.tx[mid] >> 8) < key) lo = mid + 1; else hi = mid;
+        if (I.tk32[mid] < k32) lo = mid + 1; else hi = mid;
     }
     *start = lo;
-    if (lo >= I.M || (I.tx[lo] >> 8) != key) return 0;
+    if (lo >= I.M || lo >= I.boff[b + 1] || I.tk32[lo] != k32) return 0;
     uint32_t n = 1;
-    const uint64_t lim = (uint64_t)lo + cap + 1 < I.M ? (uint64_t)lo + cap + 1 : I.M;
-    while ((uint64_t)lo + n < lim && (I.tx[lo + n] >> 8) == key) ++n;
+    const uint64_t lim0 = (uint64_t)lo + cap + 1 < I.M ? (uint64_t)lo + cap + 1 : I.M;
+    const uint64_t lim = lim0 < I.boff[b + 1] ? lim0 : I.boff[b + 1];
+    while ((uint64_t)lo + n < lim && I.tk32[lo + n] == k32) ++n;
     return n;
 }
 

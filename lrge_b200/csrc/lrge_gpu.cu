@@ -21,6 +21,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -169,6 +170,9 @@ struct lrge_staged {
     std::vector<std::pair<uint64_t, uint32_t>> name_hash;   // (FNV-1a of the name, read), sorted: cheap equality joins
     bool names_unique = true;
     std::vector<uint32_t> lex_rank;                        // lazily: lexicographic rank of each name (AVA's strcmp order)
+    cudaEvent_t ready = nullptr;                           // async staging: recorded on the copy stream after the H2D copies
+    bool pending = false;
+    ~lrge_staged() { if (ready) cudaEventDestroy(ready); }
 };
 
 struct Sketch {                            // minimizers of a read set, (rid, position) order
@@ -179,6 +183,7 @@ struct Sketch {                            // minimizers of a read set, (rid, po
 struct lrge_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // H2D staging of host read sets, overlapped with compute on `stream`
     std::string err;
     uint32_t launches = 0;
     Prof prof;
@@ -189,7 +194,7 @@ struct lrge_ctx {
     DevBuf cub_tmp;
     // index
     Sketch sk_idx, sk_str;
-    DevBuf tx, ty, boff, hist;
+    DevBuf tx, ty, boff, hist, tk32;
     // seed / anchors
     DevBuf flt, hstart, hn, acnt, aoff, qaoff;
     DevBuf akey0, akey1, aval0, aval1, flags, pstart, npairs, f, p, t, pair_res;
@@ -223,13 +228,16 @@ template <typename T> void h2d(lrge_ctx *c, DevBuf &d, const T *src, size_t n) {
     if (n) CUDA_CHECK(cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
 }
 
-void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s) {
+// Copies a host read set to HBM on the copy stream.  async: return without waiting -- the first kernel that touches the
+// set waits for `ready` on the compute stream, so the copy of the second set overlaps the sketch of the first.
+void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool async = false) {
     s->n = rs->n;
     s->total_bases = rs->n ? rs->off[rs->n] - rs->off[0] : 0;
+    s->pending = false;
     // start the big copy first; the host-side bookkeeping below overlaps with it
     s->asc.reserve(s->total_bases + 64);
     if (s->total_bases)
-        CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + rs->off[0], s->total_bases, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + rs->off[0], s->total_bases, cudaMemcpyHostToDevice, c->copy_stream));
     s->h_off.assign(rs->off, rs->off + rs->n + 1);
     if (rs->n && rs->off[0] != 0) {
         const uint64_t b = rs->off[0];
@@ -239,8 +247,8 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s) {
     s->max_len = 0;
     for (uint32_t i = 0; i < rs->n; ++i) {
         const uint64_t l = s->h_off[i + 1] - s->h_off[i];
-        if (l == 0) { cudaStreamSynchronize(c->stream); throw std::invalid_argument("MapError: Sequence is empty"); }   // aligner.rs:214-216
-        if (l >= (1u << 24)) { cudaStreamSynchronize(c->stream); throw std::length_error("reads of 16 Mbases or more are not supported"); }
+        if (l == 0) { cudaStreamSynchronize(c->copy_stream); throw std::invalid_argument("MapError: Sequence is empty"); }   // aligner.rs:214-216
+        if (l >= (1u << 24)) { cudaStreamSynchronize(c->copy_stream); throw std::length_error("reads of 16 Mbases or more are not supported"); }
         s->h_len[i] = (uint32_t)l;
         s->max_len = std::max(s->max_len, (uint32_t)l);
     }
@@ -263,8 +271,13 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s) {
             const uint32_t la = s->name_off[a + 1] - s->name_off[a], lb = s->name_off[b + 1] - s->name_off[b];
             if (la == lb && memcmp(s->names.data() + s->name_off[a], s->names.data() + s->name_off[b], la) == 0) s->names_unique = false;
         }
-    h2d(c, s->off, s->h_off.data(), s->h_off.size());
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    s->off.reserve(std::max<size_t>(s->h_off.size(), 1) * 8);
+    CUDA_CHECK(cudaMemcpyAsync(s->off.p, s->h_off.data(), s->h_off.size() * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    if (async) {
+        if (!s->ready) CUDA_CHECK(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(s->ready, c->copy_stream));
+        s->pending = true;
+    } else CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
 }
 
 __global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t mul, uint32_t n,
@@ -298,6 +311,7 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
     }
     tile_off[n] = tiles;
     const uint64_t padded_words = (pos + TILE_POS + 2 * PAD_BASES) / 32 + 8;
+    if (s->pending) CUDA_CHECK(cudaStreamWaitEvent(c->stream, s->ready, 0));
     c->prof.sbegin(ST_PACK);
     uint64_t nbases = 0;
     for (uint32_t i = 0; i < n; ++i) nbases += slen[i];
@@ -434,6 +448,7 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     // ~8 entries per bucket: the table (4 B x 2^bits) stays L2-resident, a lookup bisects <= 3 steps
     int bits = 8;
     while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
+    if (bits < 2 * o.k - 32) bits = 2 * o.k - 32;              // tk32: the in-bucket part of a key must fit 32 bits
     const uint32_t nb = 1u << bits;
     const int shift = 8 + 2 * o.k - bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
@@ -441,8 +456,9 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     c->hist.reserve((OCC_BINS + 2) * 8);
     CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));
     unsigned long long *hist = c->hist.as<unsigned long long>();
-    KLAUNCH(c, "index_post_kernel", 8.0 * M + 4.0 * nb,
-            index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), hist));
+    c->tk32.reserve((M + 64) * 4);
+    KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
+            index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(), hist));
     std::vector<unsigned long long> h(OCC_BINS + 2);
     CUDA_CHECK(cudaMemcpyAsync(h.data(), hist, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -470,7 +486,7 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     }
     if (mid_occ < o.min_mid_occ) mid_occ = o.min_mid_occ;
     if (o.max_mid_occ > o.min_mid_occ && mid_occ > o.max_mid_occ) mid_occ = o.max_mid_occ;
-    B.view.tx = c->tx.as<uint64_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.tx = c->tx.as<uint64_t>(); B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
     B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
     B.mid_occ = mid_occ; B.n_keys = n_keys;
     return B;
@@ -500,12 +516,15 @@ BuiltIndex build_index_sharded(lrge_ctx *c, const Sketch &sk, const MapOpt &o, l
     }
     int bits = 8;
     while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
+    if (bits < 2 * o.k - 32) bits = 2 * o.k - 32;              // tk32: the in-bucket part of a key must fit 32 bits
     const uint32_t nb = 1u << bits;
     const int shift = 8 + 2 * o.k - bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
     KLAUNCH(c, "bucket_bounds_kernel", 8.0 * M + 4.0 * nb,
             bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>()));
 
+    c->tk32.reserve((M + 64) * 4);
+    if (M) KLAUNCH(c, "tk32_kernel", 12.0 * M, tk32_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, c->tk32.as<uint32_t>()));
     // local run-length encoding: (key, count) per distinct local key
     c->flags.reserve(M + 1);
     c->pstart.reserve((M + 2) * 4);
@@ -630,7 +649,7 @@ BuiltIndex build_index_sharded(lrge_ctx *c, const Sketch &sk, const MapOpt &o, l
     NCCL_CHECK(ncclAllGather(c->blist.p, c->blall.p, cap, ncclUint64, c->comm, c->stream));
     c->blmap.reserve((M / 32 + 2) * 4);
     CUDA_CHECK(cudaMemsetAsync(c->blmap.p, 0, (M / 32 + 2) * 4, c->stream));
-    B.view.tx = c->tx.as<uint64_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.tx = c->tx.as<uint64_t>(); B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
     B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
     bl_mark_kernel<<<(unsigned)((cap * W + 255) / 256), 256, 0, c->stream>>>(c->blall.as<uint64_t>(), cap * W, B.view, c->blmap.as<uint32_t>());
     ++c->launches;
@@ -1073,6 +1092,7 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         { const char *e = getenv("LRGE_MAX_ANCHORS"); c->max_anchors = e ? strtoull(e, nullptr, 10) : 0; }
         { const char *e = getenv("LRGE_SKETCH_TWO_PASS"); c->sketch_two_pass = e && e[0] == '1'; }
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         c->prof.s = c->stream;
         c->prof.reset();
         { size_t f = 0, t = 0; CUDA_CHECK(cudaMemGetInfo(&f, &t)); c->free_at_create = f; c->held_at_create = dev_bytes_in_use().load(); }
@@ -1086,6 +1106,7 @@ void lrge_gpu_destroy(lrge_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     delete ctx;
 }
@@ -1126,16 +1147,19 @@ int lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_read
                            uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats) {
     if (!T || !Q || !counts || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
     return guarded(ctx, [&] {
-        Timer tm(ctx->stream);
-        tm.start();
+        const auto t0 = std::chrono::steady_clock::now();
         lrge_staged &sT = ctx->tmp_a, &sQ = ctx->tmp_b;
-        stage_readset(ctx, T, &sT);
-        stage_readset(ctx, Q, &sQ);
-        const float ms = tm.stop();
-        if (stats) stats->ms_h2d = ms;
-        if (opts->use_min_ref && sT.total_bases > sQ.total_bases) run_overlap(ctx, &sQ, &sT, MODE_INVERSE, *opts, counts, nullptr, stats);
+        const bool inverse = opts->use_min_ref && (T->n ? T->off[T->n] - T->off[0] : 0) > (Q->n ? Q->off[Q->n] - Q->off[0] : 0);
+        struct Drain { lrge_ctx *c; ~Drain() { cudaStreamSynchronize(c->copy_stream); } } drain{ctx};   // caller buffers are free on return
+        // the indexed set is needed first; the other copy overlaps its sketch
+        stage_readset(ctx, inverse ? Q : T, inverse ? &sQ : &sT, true);
+        stage_readset(ctx, inverse ? T : Q, inverse ? &sT : &sQ, true);
+        if (inverse) run_overlap(ctx, &sQ, &sT, MODE_INVERSE, *opts, counts, nullptr, stats);
         else run_overlap(ctx, &sT, &sQ, MODE_TWOSET, *opts, counts, had_mapping, stats);
-        if (stats) stats->ms_total += ms;
+        if (stats) {   // host buffers in, counts out: wall time of the whole call
+            stats->ms_h2d = 0.0f;
+            stats->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
     });
 }
 
@@ -1175,14 +1199,15 @@ int lrge_gpu_ava_overlaps(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts 
 int lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts, uint32_t *counts, lrge_stats *stats) {
     if (!R || !counts || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
     return guarded(ctx, [&] {
-        Timer tm(ctx->stream);
-        tm.start();
+        const auto t0 = std::chrono::steady_clock::now();
         lrge_staged &sR = ctx->tmp_a;
-        stage_readset(ctx, R, &sR);
-        const float ms = tm.stop();
-        if (stats) stats->ms_h2d = ms;
+        struct Drain { lrge_ctx *c; ~Drain() { cudaStreamSynchronize(c->copy_stream); } } drain{ctx};
+        stage_readset(ctx, R, &sR, true);
         run_overlap(ctx, &sR, &sR, MODE_AVA, *opts, counts, nullptr, stats);
-        if (stats) stats->ms_total += ms;
+        if (stats) {
+            stats->ms_h2d = 0.0f;
+            stats->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
     });
 }
 
