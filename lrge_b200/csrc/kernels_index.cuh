@@ -6,8 +6,8 @@
 // y = rid<<32|pos<<1|strand of one key in ascending order.  Here all target minimizers are radix-sorted
 // by hash (stable, so y stays ascending inside a key) into one CSR-like array, and a direct-address
 // table over the TOP b hash bits gives the sub-range to search:
-//     tx[M], ty[M]   sorted by tx>>8;   boff[2^b + 1]:  bucket(key) = key >> (2k - b)
-// A lookup is one read of two adjacent boff entries plus a binary search over ~1-2 entries.
+//     tx[M], ty[M]   sorted by tx>>8;   boff[2^b + 1]:  bucket(key) = key >> (2k - b);   tk32[M] = low 32 key bits
+// A lookup is one read of two adjacent boff entries plus the bucket's <= 8 compact keys fetched with independent loads.
 #pragma once
 #include "common.cuh"
 
@@ -23,37 +23,6 @@ __global__ void bucket_bounds_kernel(const uint64_t *__restrict__ tx, uint64_t M
     const int64_t b_prev = i == 0 ? -1 : (int64_t)(tx[i - 1] >> shift);
     const int64_t b_cur = i == M ? (int64_t)nb : (int64_t)(tx[i] >> shift);
     for (int64_t b = b_prev + 1; b <= b_cur; ++b) boff[b] = (uint32_t)i;
-}
-
-// Per distinct key (run of equal tx>>8): histogram of the run length, number of keys.
-// hist[OCC_BINS] + n_keys are 64-bit device counters.
-__global__ void occ_hist_kernel(const uint64_t *__restrict__ tx, uint64_t M, unsigned long long *hist,
-                                unsigned long long *n_keys) {
-    __shared__ unsigned int sh[OCC_BINS];
-    for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    unsigned int my_keys = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t key = tx[i] >> 8;
-        if (i > 0 && (tx[i - 1] >> 8) == key) continue;      // not a run start
-        // run length by galloping then bisection
-        uint64_t lo = i, step = 1;                            // invariant: key(lo) == key
-        while (lo + step < M && (tx[lo + step] >> 8) == key) { lo += step; step <<= 1; }
-        uint64_t hi = lo + step < M ? lo + step : M;          // key(hi) != key or hi == M
-        while (hi - lo > 1) {
-            const uint64_t mid = (lo + hi) >> 1;
-            if ((tx[mid] >> 8) == key) lo = mid; else hi = mid;
-        }
-        const uint64_t n = hi - i;
-        atomicAdd(&sh[n < OCC_BINS - 1 ? n : OCC_BINS - 1], 1u);
-        ++my_keys;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
-    // block-reduce the key count
-    for (int o = 16; o > 0; o >>= 1) my_keys += __shfl_down_sync(0xffffffffu, my_keys, o);
-    if ((threadIdx.x & 31) == 0 && my_keys) atomicAdd(n_keys, (unsigned long long)my_keys);
 }
 
 // K2b + K3 fused: one coalesced pass over the sorted keys writes the bucket table and the occurrence histogram.

@@ -3,12 +3,15 @@
 // Pipeline (one CUDA stream per context; every kernel is hand-written except the radix sorts and
 // prefix sums, which are CUB device primitives):
 //   K0  pack_kernel            ASCII -> 2-bit + ambiguity mask          (+ K0h hpc_compress for ava-pb)
-//   K1  sketch_kernel<COUNT>   minimizers per warp sub-tile -> scan -> sketch_kernel<EMIT>
-//   K2  radix sort of target minimizers by hash, bucket_bounds_kernel   (index in HBM)
-//   K3  occ_hist_kernel        occurrence histogram -> mid_occ          (mm_mapopt_update)
+//   K1  sketch_kernel<stage>   minimizers into per-sub-tile slots -> scan -> compact_kernel
+//                              (fallback: sketch_kernel<count> -> scan -> sketch_kernel<emit>)
+//   K2  radix sort of target minimizers by hash                         (index in HBM)
+//   K3  index_post_kernel      bucket table + compact lookup keys + occurrence histogram -> mid_occ (mm_mapopt_update)
+//       build_index_sharded    the same with the index sharded over ranks: exact occurrence exchange over NCCL
 //   K4  mz_flt_kernel, seed_count_kernel -> scan -> anchor_fill_kernel  (per query batch)
-//   K5  radix sort of anchors by (query, target, strand, target pos), pair_flag_kernel + select
-//   K6  chain_pair_kernel      chaining DP + backtrack + overlap decision per (query, target) pair
+//   K5  radix sort of anchors by (query, target, strand, target pos), group_mark_kernel + select + group_classify_kernel
+//   K6  chain_group_kernel     chaining DP + backtrack + overlap decision, one warp per (query, target, strand) group
+//                              (chain_pair_kernel: literal one-thread-per-pair cross-check, LRGE_CHAIN_V1=1)
 // There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include "../../include/lrge_b200.h"
 #include "common.cuh"
@@ -143,15 +146,6 @@ struct Prof {
     }
 };
 #define KLAUNCH(c, name, nbytes, ...) do { (c)->prof.kbegin(name, (double)(nbytes)); __VA_ARGS__; (c)->prof.kend(); ++(c)->launches; } while (0)
-
-struct Timer {
-    cudaEvent_t a, b;
-    cudaStream_t s;
-    Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
-    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
-    void start() { cudaEventRecord(a, s); }
-    float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
-};
 
 }  // namespace
 

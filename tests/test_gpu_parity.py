@@ -292,3 +292,26 @@ def test_ava_overlap_records_parity(ctx):
     assert _reg_set(ov) == _reg_set(regs, qidx)
     want, _ = oracle.ava_counts(R, "ont", threads=8)
     assert np.array_equal(cnt.counts, want)
+
+
+def test_mid_occ_overflow_bin(ctx):
+    """Keys occurring >= 4095 times leave the occurrence histogram's exact bins: mid_occ must still be the exact
+    order statistic (mm_idx_cal_max_occ)."""
+    rng = np.random.default_rng(21)
+    unit = bytes(rng.choice(list(b"ACGT"), size=400).tolist())
+    recs = [("t%05d" % i, unit) for i in range(4200)]
+    recs += [("u%03d" % i, bytes(rng.choice(list(b"ACGT"), size=700).tolist())) for i in range(30)]
+    T = ReadSet.from_records(recs)
+    opt = oracle.options("ont")
+    idx = oracle.Index(T, opt, threads=8)
+    mid, nkeys = ctx.dump_mid_occ(T, "ont")
+    assert nkeys == idx.n_keys
+    assert mid == opt.mid_occ and mid > 4095
+
+
+def test_ava_sharding_is_additive(ctx):
+    g = readsim.genome(150_000)
+    R = readsim.reads(g, 200, 3000, readsim.ONT, readsim.SEED_AVA, "r")
+    full = ctx.ava_counts(R, "ont")
+    parts = [ctx.ava_counts(R, "ont", shard_index=r, shard_count=3) for r in range(3)]
+    assert np.array_equal(sum(p.counts for p in parts), full.counts)
