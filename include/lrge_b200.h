@@ -68,8 +68,9 @@ typedef struct lrge_opts {
     int32_t remove_internal;     /* -F: drop overlaps that PafRecord::is_internal (mapping.rs:59-77); default 0 */
     float   max_overhang_ratio;  /* default 0.2 */
     int32_t use_min_ref;         /* two-set: index the smaller set (twoset.rs:596-599); default 0 */
-    /* target sharding (one process per GPU): this context keeps anchors only for targets with
-     * rid % shard_count == shard_index; seed filtering still uses global occurrence counts. */
+    /* target sharding (one process per GPU): this context keeps anchors only for its contiguous block of targets,
+     * rid in [n*shard_index/shard_count, n*(shard_index+1)/shard_count); seed filtering still uses global
+     * occurrence counts. */
     int32_t shard_index;         /* default 0 */
     int32_t shard_count;         /* default 1 */
     int32_t reserved[6];
@@ -173,6 +174,10 @@ void lrge_gpu_host_free(void *p);
  *   cnt[rs->n] = minimizers per read (may be NULL). *n_out receives the number written; cap = capacity. */
 int  lrge_gpu_dump_minimizers(lrge_ctx *ctx, const lrge_readset *rs, int32_t platform,
                               uint64_t *x, uint64_t *y, uint64_t cap, uint64_t *n_out, uint32_t *cnt);
+/* the same for the reads [first, first + count) only, staged and sketched the way a rank treats its target shard
+ * (cnt[count]; y keeps the read ids of the whole set) */
+int  lrge_gpu_dump_minimizers_block(lrge_ctx *ctx, const lrge_readset *rs, int32_t platform, uint32_t first, uint32_t count,
+                                    uint64_t *x, uint64_t *y, uint64_t cap, uint64_t *n_out, uint32_t *cnt);
 /* mid_occ of an index built over T (mm_mapopt_update, aligner.rs:189) */
 int  lrge_gpu_dump_mid_occ(lrge_ctx *ctx, const lrge_readset *T, int32_t platform, int32_t *mid_occ, uint64_t *n_keys);
 

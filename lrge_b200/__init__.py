@@ -36,6 +36,7 @@ C_API = [
     "lrge_gpu_dump_minimizers", "lrge_gpu_dump_mid_occ", "lrge_per_read_estimate", "lrge_estimate", "lrge_is_internal",
     "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates", "lrge_gpu_comm_unique_id", "lrge_gpu_comm_init",
     "lrge_gpu_set_profiling", "lrge_gpu_kernel_times", "lrge_gpu_twoset_overlaps", "lrge_gpu_ava_overlaps", "lrge_paf_format",
+    "lrge_gpu_dump_minimizers_block",
 ]
 
 
@@ -126,6 +127,8 @@ def lib():
         L.lrge_gpu_host_free.restype = None
         L.lrge_gpu_dump_minimizers.argtypes = [vp, P(CReadSet), ctypes.c_int32, vp, vp, ctypes.c_uint64,
                                                P(ctypes.c_uint64), vp]
+        L.lrge_gpu_dump_minimizers_block.argtypes = [vp, P(CReadSet), ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32, vp, vp,
+                                                     ctypes.c_uint64, P(ctypes.c_uint64), vp]
         L.lrge_gpu_dump_mid_occ.argtypes = [vp, P(CReadSet), ctypes.c_int32, P(ctypes.c_int32), P(ctypes.c_uint64)]
         L.lrge_per_read_estimate.argtypes = [ctypes.c_uint64, ctypes.c_float, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32]
         L.lrge_per_read_estimate.restype = ctypes.c_float
@@ -323,6 +326,16 @@ class Context:
         c = as_c(rs)
         self._check(lib().lrge_gpu_dump_minimizers(self.h, ctypes.byref(c), platform_code(platform), x.ctypes.data,
                                                    y.ctypes.data, cap, ctypes.byref(n), cnt.ctypes.data))
+        return x[:n.value].copy(), y[:n.value].copy(), cnt
+
+    def dump_minimizers_block(self, rs: ReadSet, first: int, count: int, platform="ont"):
+        cap = rs.total_bases + 16
+        x, y = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        cnt = np.zeros(count, np.uint32)
+        n = ctypes.c_uint64()
+        c = as_c(rs)
+        self._check(lib().lrge_gpu_dump_minimizers_block(self.h, ctypes.byref(c), platform_code(platform), first, count,
+                                                         x.ctypes.data, y.ctypes.data, cap, ctypes.byref(n), cnt.ctypes.data))
         return x[:n.value].copy(), y[:n.value].copy(), cnt
 
     def dump_mid_occ(self, T: ReadSet, platform="ont"):

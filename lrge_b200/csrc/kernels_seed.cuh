@@ -46,13 +46,14 @@ struct SkipCtx {
     const uint32_t *len_q, *len_t;     // original read lengths
     int check_names;                   // any (query, target) name comparison can matter
     int no_dual;                       // MM_F_NO_DUAL: skip when qname > tname
-    uint32_t shard_index, shard_count;
+    uint32_t shard_lo, shard_hi;       // keep hits of targets rid in [shard_lo, shard_hi) only
+    int sharded;                       // the range above is a proper subset of the index
 };
 
 // skip_seed (map.c) + target sharding
 __device__ __forceinline__ bool skip_hit(uint64_t r, uint32_t qid, uint32_t q_pos, const SkipCtx &S) {
     const uint32_t rid = (uint32_t)(r >> 32);
-    if (S.shard_count > 1 && rid % S.shard_count != S.shard_index) return true;
+    if (S.sharded && (rid < S.shard_lo || rid >= S.shard_hi)) return true;
     if (S.check_names) {
         const uint32_t rq = S.rank_q[qid], rt = S.rank_t[rid];
         if (rq == rt && S.len_t[rid] == S.len_q[qid] && ((uint32_t)r >> 1) == (q_pos >> 1)) return true;   // diagonal
@@ -74,7 +75,7 @@ __global__ void seed_count_kernel(const uint64_t *__restrict__ qx, const uint64_
         if (n > (uint32_t)mid_occ) n = 0;                     // m[i].flt = 1 (seed.c mm_collect_matches)
         if (n && I.bl && ((I.bl[start >> 5] >> (start & 31)) & 1)) n = 0;   // > mid_occ over all target shards
         if (n) {
-            if (S.check_names || S.shard_count > 1) {
+            if (S.check_names || S.sharded) {
                 const uint64_t y = qy[i];
                 for (uint32_t j = 0; j < n; ++j) cnt += !skip_hit(I.ty[start + j], (uint32_t)(y >> 32), (uint32_t)y, S);
             } else cnt = n;
@@ -106,7 +107,7 @@ __global__ void anchor_fill_kernel(const uint64_t *__restrict__ qx, const uint64
     const uint32_t qid = (uint32_t)(y >> 32), q_pos = (uint32_t)y, q_span = (uint32_t)(x & 0xff);
     const uint32_t qlen = S.len_q[qid];
     const uint64_t qpart = (uint64_t)(qid - q0) << K.RB;
-    const bool scan = S.check_names || S.shard_count > 1;
+    const bool scan = S.check_names || S.sharded;
     uint64_t o = aoff[i] - a0;
     const uint32_t start = hstart[i];
     for (uint32_t j = 0; j < n; ++j) {

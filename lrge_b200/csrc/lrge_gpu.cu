@@ -156,7 +156,9 @@ struct lrge_staged {
     uint32_t n = 0;
     uint64_t total_bases = 0;
     uint32_t max_len = 0;
-    DevBuf asc, off;                       // device: ASCII (+64 slack), n+1 offsets
+    DevBuf asc;                            // device: ASCII bases of reads [blk_first, blk_first + blk_count) (+64 slack)
+    uint32_t blk_first = 0, blk_count = 0; // which reads' bases are resident (a rank may stage only its target shard)
+    uint64_t blk_base = 0;                 // h_off[blk_first]: host offset of device byte 0
     std::vector<uint64_t> h_off;           // host copies
     std::vector<uint32_t> h_len;
     std::string names;
@@ -222,16 +224,30 @@ template <typename T> void h2d(lrge_ctx *c, DevBuf &d, const T *src, size_t n) {
     if (n) CUDA_CHECK(cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
 }
 
-// Copies a host read set to HBM on the copy stream.  async: return without waiting -- the first kernel that touches the
-// set waits for `ready` on the compute stream, so the copy of the second set overlaps the sketch of the first.
-void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool async = false) {
+// reads [lo, hi) owned by `rank` of `world`: contiguous blocks, so a rank's share of a host read set is one copy
+inline void shard_range(uint32_t n, int rank, int world, uint32_t *lo, uint32_t *hi) {
+    *lo = (uint32_t)((uint64_t)n * (uint64_t)rank / (uint64_t)world);
+    *hi = (uint32_t)((uint64_t)n * (uint64_t)(rank + 1) / (uint64_t)world);
+}
+
+// Copies a host read set (or only the bases of reads [blk_first, blk_first + blk_count)) to HBM on the copy stream;
+// names and lengths of ALL reads are kept on the host side either way.  async: return without waiting -- the first
+// kernel that touches the set waits for `ready` on the compute stream, so the copy of the second set overlaps the
+// sketch of the first.
+void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool async = false, uint32_t blk_first = 0,
+                   uint32_t blk_count = 0xffffffffu) {
     s->n = rs->n;
     s->total_bases = rs->n ? rs->off[rs->n] - rs->off[0] : 0;
     s->pending = false;
+    if (blk_first > rs->n) blk_first = rs->n;
+    if (blk_count > rs->n - blk_first) blk_count = rs->n - blk_first;
+    s->blk_first = blk_first; s->blk_count = blk_count;
+    const uint64_t b0 = rs->n ? rs->off[blk_first] : 0, b1 = rs->n ? rs->off[blk_first + blk_count] : 0;
+    s->blk_base = rs->n ? b0 - rs->off[0] : 0;
     // start the big copy first; the host-side bookkeeping below overlaps with it
-    s->asc.reserve(s->total_bases + 64);
-    if (s->total_bases)
-        CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + rs->off[0], s->total_bases, cudaMemcpyHostToDevice, c->copy_stream));
+    s->asc.reserve((b1 - b0) + 64);
+    if (b1 > b0)
+        CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_stream));
     s->h_off.assign(rs->off, rs->off + rs->n + 1);
     if (rs->n && rs->off[0] != 0) {
         const uint64_t b = rs->off[0];
@@ -265,8 +281,6 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool asy
             const uint32_t la = s->name_off[a + 1] - s->name_off[a], lb = s->name_off[b + 1] - s->name_off[b];
             if (la == lb && memcmp(s->names.data() + s->name_off[a], s->names.data() + s->name_off[b], la) == 0) s->names_unique = false;
         }
-    s->off.reserve(std::max<size_t>(s->h_off.size(), 1) * 8);
-    CUDA_CHECK(cudaMemcpyAsync(s->off.p, s->h_off.data(), s->h_off.size() * 8, cudaMemcpyHostToDevice, c->copy_stream));
     if (async) {
         if (!s->ready) CUDA_CHECK(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventRecord(s->ready, c->copy_stream));
@@ -285,19 +299,23 @@ __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32
     if (i < n) dst[i] = src[idx[i]];
 }
 
-// K0 + K1: sketch a staged read set (or the reads first, first+stride, ... of it) into `out`
-void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first = 0, uint32_t stride = 1) {
-    const bool subset = stride > 1;
-    const uint32_t n = s->n > first ? (s->n - first + stride - 1) / stride : 0;
+// K0 + K1: sketch a staged read set, or only its reads [first, first + count), into `out`
+void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first = 0, uint32_t count = 0xffffffffu) {
+    if (first > s->n) first = s->n;
+    if (count > s->n - first) count = s->n - first;
+    if (count && (first < s->blk_first || first + count > s->blk_first + s->blk_count))
+        throw std::runtime_error("internal: sketch of reads that were not staged");
+    const bool subset = first != 0 || count != s->n;
+    const uint32_t n = count;
     std::vector<uint64_t> poff(n), soff(n);
     std::vector<uint32_t> tile_off(n + 1), slen(n), rid_map(n);
     uint64_t pos = PAD_BASES;
     uint32_t tiles = 0;
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t r = first + i * stride;
+        const uint32_t r = first + i;
         poff[i] = pos;
         tile_off[i] = tiles;
-        soff[i] = s->h_off[r];
+        soff[i] = s->h_off[r] - s->blk_base;
         slen[i] = s->h_len[r];
         rid_map[i] = r;
         pos += ((uint64_t)s->h_len[r] + PAD_BASES - 1) / PAD_BASES * PAD_BASES;
@@ -326,8 +344,9 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
     L.nm = c->nm.as<uint32_t>();
     L.n = n;
     if (o.is_hpc) {
-        c->casc.reserve(s->total_bases + 64);
-        c->cend.reserve((s->total_bases + 1) * 4);
+        const uint64_t resident = s->h_off[s->blk_first + s->blk_count] - s->blk_base;
+        c->casc.reserve(resident + 64);
+        c->cend.reserve((resident + 1) * 4);
         c->clen.reserve((size_t)std::max(n, 1u) * 4);
         if (n) {
             KLAUNCH(c, "hpc_compress_kernel", 6 * nbases,
@@ -741,7 +760,9 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         throw std::runtime_error("shard_index/shard_count do not match the communicator");
     BuiltIndex B;
     if (sharded_index) {
-        sketch_readset(c, idx, o, &c->sk_idx, (uint32_t)c->rank, (uint32_t)world);
+        uint32_t r0, r1;
+        shard_range(idx->n, c->rank, world, &r0, &r1);
+        sketch_readset(c, idx, o, &c->sk_idx, r0, r1 - r0);
         c->prof.sbegin(ST_INDEX);
         B = build_index_sharded(c, c->sk_idx, o, &S);
         c->prof.send(ST_INDEX);
@@ -773,8 +794,8 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     K.len_q = c->len_str.as<uint32_t>(); K.len_t = c->len_idx.as<uint32_t>();
     K.no_dual = mode == MODE_AVA;                                      // aligner.rs:93-103, ava.rs:378
     K.check_names = mode == MODE_AVA || R.shared;                      // NO_DIAG only matters for equal names
-    K.shard_index = (uint32_t)opts.shard_index; K.shard_count = (uint32_t)world;
-    if (sharded_index) K.shard_count = 1;                              // every local hit already belongs to this shard
+    shard_range(idx->n, opts.shard_index, world, &K.shard_lo, &K.shard_hi);
+    K.sharded = world > 1 && !sharded_index;                          // sharded index: every local hit already belongs to this shard
 
     c->counts.reserve(((size_t)n_counts + 1) * 4);
     c->had.reserve((size_t)str->n + 1);
@@ -1146,7 +1167,13 @@ int lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_read
         const bool inverse = opts->use_min_ref && (T->n ? T->off[T->n] - T->off[0] : 0) > (Q->n ? Q->off[Q->n] - Q->off[0] : 0);
         struct Drain { lrge_ctx *c; ~Drain() { cudaStreamSynchronize(c->copy_stream); } } drain{ctx};   // caller buffers are free on return
         // the indexed set is needed first; the other copy overlaps its sketch
-        stage_readset(ctx, inverse ? Q : T, inverse ? &sQ : &sT, true);
+        uint32_t b0 = 0, b1 = 0xffffffffu;
+        if (ctx->comm && opts->shard_count > 1) {                 // sharded index: only this rank's block of the indexed set
+            uint32_t lo, hi;
+            shard_range(inverse ? Q->n : T->n, opts->shard_index, opts->shard_count, &lo, &hi);
+            b0 = lo; b1 = hi - lo;
+        }
+        stage_readset(ctx, inverse ? Q : T, inverse ? &sQ : &sT, true, b0, b1);
         stage_readset(ctx, inverse ? T : Q, inverse ? &sT : &sQ, true);
         if (inverse) run_overlap(ctx, &sQ, &sT, MODE_INVERSE, *opts, counts, nullptr, stats);
         else run_overlap(ctx, &sT, &sQ, MODE_TWOSET, *opts, counts, had_mapping, stats);
@@ -1253,27 +1280,32 @@ int lrge_gpu_host_alloc(size_t bytes, void **out) {
 }
 void lrge_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-int lrge_gpu_dump_minimizers(lrge_ctx *ctx, const lrge_readset *rs, int32_t platform, uint64_t *x, uint64_t *y, uint64_t cap,
-                             uint64_t *n_out, uint32_t *cnt) {
+int lrge_gpu_dump_minimizers_block(lrge_ctx *ctx, const lrge_readset *rs, int32_t platform, uint32_t first, uint32_t count,
+                                   uint64_t *x, uint64_t *y, uint64_t cap, uint64_t *n_out, uint32_t *cnt) {
     if (!rs || !n_out) return LRGE_ERR_INVALID_ARG;
     return guarded(ctx, [&] {
         lrge_staged s;
-        stage_readset(ctx, rs, &s);
+        stage_readset(ctx, rs, &s, false, first, count);     // only the block's bases go to the device
         const MapOpt o = preset_for(platform);
-        sketch_readset(ctx, &s, o, &ctx->sk_str);
+        sketch_readset(ctx, &s, o, &ctx->sk_str, s.blk_first, s.blk_count);
         const uint64_t M = ctx->sk_str.M;
         *n_out = M;
         const uint64_t m = std::min(M, cap);
         if (x && m) CUDA_CHECK(cudaMemcpyAsync(x, ctx->sk_str.x.p, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
         if (y && m) CUDA_CHECK(cudaMemcpyAsync(y, ctx->sk_str.y.p, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (cnt && rs->n) {
-            std::vector<uint32_t> moff((size_t)rs->n + 1);
-            CUDA_CHECK(cudaMemcpyAsync(moff.data(), ctx->sk_str.moff.p, ((size_t)rs->n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cnt && s.blk_count) {
+            std::vector<uint32_t> moff((size_t)s.blk_count + 1);
+            CUDA_CHECK(cudaMemcpyAsync(moff.data(), ctx->sk_str.moff.p, ((size_t)s.blk_count + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            for (uint32_t i = 0; i < rs->n; ++i) cnt[i] = moff[i + 1] - moff[i];
+            for (uint32_t i = 0; i < s.blk_count; ++i) cnt[i] = moff[i + 1] - moff[i];
         }
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     });
+}
+
+int lrge_gpu_dump_minimizers(lrge_ctx *ctx, const lrge_readset *rs, int32_t platform, uint64_t *x, uint64_t *y, uint64_t cap,
+                             uint64_t *n_out, uint32_t *cnt) {
+    return lrge_gpu_dump_minimizers_block(ctx, rs, platform, 0, 0xffffffffu, x, y, cap, n_out, cnt);
 }
 
 int lrge_gpu_dump_mid_occ(lrge_ctx *ctx, const lrge_readset *T, int32_t platform, int32_t *mid_occ, uint64_t *n_keys) {

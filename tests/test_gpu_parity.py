@@ -315,3 +315,21 @@ def test_ava_sharding_is_additive(ctx):
     full = ctx.ava_counts(R, "ont")
     parts = [ctx.ava_counts(R, "ont", shard_index=r, shard_count=3) for r in range(3)]
     assert np.array_equal(sum(p.counts for p in parts), full.counts)
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_shard_block_staging_and_sketch(ctx, platform):
+    """A rank stages and sketches only its contiguous block of targets; read ids stay those of the whole set."""
+    T, _ = small_sets(nt=101, err=readsim.ONT if platform == "ont" else readsim.HIFI)
+    want, wcnt = oracle.sketch_readset(T, oracle.options(platform))
+    starts = np.concatenate([[0], np.cumsum(wcnt.astype(np.int64))])
+    world = 3
+    seen = 0
+    for rank in range(world):
+        lo, hi = T.n * rank // world, T.n * (rank + 1) // world
+        x, y, cnt = ctx.dump_minimizers_block(T, lo, hi - lo, platform)
+        a, b = int(starts[lo]), int(starts[hi])
+        assert np.array_equal(cnt, wcnt[lo:hi])
+        assert np.array_equal(x, want["x"][a:b]) and np.array_equal(y, want["y"][a:b])
+        seen += x.shape[0]
+    assert seen == want.shape[0]
