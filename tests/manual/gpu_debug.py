@@ -5,7 +5,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import lrge_b200  # noqa: E402
 import oracle  # noqa: E402
 from lrge_b200 import readsim  # noqa: E402

@@ -14,7 +14,7 @@ timeout 300 ncu --set full --clock-control none --import-source on \
     -s 40 -c 24 -o gpurun_out/prof_${TAG} python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -1 gpurun_out/ncu_full_${TAG}.log | cut -c1-120
 if [ "${2:-}" = "C4" ]; then
-    timeout 400 python tools/run_config.py C4 --repeat 2 --oracle --oracle-queries 2000 2>&1 | tail -6 | cut -c1-900 | tee gpurun_out/c4_${TAG}.log
+    timeout 400 python tests/manual/run_config.py C4 --repeat 2 --oracle --oracle-queries 2000 2>&1 | tail -6 | cut -c1-900 | tee gpurun_out/c4_${TAG}.log
 fi
 python - <<PY
 import json
