@@ -190,7 +190,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     barrier()
-    ev_ms, chain_ms, launches, step_ms = 0.0, 0.0, 0, []
+    ev_ms, launches, step_ms = 0.0, 0, []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
@@ -198,7 +198,6 @@ def run_ours(args):
         last = ctx.twoset_counts(sT, sQ, platform, **shard)
         ev_ms += last.stats["ms_total"]
         step_ms.append(round(last.stats["ms_total"], 3))
-        chain_ms += last.stats["ms_chain_kernel"]
         launches += last.stats["n_kernel_launches"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)

@@ -90,7 +90,7 @@ typedef struct lrge_stats {
     uint32_t n_kernel_launches;
     /* device time per stage in ms (CUDA events on the context's stream) */
     float ms_h2d, ms_pack, ms_sketch, ms_index, ms_seed, ms_sort, ms_chain, ms_d2h, ms_total;
-    float ms_chain_kernel;       /* the chaining kernel alone, summed over batches */
+    float ms_chain_kernel;       /* the chaining kernel alone, summed over batches (0 unless lrge_gpu_set_profiling is on) */
     float ms_comm;               /* NCCL reduction of the per-read counts */
     float reserved[5];
 } lrge_stats;

@@ -753,7 +753,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     const std::vector<uint32_t> &rank_idx = R.a, &rank_str = mode == MODE_AVA ? R.a : R.b;
 
     // K0/K1 on the indexed set, K2/K3.  With a communicator the index itself is sharded: this rank sketches only
-    // its targets (rid % world == rank) and the occurrence filter is made exact by build_index_sharded.
+    // its block of targets (shard_range) and the occurrence filter is made exact by build_index_sharded.
     const int world = std::max(opts.shard_count, 1);
     const bool sharded_index = c->comm != nullptr && world > 1;
     if (sharded_index && (world != c->world || opts.shard_index != c->rank))
