@@ -13,8 +13,8 @@
 #pragma once
 #include "lrge_b200.h"
 
+#include <cctype>
 #include <cstdint>
-#include <fstream>
 #include <limits>
 #include <optional>
 #include <stdexcept>
@@ -64,36 +64,17 @@ struct ReadSet {
         v.bases = bases.data(); v.off = off.data(); v.names = names.data(); v.name_off = name_off.data(); v.n = size();
         return v;
     }
-    // plain FASTA / FASTQ; the read id is the header up to the first whitespace (io.rs:192-205)
+    // plain or gzip FASTA / FASTQ; the read id is the header up to the first whitespace (io.rs:192-205)
     static ReadSet from_fastx(const std::string &path) {
-        std::ifstream in(path);
-        if (!in) throw LrgeError(LRGE_ERR_IO, "IO error: cannot open " + path);
+        uint64_t n = 0, nb = 0, nn = 0;
+        int rc = lrge_fastx_count(path.c_str(), &n, &nb, &nn);
+        if (rc == LRGE_ERR_IO) throw LrgeError(LRGE_ERR_IO, "IO error: cannot read " + path + " (is the file empty?)");
+        if (rc == LRGE_ERR_UNSUPPORTED) throw LrgeError(LRGE_ERR_UNSUPPORTED, "unsupported compression: " + path);
+        if (rc != LRGE_OK) throw LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: " + path);
         ReadSet rs;
-        std::string line, name, seq;
-        bool have = false, fastq = false;
-        auto id_of = [](const std::string &h) { size_t e = h.find_first_of(" \t\r", 1); return h.substr(1, e == std::string::npos ? e : e - 1); };
-        while (std::getline(in, line)) {
-            if (!line.empty() && line.back() == '\r') line.pop_back();
-            if (line.empty()) continue;
-            if (!have && line[0] == '@') fastq = true;
-            if (fastq) {
-                if (line[0] != '@') throw LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: " + path);
-                name = id_of(line);
-                std::string plus, qual;
-                if (!std::getline(in, seq) || !std::getline(in, plus) || !std::getline(in, qual))
-                    throw LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: truncated record in " + path);
-                if (!seq.empty() && seq.back() == '\r') seq.pop_back();
-                rs.push(name, seq);
-                have = true;
-            } else if (line[0] == '>') {
-                if (have) rs.push(name, seq);
-                name = id_of(line); seq.clear(); have = true;
-            } else {
-                if (!have) throw LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: " + path);
-                seq += line;
-            }
-        }
-        if (have && !fastq) rs.push(name, seq);
+        rs.bases.resize(nb); rs.off.resize(n + 1); rs.names.resize(nn); rs.name_off.resize(n + 1);
+        rc = lrge_fastx_load(path.c_str(), rs.bases.data(), rs.off.data(), rs.names.data(), rs.name_off.data());
+        if (rc != LRGE_OK) throw LrgeError((lrge_status)rc, "FASTQ parse error: " + path);
         return rs;
     }
 };

@@ -36,7 +36,7 @@ C_API = [
     "lrge_gpu_dump_minimizers", "lrge_gpu_dump_mid_occ", "lrge_per_read_estimate", "lrge_estimate", "lrge_is_internal",
     "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates", "lrge_gpu_comm_unique_id", "lrge_gpu_comm_init",
     "lrge_gpu_set_profiling", "lrge_gpu_kernel_times", "lrge_gpu_twoset_overlaps", "lrge_gpu_ava_overlaps", "lrge_paf_format",
-    "lrge_gpu_dump_minimizers_block",
+    "lrge_gpu_dump_minimizers_block", "lrge_fastx_count", "lrge_fastx_load",
 ]
 
 
@@ -122,6 +122,8 @@ def lib():
         L.lrge_gpu_ava_overlaps.argtypes = [vp, P(CReadSet), P(Opts), vp, ctypes.c_uint64, P(ctypes.c_uint64), vp, P(Stats)]
         L.lrge_paf_format.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int, ctypes.c_int32,
                                       ctypes.c_float, ctypes.c_int32, ctypes.c_char_p, ctypes.c_size_t]
+        L.lrge_fastx_count.argtypes = [ctypes.c_char_p, P(ctypes.c_uint64), P(ctypes.c_uint64), P(ctypes.c_uint64)]
+        L.lrge_fastx_load.argtypes = [ctypes.c_char_p, vp, vp, vp, vp]
         L.lrge_gpu_host_alloc.argtypes = [ctypes.c_size_t, P(vp)]
         L.lrge_gpu_host_free.argtypes = [vp]
         L.lrge_gpu_host_free.restype = None
@@ -343,6 +345,20 @@ class Context:
         c = as_c(T)
         self._check(lib().lrge_gpu_dump_mid_occ(self.h, ctypes.byref(c), platform_code(platform), ctypes.byref(m), ctypes.byref(nk)))
         return m.value, nk.value
+
+
+def read_fastx(path: str) -> ReadSet:
+    """Plain or gzip FASTA / FASTQ through the library's host reader (lrge_fastx_count / lrge_fastx_load)."""
+    n, nb, nn = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    rc = lib().lrge_fastx_count(path.encode(), ctypes.byref(n), ctypes.byref(nb), ctypes.byref(nn))
+    if rc != 0:
+        raise LrgeError(rc, path)
+    bases, off = np.zeros(max(nb.value, 1), np.uint8), np.zeros(n.value + 1, np.uint64)
+    names, noff = np.zeros(max(nn.value, 1), np.uint8), np.zeros(n.value + 1, np.uint32)
+    rc = lib().lrge_fastx_load(path.encode(), bases.ctypes.data, off.ctypes.data, names.ctypes.data, noff.ctypes.data)
+    if rc != 0:
+        raise LrgeError(rc, path)
+    return ReadSet(bases[:nb.value], off, names[:nn.value], noff)
 
 
 def paf_line(ov, Q: ReadSet, T: ReadSet, dv: float = -1.0, rl: int = 0) -> bytes:

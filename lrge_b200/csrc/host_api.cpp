@@ -9,9 +9,115 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <cctype>
 #include <vector>
 
+#include <zlib.h>
+#include <string>
+
+namespace {
+
+// Line reader over a plain or gzip file (zlib reads both); other compressions are recognised by their magic bytes
+// (io.rs:35-61) and refused.
+struct LineReader {
+    gzFile f = nullptr;
+    std::vector<char> buf;
+    size_t pos = 0, len = 0;
+    int status = LRGE_OK;
+    explicit LineReader(const char *path) : buf(1 << 20) {
+        FILE *fp = fopen(path, "rb");
+        if (!fp) { status = LRGE_ERR_IO; return; }
+        unsigned char m[5] = {0, 0, 0, 0, 0};
+        const size_t n = fread(m, 1, 5, fp);
+        fclose(fp);
+        if (n >= 2 && m[0] == 0x42 && m[1] == 0x5a) { status = LRGE_ERR_UNSUPPORTED; return; }                         // bzip2
+        if (n >= 4 && m[0] == 0x28 && m[1] == 0xb5 && m[2] == 0x2f && m[3] == 0xfd) { status = LRGE_ERR_UNSUPPORTED; return; }   // zstd
+        if (n >= 5 && m[0] == 0xfd && m[1] == 0x37 && m[2] == 0x7a && m[3] == 0x58 && m[4] == 0x5a) { status = LRGE_ERR_UNSUPPORTED; return; }   // xz
+        f = gzopen(path, "rb");
+        if (!f) status = LRGE_ERR_IO;
+        else gzbuffer(f, 1 << 20);
+    }
+    ~LineReader() { if (f) gzclose(f); }
+    bool getline(std::string &out) {
+        out.clear();
+        for (;;) {
+            if (pos == len) {
+                const int n = gzread(f, buf.data(), (unsigned)buf.size());
+                if (n < 0) { status = LRGE_ERR_IO; return false; }
+                if (n == 0) return !out.empty();
+                pos = 0; len = (size_t)n;
+            }
+            const char *p = buf.data() + pos;
+            const char *nl = (const char *)memchr(p, '\n', len - pos);
+            if (nl) { out.append(p, nl - p); pos = (size_t)(nl - buf.data()) + 1; break; }
+            out.append(p, len - pos);
+            pos = len;
+        }
+        if (!out.empty() && out.back() == '\r') out.pop_back();
+        return true;
+    }
+};
+
+// Calls rec(id, id_len, seq, seq_len) for every FASTA / FASTQ record; the id is the header up to the first
+// whitespace (io.rs:192-205).
+template <typename F> int for_each_record(const char *path, F rec) {
+    LineReader in(path);
+    if (in.status != LRGE_OK) return in.status;
+    std::string line, name, seq, plus, qual;
+    bool have = false, fastq = false, first = true;
+    auto id_len = [](const std::string &h) { size_t e = 1; while (e < h.size() && !isspace((unsigned char)h[e])) ++e; return e - 1; };
+    while (in.getline(line)) {
+        if (line.empty()) continue;
+        if (first) { first = false; if (line[0] == '@') fastq = true; else if (line[0] != '>') return LRGE_ERR_FASTQ_PARSE; }
+        if (fastq) {
+            if (line[0] != '@') return LRGE_ERR_FASTQ_PARSE;
+            name = line;
+            if (!in.getline(seq) || !in.getline(plus) || !in.getline(qual) || plus.empty() || plus[0] != '+' || qual.size() != seq.size())
+                return LRGE_ERR_FASTQ_PARSE;
+            rec(name.data() + 1, id_len(name), seq.data(), seq.size());
+        } else if (line[0] == '>') {
+            if (have) rec(name.data() + 1, id_len(name), seq.data(), seq.size());
+            name = line; seq.clear(); have = true;
+        } else {
+            if (!have) return LRGE_ERR_FASTQ_PARSE;
+            seq += line;
+        }
+    }
+    if (in.status != LRGE_OK) return in.status;
+    if (have && !fastq) rec(name.data() + 1, id_len(name), seq.data(), seq.size());
+    return LRGE_OK;
+}
+
+}  // namespace
+
 extern "C" {
+
+// io::count_records (io.rs:121-147): number of records, plus the bases and name bytes a loader needs to allocate
+int lrge_fastx_count(const char *path, uint64_t *n_records, uint64_t *n_bases, uint64_t *n_name_bytes) {
+    if (!path) return LRGE_ERR_INVALID_ARG;
+    uint64_t n = 0, b = 0, nb = 0;
+    const int rc = for_each_record(path, [&](const char *, size_t il, const char *, size_t sl) { ++n; b += sl; nb += il; });
+    if (rc != LRGE_OK) return rc;
+    if (n == 0) return LRGE_ERR_IO;                       // "Is the file empty?" (io.rs:140-145)
+    if (n_records) *n_records = n;
+    if (n_bases) *n_bases = b;
+    if (n_name_bytes) *n_name_bytes = nb;
+    return LRGE_OK;
+}
+
+// Loads every record into caller buffers sized from lrge_fastx_count: bases[n_bases], off[n+1], names[n_name_bytes],
+// name_off[n+1] -- the lrge_readset layout.
+int lrge_fastx_load(const char *path, uint8_t *bases, uint64_t *off, char *names, uint32_t *name_off) {
+    if (!path || !bases || !off || !names || !name_off) return LRGE_ERR_INVALID_ARG;
+    uint64_t n = 0, b = 0;
+    uint32_t nb = 0;
+    off[0] = 0; name_off[0] = 0;
+    return for_each_record(path, [&](const char *id, size_t il, const char *seq, size_t sl) {
+        memcpy(bases + b, seq, sl); b += sl;
+        memcpy(names + nb, id, il); nb += (uint32_t)il;
+        ++n; off[n] = b; name_off[n] = nb;
+    });
+}
 
 float lrge_per_read_estimate(uint64_t read_len, float avg_target_len, uint64_t n_target_reads, uint64_t n_ovlaps,
                              uint32_t ovlap_thresh) {

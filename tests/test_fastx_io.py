@@ -1,0 +1,69 @@
+"""Host-side FASTA / FASTQ ingestion of the library (io.rs:63-205 for the formats in scope: plain and gzip)."""
+import gzip
+
+import numpy as np
+import pytest
+
+import lrge_b200
+from lrge_b200 import readsim
+from lrge_b200.readset import ReadSet
+
+
+@pytest.fixture(scope="module")
+def reads():
+    g = readsim.genome(30_000)
+    return readsim.reads(g, 40, 1500, readsim.ONT, 7, "r")
+
+
+def same(a: ReadSet, b: ReadSet):
+    return (np.array_equal(a.bases, b.bases) and np.array_equal(a.off, b.off) and np.array_equal(a.names, b.names)
+            and np.array_equal(a.name_off, b.name_off))
+
+
+def test_fasta_plain_gz_and_multiline(tmp_path, reads):
+    fa = tmp_path / "r.fa"
+    reads.write_fasta(str(fa))
+    assert same(lrge_b200.read_fastx(str(fa)), reads)
+    assert same(ReadSet.from_fasta(str(fa)), reads)
+    gz = tmp_path / "r.fa.gz"
+    with gzip.open(gz, "wb") as fh:
+        fh.write(fa.read_bytes())
+    assert same(lrge_b200.read_fastx(str(gz)), reads)
+    ml = tmp_path / "multi.fa"                          # wrapped sequence lines, comments after the id, CRLF
+    with open(ml, "wb") as fh:
+        for i in range(reads.n):
+            s = reads.seq(i)
+            fh.write(b">" + reads.name(i) + b" some comment\r\n")
+            for j in range(0, len(s), 70):
+                fh.write(s[j:j + 70] + b"\r\n")
+    assert same(lrge_b200.read_fastx(str(ml)), reads)
+
+
+def test_fastq(tmp_path, reads):
+    fq = tmp_path / "r.fq.gz"
+    with gzip.open(fq, "wb") as fh:
+        for i in range(reads.n):
+            s = reads.seq(i)
+            fh.write(b"@" + reads.name(i) + b"\tdesc\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    assert same(lrge_b200.read_fastx(str(fq)), reads)
+
+
+def test_errors(tmp_path):
+    empty = tmp_path / "empty.fa"
+    empty.write_bytes(b"")
+    with pytest.raises(lrge_b200.LrgeError) as e:          # io.rs:140-145 "Is the file empty?"
+        lrge_b200.read_fastx(str(empty))
+    assert e.value.kind == "IoError"
+    with pytest.raises(lrge_b200.LrgeError) as e:
+        lrge_b200.read_fastx(str(tmp_path / "missing.fa"))
+    assert e.value.kind == "IoError"
+    bad = tmp_path / "bad.fq"
+    bad.write_bytes(b"@r1\nACGT\n+\nII\n")                 # quality shorter than sequence
+    with pytest.raises(lrge_b200.LrgeError) as e:
+        lrge_b200.read_fastx(str(bad))
+    assert e.value.kind == "FastqParseError"
+    bz = tmp_path / "r.fa.bz2"
+    bz.write_bytes(b"BZh91AY&SY")                          # io.rs:47-48 magic bytes
+    with pytest.raises(lrge_b200.LrgeError) as e:
+        lrge_b200.read_fastx(str(bz))
+    assert e.value.kind == "Unsupported"
