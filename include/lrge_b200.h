@@ -86,13 +86,14 @@ typedef struct lrge_stats {
     uint64_t n_overlaps;         /* pairs with at least one kept chain that passes the -F filter */
     uint32_t no_mapping_count;   /* twoset.rs:303-309 / ava.rs:329-330 semantics */
     int32_t  mid_occ;
-    uint32_t n_batches;
+    uint32_t n_batches;          /* shared-memory rounds of the fused kernel + query batches of the global path */
     uint32_t n_kernel_launches;
     /* device time per stage in ms (CUDA events on the context's stream) */
     float ms_h2d, ms_pack, ms_sketch, ms_index, ms_seed, ms_sort, ms_chain, ms_d2h, ms_total;
     float ms_chain_kernel;       /* the chaining kernel alone, summed over batches (0 unless lrge_gpu_set_profiling is on) */
     float ms_comm;               /* NCCL reduction of the per-read counts */
-    float reserved[5];
+    uint32_t n_deferred;         /* queries the fused shared-memory kernel handed to the global-memory path */
+    float reserved[4];
 } lrge_stats;
 
 typedef struct lrge_ctx lrge_ctx;

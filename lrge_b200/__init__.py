@@ -76,7 +76,7 @@ class Stats(ctypes.Structure):
         ("ms_index", ctypes.c_float), ("ms_seed", ctypes.c_float), ("ms_sort", ctypes.c_float),
         ("ms_chain", ctypes.c_float), ("ms_d2h", ctypes.c_float), ("ms_total", ctypes.c_float),
         ("ms_chain_kernel", ctypes.c_float), ("ms_comm", ctypes.c_float),
-        ("reserved", ctypes.c_float * 5),
+        ("n_deferred", ctypes.c_uint32), ("reserved", ctypes.c_float * 4),
     ]
 
     def as_dict(self):
@@ -87,7 +87,8 @@ _LIB = None
 
 
 def library_path() -> str:
-    return os.path.join(csrc_dir(), "liblrge_b200.so")
+    # LRGE_B200_LIB: tests load the test-only build (liblrge_b200_v1check.so) in a subprocess
+    return os.environ.get("LRGE_B200_LIB") or os.path.join(csrc_dir(), "liblrge_b200.so")
 
 
 def lib():

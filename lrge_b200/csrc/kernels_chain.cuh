@@ -58,6 +58,20 @@ struct CountOut {
     int names_unique;            // target names are unique: device-side counting is exact
 };
 
+struct ChainCoord { int32_t a_first, a_last, sc, cnt; };   // local anchor indices of the chain ends
+
+// Sorted anchors of one group as the DP reads them: [i] -> (x = target position, y = q_span << 24 | query position').
+// AncAoS: compact uint2 records in HBM (global path, after group_mark_kernel).
+// AncSoA: the shared-memory sort buffers of the fused per-query kernel (key array + payload array), used in place.
+struct AncAoS {
+    const uint2 *p;
+    __device__ __forceinline__ uint2 operator[](int32_t i) const { return p[i]; }
+};
+template <typename KT> struct AncSoA {
+    const KT *k; const uint32_t *v; KT posmask;
+    __device__ __forceinline__ uint2 operator[](int32_t i) const { return make_uint2((uint32_t)(k[i] & posmask), v[i]); }
+};
+
 __device__ __forceinline__ int32_t comput_sc(int32_t ri, int32_t qi, int32_t rj, int32_t qj, int32_t span_j,
                                              const ChainParams &P) {
     const int32_t dq = qi - qj;
@@ -71,153 +85,6 @@ __device__ __forceinline__ int32_t comput_sc(int32_t ri, int32_t qi, int32_t rj,
     if (dd || dg > span_j) sc -= P.pen[dd];
     return sc;
 }
-
-// mg_lchain_dp over one (target, strand) group of n anchors starting at g0. Fills f/p (p local, -1 none).
-__device__ void group_dp(const uint64_t *akey, const uint32_t *aval, uint32_t g0, int32_t n, uint64_t posmask,
-                         const ChainParams &P, int32_t *f, int32_t *p, int32_t *t) {
-    int32_t st = 0, max_ii = -1;
-    for (int32_t i = 0; i < n; ++i) {
-        const int32_t ri = (int32_t)(akey[g0 + i] & posmask);
-        const uint32_t vi = aval[g0 + i];
-        const int32_t qi = (int32_t)(vi & 0xffffff);
-        int32_t max_j = -1, max_f = (int32_t)(vi >> 24), n_skip = 0, end_j, j;
-        while (st < i && ri > (int32_t)(akey[g0 + st] & posmask) + P.max_dist_x) ++st;
-        if (i - st > P.max_iter) st = i - P.max_iter;
-        for (j = i - 1; j >= st; --j) {
-            const uint32_t vj = aval[g0 + j];
-            int32_t sc = comput_sc(ri, qi, (int32_t)(akey[g0 + j] & posmask), (int32_t)(vj & 0xffffff), (int32_t)(vj >> 24), P);
-            if (sc == INT32_MIN) continue;
-            sc += f[g0 + j];
-            if (sc > max_f) {
-                max_f = sc, max_j = j;
-                if (n_skip > 0) --n_skip;
-            } else if (t[g0 + j] == i) {
-                if (++n_skip > P.max_skip) break;
-            }
-            if (p[g0 + j] >= 0) t[g0 + p[g0 + j]] = i;
-        }
-        end_j = j;
-        if (max_ii < 0 || ri - (int32_t)(akey[g0 + max_ii] & posmask) > P.max_dist_x) {
-            int32_t mx = INT32_MIN;
-            max_ii = -1;
-            for (j = i - 1; j >= st; --j)
-                if (mx < f[g0 + j]) mx = f[g0 + j], max_ii = j;
-        }
-        if (max_ii >= 0 && max_ii < end_j) {
-            const uint32_t vj = aval[g0 + max_ii];
-            const int32_t tmp = comput_sc(ri, qi, (int32_t)(akey[g0 + max_ii] & posmask), (int32_t)(vj & 0xffffff), (int32_t)(vj >> 24), P);
-            if (tmp != INT32_MIN && max_f < tmp + f[g0 + max_ii]) max_f = tmp + f[g0 + max_ii], max_j = max_ii;
-        }
-        f[g0 + i] = max_f, p[g0 + i] = max_j;
-        if (max_ii < 0 || (ri - (int32_t)(akey[g0 + max_ii] & posmask) <= P.max_dist_x && f[g0 + max_ii] < f[g0 + i])) max_ii = i;
-    }
-}
-
-struct ChainCoord { int32_t a_first, a_last, sc, cnt; };   // local anchor indices of the chain ends
-
-// mg_chain_backtrack over one group, visiting chain starts in the reference's order and calling
-// `on_chain` for every kept chain until it returns true (stop).  t[] is reused as the visit marks.
-template <typename F>
-__device__ void group_backtrack(uint32_t g0, int32_t n, const ChainParams &P, const int32_t *f, const int32_t *p,
-                                int32_t *t, F on_chain) {
-    for (int32_t i = 0; i < n; ++i) t[g0 + i] = 0;
-    int32_t last_f = INT32_MAX, last_i = n;
-    for (;;) {
-        // next z entry: largest (f, i) below (last_f, last_i) with f >= min_sc
-        int32_t best = -1, bf = INT32_MIN;
-        for (int32_t i = 0; i < n; ++i) {
-            const int32_t fi = f[g0 + i];
-            if (fi < P.min_sc) continue;
-            if (fi > last_f || (fi == last_f && i >= last_i)) continue;
-            if (fi > bf || (fi == bf && i > best)) bf = fi, best = i;
-        }
-        if (best < 0) break;
-        last_f = bf, last_i = best;
-        if (t[g0 + best] != 0) continue;
-        // mg_chain_bk_end
-        int32_t i = best, end_i = -1, max_i = best, max_s = 0;
-        do {
-            int32_t s;
-            t[g0 + i] = 2;
-            end_i = i = p[g0 + i];
-            s = i < 0 ? bf : bf - f[g0 + i];
-            if (s > max_s) max_s = s, max_i = i;
-            else if (max_s - s > P.bw) break;
-        } while (i >= 0 && t[g0 + i] == 0);
-        for (i = best; i >= 0 && i != end_i; i = p[g0 + i]) t[g0 + i] = 0;
-        end_i = max_i;
-        // mark the chain
-        int32_t cnt = 0, first = best;
-        for (i = best; i != end_i; i = p[g0 + i]) { ++cnt; t[g0 + i] = 1; first = i; }
-        const int32_t sc = i < 0 ? bf : bf - f[g0 + i];
-        if (sc >= P.min_sc && cnt > 0 && cnt >= P.min_cnt) {
-            ChainCoord c; c.a_first = first; c.a_last = best; c.sc = sc; c.cnt = cnt;
-            if (on_chain(c)) return;
-        }
-    }
-}
-
-// v1: one thread per (query, target) pair, literal sequential semantics.
-__global__ void __launch_bounds__(128) chain_pair_kernel(PairTask T, ChainParams P, CountOut O) {
-    const uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pi >= T.n_pairs) return;
-    const uint32_t a0 = T.pstart[pi], a1 = T.pstart[pi + 1];
-    const uint64_t posmask = (1ULL << T.PB) - 1;
-    const uint64_t k0 = T.akey[a0];
-    const uint32_t rid = (uint32_t)((k0 >> (T.PB + 1)) & ((1ULL << T.RB) - 1));
-    const uint32_t qid = T.q0 + (uint32_t)(k0 >> (T.PB + 1 + T.RB));
-    // split point between strands: first anchor with the strand bit set
-    uint32_t lo = a0, hi = a1;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((T.akey[mid] >> T.PB) & 1) hi = mid; else lo = mid + 1; }
-    const uint32_t split = lo;
-    const int32_t qlen = (int32_t)O.len_q[qid], tlen = (int32_t)O.len_t[rid];
-    int kept = 0, pass = 0;
-    for (int strand = 0; strand < 2 && !pass; ++strand) {
-        const uint32_t g0 = strand ? split : a0;
-        const int32_t n = (int32_t)(strand ? a1 - split : split - a0);
-        if (n < P.min_cnt) continue;
-        group_dp(T.akey, T.aval, g0, n, posmask, P, T.f, T.p, T.t);
-        group_backtrack(g0, n, P, T.f, T.p, T.t, [&](const ChainCoord &c) -> bool {
-            kept = 1;
-            if (!O.remove_internal) { pass = 1; return true; }
-            // mm_reg_set_coor (hit.c) then PafRecord::is_internal (mapping.rs:59-77)
-            const uint32_t vf = T.aval[g0 + c.a_first], vl = T.aval[g0 + c.a_last];
-            const int32_t span0 = (int32_t)(vf >> 24);
-            const int32_t x0 = (int32_t)(T.akey[g0 + c.a_first] & posmask), x1 = (int32_t)(T.akey[g0 + c.a_last] & posmask);
-            const int32_t y0 = (int32_t)(vf & 0xffffff), y1 = (int32_t)(vl & 0xffffff);
-            const int32_t rs = x0 + 1 > span0 ? x0 + 1 - span0 : 0, re = x1 + 1;
-            int32_t qs, qe;
-            if (!strand) { qs = y0 + 1 - span0; qe = y1 + 1; }
-            else { qs = qlen - (y1 + 1); qe = qlen - (y0 + 1 - span0); }
-            int32_t overhang, maplen;
-            if (!strand) overhang = min(qs, rs) + min(qlen - qe, tlen - re);
-            else overhang = min(qs, tlen - re) + min(qlen - qe, rs);
-            maplen = max(qe - qs, re - rs);
-            bool drop;
-            if (O.mode == 2) drop = overhang > (int32_t)__fmul_rn((float)maplen, O.ratio);          // twoset.rs:514-517
-            else drop = __fdiv_rn((float)overhang, (float)maplen) < O.ratio;                          // mapping.rs:75-76
-            if (!drop) { pass = 1; return true; }
-            return false;
-        });
-    }
-    O.pair_res[pi] = (uint8_t)(kept | pass << 1);
-    if (O.mode == 0) {
-        if (kept) O.had_mapping[qid] = 1;
-        if (pass && O.names_unique) atomicAdd(&O.counts[qid], 1u);
-    } else if (O.mode == 1) {
-        if (pass && O.rank_q[qid] != O.rank_t[rid]) { atomicAdd(&O.counts[qid], 1u); atomicAdd(&O.counts[rid], 1u); }
-    } else {
-        if (pass) atomicAdd(&O.counts[rid], 1u);
-    }
-}
-
-// flags[i] = 1 where a new (query, target) pair starts
-__global__ void pair_flag_kernel(const uint64_t *__restrict__ akey, uint64_t n, int shift, uint8_t *__restrict__ flags) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    flags[i] = (i == 0 || (akey[i] >> shift) != (akey[i - 1] >> shift)) ? 1 : 0;
-}
-
 
 // =================================================================================================
 // v2: one WARP per (query, target, strand) group; anchors i are processed in order, the predecessors
@@ -285,7 +152,8 @@ __device__ __forceinline__ int32_t comput_sc_smem(int32_t ri, int32_t qi, int32_
 
 // mg_lchain_dp for one group, warp-cooperative.  Returns the first anchor whose score reaches stop_sc (the DP is
 // causal, so f[0..i] are final at that point), or -1 after the whole group.
-__device__ int32_t warp_group_dp(const uint2 *__restrict__ anc, int32_t n, const ChainParams &P, const uint8_t *s_pen,
+template <typename A>
+__device__ int32_t warp_group_dp(const A anc, int32_t n, const ChainParams &P, const uint8_t *s_pen,
                                  int2 *fp, int32_t *t, uint32_t lane, int32_t stop_sc) {
     int32_t st = 0, r_st = n > 0 ? (int32_t)anc[0].x : 0, max_ii = -1, r_maxii = 0, f_maxii = 0;
     const uint32_t le_mask = lane == 31 ? 0xffffffffu : ((2u << lane) - 1);
@@ -475,13 +343,95 @@ __device__ void warp_group_backtrack(int32_t n, const ChainParams &P, const int2
     }
 }
 
+// One (query, target, strand) group: DP (+ backtrack where needed) and the overlap decision.  All lanes of the warp
+// call it with uniform arguments; kept = the group yields a kept chain, pass = one of them also survives -F.
+template <typename A>
+__device__ void chain_one_group(const A anc, int32_t n, int2 *fp, int32_t *t, const ChainParams &P, const uint8_t *s_pen,
+                                const CountOut &O, uint32_t lane, uint32_t qid, uint32_t rid, int strand, int &kept, int &pass) {
+    const int32_t qlen = (int32_t)O.len_q[qid], tlen = (int32_t)O.len_t[rid];
+    kept = 0; pass = 0;
+    bool full = true;
+    if (!O.remove_internal && !O.regs) {
+        // Counting only needs "does this group yield a kept chain".  The chain extracted first starts at the group's
+        // highest f; nothing is used yet and no predecessor scores above the start, so mg_chain_bk_end keeps
+        // sc >= min(f_max, max_drop) -- and with every span <= (min_sc-1)/(min_cnt-1) a score >= min_sc needs
+        // >= min_cnt anchors.  Hence: kept chain exists <=> some f[i] >= min_sc, and the DP can stop there.
+        const int32_t hit = warp_group_dp(anc, n, P, s_pen, fp, t, lane, P.min_sc);
+        full = false;
+        if (hit >= 0) {
+            int32_t mspan = 0;
+            if (!P.span_bound_ok) {
+                for (int32_t i = lane; i < n; i += 32) mspan = max(mspan, (int32_t)(anc[i].y >> 24));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mspan = max(mspan, __shfl_xor_sync(0xffffffffu, mspan, o));
+            }
+            if (P.span_bound_ok || (mspan * (P.min_cnt - 1) < P.min_sc && P.bw >= P.min_sc)) kept = pass = 1;
+            else {                                                  // HPC group with a very long span: literal path
+                for (int32_t i = lane; i < n; i += 32) t[i] = 0;
+                __syncwarp();
+                full = true;
+            }
+        }
+    }
+    if (!full) return;
+    warp_group_dp(anc, n, P, s_pen, fp, t, lane, INT32_MAX);
+    __syncwarp();
+    warp_group_backtrack(n, P, fp, t, lane, [&](const ChainCoord &c) -> bool {
+        kept = 1;
+        if (!O.remove_internal && !O.regs) { pass = 1; return true; }
+        // mm_reg_set_coor (hit.c)
+        const uint2 af = anc[c.a_first], al = anc[c.a_last];
+        const int32_t span0 = (int32_t)(af.y >> 24);
+        const int32_t x0 = (int32_t)af.x, x1 = (int32_t)al.x;
+        const int32_t y0 = (int32_t)(af.y & 0xffffff), y1 = (int32_t)(al.y & 0xffffff);
+        const int32_t rs = x0 + 1 > span0 ? x0 + 1 - span0 : 0, re = x1 + 1;
+        int32_t qs, qe;
+        if (!strand) { qs = y0 + 1 - span0; qe = y1 + 1; }
+        else { qs = qlen - (y1 + 1); qe = qlen - (y0 + 1 - span0); }
+        bool drop = false;
+        if (O.remove_internal) {                                // PafRecord::is_internal / the inverse path's inline test
+            int32_t overhang;
+            if (!strand) overhang = min(qs, rs) + min(qlen - qe, tlen - re);
+            else overhang = min(qs, tlen - re) + min(qlen - qe, rs);
+            const int32_t maplen = max(qe - qs, re - rs);
+            if (O.mode == 2) drop = overhang > (int32_t)__fmul_rn((float)maplen, O.ratio);
+            else drop = __fdiv_rn((float)overhang, (float)maplen) < O.ratio;
+        }
+        if (!drop) pass = 1;
+        if (O.regs) {
+            if (lane == 0) {
+                // mm_cal_fuzzy_len (hit.c): walk the chain once more, last anchor -> first
+                int32_t mlen = span0, blen = span0;
+                for (int32_t i = c.a_last; i != c.a_first;) {
+                    const int32_t pi = fp[i].y;
+                    const uint2 a1 = anc[i], a0 = anc[pi];
+                    const int32_t span = (int32_t)(a1.y >> 24);
+                    const int32_t tl = (int32_t)a1.x - (int32_t)a0.x, ql = (int32_t)(a1.y & 0xffffff) - (int32_t)(a0.y & 0xffffff);
+                    blen += tl > ql ? tl : ql;
+                    mlen += (tl > span && ql > span) ? span : (tl < ql ? tl : ql);
+                    i = pi;
+                }
+                const unsigned long long slot = atomicAdd(O.n_regs, 1ull);
+                if (slot < O.regs_cap) {
+                    RegOut r; r.qid = qid; r.rid = rid; r.rev = strand; r.qs = qs; r.qe = qe; r.rs = rs; r.re = re;
+                    r.score = c.sc; r.cnt = c.cnt; r.mlen = mlen; r.blen = blen;
+                    O.regs[slot] = r;
+                }
+            }
+            return false;                                       // every chain of the group is reported
+        }
+        return !drop;
+    });
+}
+
+// Global path (queries whose anchors do not fit the fused kernel's shared-memory rounds): one warp per group of the
+// globally sorted anchor array, persistent CTAs pulling groups largest-first from an atomic work counter.
 __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, ChainParams P, CountOut O) {
     __shared__ uint8_t s_pen[2048];
     for (int i = threadIdx.x; i <= P.bw && i < 2048; i += blockDim.x) s_pen[i] = (uint8_t)P.pen[i];
     __syncthreads();
     const uint32_t lane = lane_id();
     const uint32_t c0 = T.gcount[0], c1 = c0 + T.gcount[1], c2 = c1 + T.gcount[2], total = c2 + T.gcount[3];
-    const uint64_t posmask = (1ULL << T.PB) - 1;
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(T.work_ctr, 1u);
@@ -498,84 +448,8 @@ __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, Ch
         const int strand = (int)((k0 >> T.PB) & 1);
         const uint32_t rid = (uint32_t)((k0 >> (T.PB + 1)) & ((1ULL << T.RB) - 1));
         const uint32_t qid = T.q0 + (uint32_t)(k0 >> (T.PB + 1 + T.RB));
-        const uint2 *anc = T.anc + g0;
-        int2 *fp = T.fp + g0;
-        int32_t *t = T.t + g0;
-        const int32_t qlen = (int32_t)O.len_q[qid], tlen = (int32_t)O.len_t[rid];
         int kept = 0, pass = 0;
-        bool full = true;
-        if (!O.remove_internal && !O.regs) {
-            // Counting only needs "does this group yield a kept chain".  The chain extracted first starts at the group's
-            // highest f; nothing is used yet and no predecessor scores above the start, so mg_chain_bk_end keeps
-            // sc >= min(f_max, max_drop) -- and with every span <= (min_sc-1)/(min_cnt-1) a score >= min_sc needs
-            // >= min_cnt anchors.  Hence: kept chain exists <=> some f[i] >= min_sc, and the DP can stop there.
-            const int32_t hit = warp_group_dp(anc, n, P, s_pen, fp, t, lane, P.min_sc);
-            full = false;
-            if (hit >= 0) {
-                int32_t mspan = 0;
-                if (!P.span_bound_ok) {
-                    for (int32_t i = lane; i < n; i += 32) mspan = max(mspan, (int32_t)(anc[i].y >> 24));
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) mspan = max(mspan, __shfl_xor_sync(0xffffffffu, mspan, o));
-                }
-                if (P.span_bound_ok || (mspan * (P.min_cnt - 1) < P.min_sc && P.bw >= P.min_sc)) kept = pass = 1;
-                else {                                                  // HPC group with a very long span: literal path
-                    for (int32_t i = lane; i < n; i += 32) t[i] = 0;
-                    __syncwarp();
-                    full = true;
-                }
-            }
-        }
-        if (full) {
-            warp_group_dp(anc, n, P, s_pen, fp, t, lane, INT32_MAX);
-            __syncwarp();
-            warp_group_backtrack(n, P, fp, t, lane, [&](const ChainCoord &c) -> bool {
-                kept = 1;
-                if (!O.remove_internal && !O.regs) { pass = 1; return true; }
-                // mm_reg_set_coor (hit.c)
-                const uint2 af = anc[c.a_first], al = anc[c.a_last];
-                const int32_t span0 = (int32_t)(af.y >> 24);
-                const int32_t x0 = (int32_t)af.x, x1 = (int32_t)al.x;
-                const int32_t y0 = (int32_t)(af.y & 0xffffff), y1 = (int32_t)(al.y & 0xffffff);
-                const int32_t rs = x0 + 1 > span0 ? x0 + 1 - span0 : 0, re = x1 + 1;
-                int32_t qs, qe;
-                if (!strand) { qs = y0 + 1 - span0; qe = y1 + 1; }
-                else { qs = qlen - (y1 + 1); qe = qlen - (y0 + 1 - span0); }
-                bool drop = false;
-                if (O.remove_internal) {                                // PafRecord::is_internal / the inverse path's inline test
-                    int32_t overhang;
-                    if (!strand) overhang = min(qs, rs) + min(qlen - qe, tlen - re);
-                    else overhang = min(qs, tlen - re) + min(qlen - qe, rs);
-                    const int32_t maplen = max(qe - qs, re - rs);
-                    if (O.mode == 2) drop = overhang > (int32_t)__fmul_rn((float)maplen, O.ratio);
-                    else drop = __fdiv_rn((float)overhang, (float)maplen) < O.ratio;
-                }
-                if (!drop) pass = 1;
-                if (O.regs) {
-                    if (lane == 0) {
-                        // mm_cal_fuzzy_len (hit.c): walk the chain once more, last anchor -> first
-                        int32_t mlen = span0, blen = span0;
-                        for (int32_t i = c.a_last; i != c.a_first;) {
-                            const int32_t pi = fp[i].y;
-                            const uint2 a1 = anc[i], a0 = anc[pi];
-                            const int32_t span = (int32_t)(a1.y >> 24);
-                            const int32_t tl = (int32_t)a1.x - (int32_t)a0.x, ql = (int32_t)(a1.y & 0xffffff) - (int32_t)(a0.y & 0xffffff);
-                            blen += tl > ql ? tl : ql;
-                            mlen += (tl > span && ql > span) ? span : (tl < ql ? tl : ql);
-                            i = pi;
-                        }
-                        const unsigned long long slot = atomicAdd(O.n_regs, 1ull);
-                        if (slot < O.regs_cap) {
-                            RegOut r; r.qid = qid; r.rid = rid; r.rev = strand; r.qs = qs; r.qe = qe; r.rs = rs; r.re = re;
-                            r.score = c.sc; r.cnt = c.cnt; r.mlen = mlen; r.blen = blen;
-                            O.regs[slot] = r;
-                        }
-                    }
-                    return false;                                       // every chain of the group is reported
-                }
-                return !drop;
-            });
-        }
+        chain_one_group(AncAoS{T.anc + g0}, n, T.fp + g0, T.t + g0, P, s_pen, O, lane, qid, rid, strand, kept, pass);
         if (lane == 0 && kept) {
             // the two strand groups of one (query, target) pair share a slot: the forward group's
             uint32_t slot = g;
@@ -587,7 +461,6 @@ __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, Ch
                 else atomicAdd(&O.counts[rid], 1u);
             }
         }
-        (void)posmask;
     }
 }
 

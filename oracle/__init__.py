@@ -57,7 +57,8 @@ class Stats(ctypes.Structure):
         ("n_chains", ctypes.c_uint64), ("n_dp_iter", ctypes.c_uint64), ("n_overlaps", ctypes.c_uint64),
         ("no_mapping_count", ctypes.c_uint32), ("mid_occ", ctypes.c_int32),
         ("t_index_s", ctypes.c_double), ("t_map_s", ctypes.c_double),
-        ("n_tie_x_queries", ctypes.c_uint64),
+        ("n_tie_x_queries", ctypes.c_uint64), ("n_tie_x_anchors", ctypes.c_uint64), ("n_mz_flt_deleted", ctypes.c_uint64),
+        ("n_max_iter_clamp", ctypes.c_uint64), ("n_skip_break", ctypes.c_uint64), ("n_occ_filtered", ctypes.c_uint64),
     ]
 
     def as_dict(self):

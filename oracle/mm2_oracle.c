@@ -533,7 +533,7 @@ typedef struct {
     const uint64_t *cr;
 } seed_t;
 
-static void seed_mz_flt(v128_t *mv, int32_t q_occ_max, float q_occ_frac) {
+static void seed_mz_flt(v128_t *mv, int32_t q_occ_max, float q_occ_frac, orc_stats_t *st_) {
     orc128_t *a;
     size_t i, j, st;
     if (mv->n <= (size_t)q_occ_max || q_occ_frac <= 0.0f || q_occ_max <= 0) return;
@@ -544,7 +544,10 @@ static void seed_mz_flt(v128_t *mv, int32_t q_occ_max, float q_occ_frac) {
         if (i == mv->n || a[i].x != a[st].x) {
             int32_t cnt = (int32_t)(i - st);
             if (cnt > q_occ_max && cnt > mv->n * q_occ_frac)
+            {
                 for (j = st; j < i; ++j) mv->a[a[j].y].x = 0;
+                if (st_) st_->n_mz_flt_deleted += cnt;
+            }
             st = i;
         }
     }
@@ -574,12 +577,12 @@ static seed_t *seed_collect_all(const orc_index_t *mi, const v128_t *mv, int32_t
 }
 
 /* occ_dist == 0 for both presets -> the plain "n > max_occ => filtered" branch */
-static seed_t *collect_matches(int *_n_m, int max_occ, const orc_index_t *mi, const v128_t *mv, int64_t *n_a, int *rep_len) {
+static seed_t *collect_matches(int *_n_m, int max_occ, const orc_index_t *mi, const v128_t *mv, int64_t *n_a, int *rep_len, uint64_t *n_flt) {
     int rep_st = 0, rep_en = 0, n_m, n_m0;
     int i;
     seed_t *m = seed_collect_all(mi, mv, &n_m0);
     for (i = 0; i < n_m0; ++i)
-        if (m[i].n > (uint32_t)max_occ) m[i].flt = 1;
+        if (m[i].n > (uint32_t)max_occ) { m[i].flt = 1; if (n_flt) ++*n_flt; }
     for (i = 0, n_m = 0, *rep_len = 0, *n_a = 0; i < n_m0; ++i) {
         seed_t *q = &m[i];
         if (q->flt) {
@@ -618,7 +621,7 @@ static int skip_seed(int64_t flag, uint64_t r, const seed_t *q, const char *qnam
 static orc128_t *collect_seed_hits(const orc_opt_t *opt, int max_occ, const orc_index_t *mi, const char *qname,
                                    const v128_t *mv, int qlen, int64_t *n_a, int *rep_len, orc_stats_t *st) {
     int i, n_m;
-    seed_t *m = collect_matches(&n_m, max_occ, mi, mv, n_a, rep_len);
+    seed_t *m = collect_matches(&n_m, max_occ, mi, mv, n_a, rep_len, st ? &st->n_occ_filtered : 0);
     orc128_t *a = (orc128_t*)malloc((*n_a ? *n_a : 1) * sizeof(orc128_t));
     if (st) { st->n_seeds += n_m; st->n_hits += *n_a; }
     for (i = 0, *n_a = 0; i < n_m; ++i) {
@@ -793,7 +796,7 @@ static orc128_t *lchain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip,
         int64_t max_j = -1, end_j;
         int32_t max_f = a[i].y >> 32 & 0xff, n_skip = 0;
         while (st < i && (a[i].x >> 32 != a[st].x >> 32 || a[i].x > a[st].x + max_dist_x)) ++st;
-        if (i - st > max_iter) st = i - max_iter;
+        if (i - st > max_iter) { st = i - max_iter; if (st_) ++st_->n_max_iter_clamp; }
         for (j = i - 1; j >= st; --j) {
             int32_t sc;
             sc = comput_sc(&a[i], &a[j], max_dist_x, max_dist_y, bw, chn_pen_gap, chn_pen_skip);
@@ -804,7 +807,7 @@ static orc128_t *lchain_dp(int max_dist_x, int max_dist_y, int bw, int max_skip,
                 max_f = sc, max_j = j;
                 if (n_skip > 0) --n_skip;
             } else if (t[j] == (int32_t)i) {
-                if (++n_skip > max_skip) break;
+                if (++n_skip > max_skip) { if (st_) ++st_->n_skip_break; break; }
             }
             if (p[j] >= 0) t[p[j]] = (int32_t)i;
         }
@@ -940,12 +943,15 @@ int orc_map(const orc_index_t *mi, const orc_opt_t *opt, const uint8_t *seq, int
 
     mm_sketch(seq, qlen, mi->w, mi->k, 0, mi->is_hpc, &mv);     /* collect_minimizers; sdust_thres == 0 */
     if (st) st->n_q_minimizers += mv.n;
-    if (opt->q_occ_frac > 0.0f) seed_mz_flt(&mv, opt->mid_occ, opt->q_occ_frac);
+    if (opt->q_occ_frac > 0.0f) seed_mz_flt(&mv, opt->mid_occ, opt->q_occ_frac, st);
     a = collect_seed_hits(opt, opt->mid_occ, mi, qname, &mv, qlen, &n_a, &rep_len, st);
     free(mv.a);
     if (st) {
         st->n_anchors += n_a;
-        for (int64_t i = 1; i < n_a; ++i) if (a[i].x == a[i - 1].x) { ++st->n_tie_x_queries; break; }
+        int64_t ties = 0;
+        for (int64_t i = 1; i < n_a; ++i) if (a[i].x == a[i - 1].x) ++ties;
+        st->n_tie_x_anchors += ties;
+        if (ties) ++st->n_tie_x_queries;
     }
     if (anchors) {
         *anchors = (orc128_t*)malloc((n_a ? n_a : 1) * sizeof(orc128_t));
@@ -1072,7 +1078,9 @@ static void *map_thread(void *arg) {
     pthread_mutex_lock(&j->mu);
     j->st.n_q_minimizers += st.n_q_minimizers; j->st.n_seeds += st.n_seeds; j->st.n_hits += st.n_hits;
     j->st.n_anchors += st.n_anchors; j->st.n_chains += st.n_chains; j->st.n_dp_iter += st.n_dp_iter;
-    j->st.n_tie_x_queries += st.n_tie_x_queries;
+    j->st.n_tie_x_queries += st.n_tie_x_queries; j->st.n_tie_x_anchors += st.n_tie_x_anchors;
+    j->st.n_mz_flt_deleted += st.n_mz_flt_deleted; j->st.n_max_iter_clamp += st.n_max_iter_clamp;
+    j->st.n_skip_break += st.n_skip_break; j->st.n_occ_filtered += st.n_occ_filtered;
     pthread_mutex_unlock(&j->mu);
     return 0;
 }

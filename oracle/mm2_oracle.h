@@ -84,6 +84,12 @@ typedef struct {
     int32_t  mid_occ;
     double   t_index_s, t_map_s;
     uint64_t n_tie_x_queries;    /* queries holding >=2 anchors with identical x */
+    /* which order-dependent branches the inputs exercised (test reporting only) */
+    uint64_t n_tie_x_anchors;    /* anchors whose x equals the previous anchor's */
+    uint64_t n_mz_flt_deleted;   /* query minimizers deleted by mm_seed_mz_flt */
+    uint64_t n_max_iter_clamp;   /* DP rows whose window was clamped to max_chain_iter */
+    uint64_t n_skip_break;       /* DP rows left through the max_chain_skip break */
+    uint64_t n_occ_filtered;     /* seeds dropped because n > mid_occ */
 } orc_stats_t;
 
 typedef struct orc_index_s orc_index_t;

@@ -196,20 +196,35 @@ def test_strategy_estimates_match_oracle(ctx):
     assert abs(r.estimate - 300_000) / 300_000 < 0.5
 
 
+_V1_SNIPPET = """
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import lrge_b200
+from lrge_b200 import readsim
+from test_gpu_parity import small_sets
+T, Q = small_sets(nt=400, nq=150, mean=5000, gsize=250_000, err=readsim.ONT if {platform!r} == "ont" else readsim.HIFI)
+with lrge_b200.Context(0) as c:
+    r = c.twoset_counts(T, Q, {platform!r}, remove_internal={F!r})
+np.savez({out!r}, counts=r.counts, had=r.had_mapping)
+"""
+
+
 @pytest.mark.parametrize("platform,F", [("ont", True), ("ont", False), ("pb", False), ("pb", True)])
-def test_chain_kernels_agree(ctx, monkeypatch, platform, F):
-    """The warp-per-group chaining kernel (early-exit counting when F is off, full DP + backtrack when on) against
-    the literal thread-per-pair one (LRGE_CHAIN_V1=1: always full DP + backtrack)."""
+def test_chain_kernels_agree(ctx, tmp_path, platform, F):
+    """The product's kernels (fused shared-memory path; early-exit counting when F is off, full DP + backtrack when on)
+    against the literal thread-per-pair kernel, which only exists in the test build liblrge_b200_v1check.so
+    (tests/native/kernels_chain_v1.cuh; always full DP + backtrack), run in a subprocess."""
+    import os, subprocess, sys
+    from lrge_b200.readset import csrc_dir
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     T, Q = small_sets(nt=400, nq=150, mean=5000, gsize=250_000, err=readsim.ONT if platform == "ont" else readsim.HIFI)
     a = ctx.twoset_counts(T, Q, platform, remove_internal=F)
-    monkeypatch.setenv("LRGE_CHAIN_V1", "1")
-    c1 = lrge_b200.Context(0)
-    try:
-        b = c1.twoset_counts(T, Q, platform, remove_internal=F)
-    finally:
-        c1.close()
-    assert np.array_equal(a.counts, b.counts)
-    assert np.array_equal(a.had_mapping, b.had_mapping)
+    out = str(tmp_path / "v1.npz")
+    env = dict(os.environ, LRGE_B200_LIB=os.path.join(csrc_dir(), "liblrge_b200_v1check.so"), LRGE_CHAIN_V1="1", LRGE_FORCE_GLOBAL="1")
+    subprocess.run([sys.executable, "-c", _V1_SNIPPET.format(root=root, platform=platform, F=F, out=out)], check=True, env=env, timeout=600)
+    b = np.load(out)
+    assert np.array_equal(a.counts, b["counts"])
+    assert np.array_equal(a.had_mapping, b["had"])
     assert a.counts.sum() > 0
 
 
@@ -234,9 +249,10 @@ def test_long_span_hpc_group_takes_literal_path(ctx):
 
 
 def test_query_batching(ctx, monkeypatch):
-    """Anchors are processed in query batches sized from device memory; force many small batches."""
+    """Global-memory path: anchors are processed in query batches sized from device memory; force many small batches."""
     T, Q = small_sets()
     full = ctx.twoset_counts(T, Q, "ont")
+    monkeypatch.setenv("LRGE_FORCE_GLOBAL", "1")
     monkeypatch.setenv("LRGE_MAX_ANCHORS", "6000")
     c1 = lrge_b200.Context(0)
     try:
@@ -333,3 +349,148 @@ def test_shard_block_staging_and_sketch(ctx, platform):
         assert np.array_equal(x, want["x"][a:b]) and np.array_equal(y, want["y"][a:b])
         seen += x.shape[0]
     assert seen == want.shape[0]
+
+
+# ---- the fused shared-memory path (default) vs the global-memory path vs the oracle -----------------------------
+
+def _ctx_with(monkeypatch, **env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    return lrge_b200.Context(0)
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_global_path_parity(ctx, monkeypatch, platform):
+    """LRGE_FORCE_GLOBAL=1 sends every query through the global-memory pipeline (device-wide sort, warp per group):
+    counts, had_mapping, anchor totals and overlap records must equal the fused path's and the oracle's."""
+    T, Q = small_sets(nt=300, nq=120, mean=4000, gsize=250_000, err=readsim.ONT if platform == "ont" else readsim.HIFI)
+    want, had, st = oracle.twoset_counts(T, Q, platform, threads=8)
+    a = ctx.twoset_counts(T, Q, platform)
+    ov_a, _ = ctx.twoset_overlaps(T, Q, platform)
+    g = _ctx_with(monkeypatch, LRGE_FORCE_GLOBAL=1)
+    try:
+        b = g.twoset_counts(T, Q, platform)
+        ov_b, _ = g.twoset_overlaps(T, Q, platform)
+        R = readsim.reads(readsim.genome(150_000), 200, 3000, readsim.ONT if platform == "ont" else readsim.HIFI, readsim.SEED_AVA, "r")
+        av_b = g.ava_counts(R, platform)
+    finally:
+        g.close()
+    for r in (a, b):
+        assert np.array_equal(r.counts, want) and np.array_equal(r.had_mapping, had)
+        assert r.stats["n_anchors"] == st["n_anchors"]
+    assert a.stats["n_deferred"] == 0 and a.stats["n_pairs"] == b.stats["n_pairs"]
+    assert _reg_set(ov_a) == _reg_set(ov_b)
+    av_want, _ = oracle.ava_counts(R, platform, threads=8)
+    assert np.array_equal(av_b.counts, av_want)
+    assert np.array_equal(ctx.ava_counts(R, platform).counts, av_want)
+
+
+@pytest.mark.parametrize("cap", [2048, 256])
+def test_fused_rounds_and_deferral(ctx, monkeypatch, cap):
+    """LRGE_MAP_CAP shrinks the shared-memory capacity of the fused kernel: queries are mapped in several rounds over
+    disjoint target ranges, and a query holding one (query, target) bin above the capacity is deferred to the global
+    path.  Results must not change."""
+    T, Q = small_sets()
+    want, had, st = oracle.twoset_counts(T, Q, "ont", threads=8)
+    g = readsim.genome(200_000)
+    R = readsim.reads(g, 250, 4000, readsim.HIFI, readsim.SEED_AVA, "r")
+    av_want, av_st = oracle.ava_counts(R, "pb", threads=8)
+    regs, qidx, _ = oracle.twoset_regs(T, Q, "ont", threads=8, tie_mode=oracle.TIE_STABLE)
+    c1 = _ctx_with(monkeypatch, LRGE_MAP_CAP=cap)
+    try:
+        b = c1.twoset_counts(T, Q, "ont")
+        bf = c1.twoset_counts(T, Q, "ont", remove_internal=True)
+        av = c1.ava_counts(R, "pb")
+        ov, _ = c1.twoset_overlaps(T, Q, "ont")
+    finally:
+        c1.close()
+    assert np.array_equal(b.counts, want) and np.array_equal(b.had_mapping, had)
+    assert b.stats["n_anchors"] == st["n_anchors"]
+    assert b.stats["n_batches"] > Q.n                       # several rounds per query
+    if cap == 256:
+        assert b.stats["n_deferred"] > 0                    # 4 kb overlaps hold > 256 anchors of one target
+    else:
+        assert b.stats["n_deferred"] == 0
+    assert np.array_equal(bf.counts, ctx.twoset_counts(T, Q, "ont", remove_internal=True).counts)
+    assert np.array_equal(av.counts, av_want) and av.stats["n_anchors"] == av_st["n_anchors"]
+    assert _reg_set(ov) == _reg_set(regs, qidx)
+
+
+def _branch_report(st):
+    return {k: int(st[k]) for k in ("mid_occ", "n_anchors", "n_tie_x_queries", "n_tie_x_anchors", "n_mz_flt_deleted",
+                                    "n_occ_filtered", "n_max_iter_clamp", "n_skip_break")}
+
+
+@pytest.mark.parametrize("platform", ["ont", "pb"])
+def test_adversarial_repeats_parity(ctx, monkeypatch, platform):
+    """Reads drawn from a genome with 2-5 kb tandem repeats, low-complexity tracts and dispersed duplications shared by
+    T and Q.  These reach the order-dependent branches uniform genomes never do (reported below): mm_seed_mz_flt
+    deletions, n > mid_occ seeds, the max_chain_iter clamp, the max_chain_skip break, equal-x anchors.
+    Counts and had_mapping are compared with the oracle in its literal (ksort) tie order; overlap records with the
+    oracle's stable tie order, which is what the CUDA sort implements."""
+    import adversarial
+    T, Q = adversarial.repeat_sets(errors=readsim.ONT if platform == "ont" else readsim.HIFI)
+    want, had, st = oracle.twoset_counts(T, Q, platform, threads=8, tie_mode=oracle.TIE_KSORT)
+    rep = _branch_report(st)
+    print("adversarial", platform, rep)
+    assert rep["n_tie_x_anchors"] > 1000 and rep["n_skip_break"] > 1000 and rep["n_occ_filtered"] > 100
+    if platform == "ont":
+        assert rep["n_mz_flt_deleted"] > 100
+    else:
+        assert rep["n_max_iter_clamp"] > 1000
+    res = ctx.twoset_counts(T, Q, platform)
+    assert res.stats["n_anchors"] == st["n_anchors"]
+    assert np.array_equal(res.counts, want) and np.array_equal(res.had_mapping, had)
+    resF = ctx.twoset_counts(T, Q, platform, remove_internal=True)
+    wantF, hadF, _ = oracle.twoset_counts(T, Q, platform, remove_internal=True, threads=8, tie_mode=oracle.TIE_STABLE)
+    assert np.array_equal(resF.counts, wantF) and np.array_equal(resF.had_mapping, hadF)
+    ov, _ = ctx.twoset_overlaps(T, Q, platform)
+    regs, qidx, _ = oracle.twoset_regs(T, Q, platform, threads=8, tie_mode=oracle.TIE_STABLE)
+    assert _reg_set(ov) == _reg_set(regs, qidx)
+    # the same inputs through the global-memory path and with the fused kernel forced into rounds
+    for env in (dict(LRGE_FORCE_GLOBAL=1), dict(LRGE_MAP_CAP=1024)):
+        c1 = _ctx_with(monkeypatch, **env)
+        try:
+            r1 = c1.twoset_counts(T, Q, platform)
+        finally:
+            c1.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        assert np.array_equal(r1.counts, want) and np.array_equal(r1.had_mapping, had)
+
+
+def test_adversarial_repeats_ava(ctx):
+    import adversarial
+    g = adversarial.repeat_genome(120_000, seed=9)
+    R = readsim.reads(g, 220, 3500, readsim.ONT, readsim.SEED_AVA, "r")
+    want, st = oracle.ava_counts(R, "ont", threads=8, tie_mode=oracle.TIE_KSORT)
+    print("adversarial ava", _branch_report(st))
+    res = ctx.ava_counts(R, "ont")
+    assert res.stats["n_anchors"] == st["n_anchors"]
+    assert np.array_equal(res.counts, want)
+
+
+def test_toy_real_reads(ctx):
+    """The reference's only real-data fixture (lrge/tests/data/toy.bam: 500 ONT reads of M. tuberculosis, decoded by
+    tests/golden/make_toy_fasta.py): all-vs-all and a two-set split, counts and records against the oracle."""
+    import os
+    R = lrge_b200.read_fastx(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "toy_reads.fa.gz"))
+    assert R.n == 500 and R.total_bases == 1272286
+    want, st = oracle.ava_counts(R, "ont", threads=8)
+    print("toy ava", _branch_report(st), "overlaps", st["n_overlaps"])
+    res = ctx.ava_counts(R, "ont")
+    assert res.stats["n_anchors"] == st["n_anchors"] and res.stats["mid_occ"] == st["mid_occ"]
+    assert np.array_equal(res.counts, want) and res.stats["n_overlaps"] == st["n_overlaps"] > 1000
+    T, Q = R.subset(range(300, 500)), R.subset(range(0, 300))
+    want2, had2, st2 = oracle.twoset_counts(T, Q, "ont", threads=8)
+    r2 = ctx.twoset_counts(T, Q, "ont")
+    assert np.array_equal(r2.counts, want2) and np.array_equal(r2.had_mapping, had2) and want2.sum() > 500
+    ov, _ = ctx.twoset_overlaps(T, Q, "ont")
+    regs, qidx, _ = oracle.twoset_regs(T, Q, "ont", threads=8, tie_mode=oracle.TIE_STABLE)
+    assert _reg_set(ov) == _reg_set(regs, qidx)
+    # the estimate the CLI would print for this split (twoset.rs:311-317, estimate.rs:55-77)
+    s = lrge_b200.TwoSetStrategy(T, Q, ctx=ctx)
+    r = s.estimate(True, lrge_b200.LOWER_QUANTILE, lrge_b200.UPPER_QUANTILE)
+    avg = np.float32(T.total_bases) / np.float32(T.n)
+    est = [oracle.per_read_estimate(int(l), avg, T.n, int(c), 100) for l, c in zip(Q.lengths(), want2)]
+    assert (r.lower, r.estimate, r.upper) == oracle.estimate(est, True, 0.15, 0.65)
