@@ -11,7 +11,11 @@ target set grows to N x 10 000 reads and is sharded in N contiguous blocks acros
 ("weak") -- and every step ends with the library's NCCL all-reduce of the per-read counts.
 
 Prints ONE JSON line on rank 0.  `value` is timed with the read sets already resident in HBM; `e2e` goes
-through the host-buffer C-ABI call with pinned inputs, H2D and D2H inside the timed region.
+through the host-buffer C-ABI call with pinned inputs, H2D and D2H inside the timed region.  Keys the driver keeps:
+  roofline      the dominant kernel against the measured HBM peak, algorithmic bytes per SURVEY.md 8(d); also carries
+                `kernels` (live per-kernel CUDA-event table), `stage_ms` and `counts` of the last step
+  cpu_baseline  the oracle port on this box's host cores; also carries `parity` (counts identical to the GPU's over
+                ALL reads) and `configs`: the other BASELINE.json configurations (C1, C3, C4) run and verified here
 """
 from __future__ import annotations
 
@@ -40,6 +44,12 @@ def workload(name: str, n_gpus: int, scale: float):
     desc = (f"{name} two-set {Q.n} query x {T.n} target synthetic ONT reads, mean 8 kb, "
             f"{readsim.CONFIGS[name][4] * scale / 1e6:.2f} Mbp genome")
     return platform, T, Q, desc
+
+
+def config_dict(desc: str):
+    """The same dict in both arms (the driver compares them)."""
+    return {"workload": desc, "targets_scale_with_gpus": True, "sharding": "N contiguous target blocks, one per GPU",
+            "l2": "256 MiB memset between timed steps; index + hit lists (> 0.5 GB) exceed L2"}
 
 
 class ClockSampler(threading.Thread):
@@ -114,8 +124,8 @@ def run_reference(args):
     platform, T, Q, desc = workload(args.config, args.gpus, args.scale)
     threads = os.cpu_count() or 1
     # Bounded sample: at N = 1 the whole workload; at N > 1 (targets x N) the full target set is indexed but only the
-    # first Q/N queries are mapped, and the whole-workload time is t_index + t_map * Q/Qs (index build does not depend
-    # on the queries; mapping cost is per query).
+    # first Q/N queries are mapped, and the whole-workload time is EXTRAPOLATED as t_index + t_map * Q/Qs (index build
+    # does not depend on the queries; mapping cost is per query).
     qs = Q.n if args.gpus <= 1 else max(250, Q.n // args.gpus)
     Qs = Q if qs == Q.n else Q.subset(range(qs))
     scale_q = Q.n / qs
@@ -128,20 +138,67 @@ def run_reference(args):
         ovl = float(counts.sum()) * scale_q
     ms = 1e3 * sum(times) / len(times)
     value = ovl / (ms / 1e3)
-    sample = ("the full workload (index build + map + count), every step" if qs == Q.n else
-              f"all {T.n} targets indexed, first {qs} of {Q.n} queries mapped; step time = t_index + t_map * {scale_q:.1f}, "
-              f"overlaps scaled by {scale_q:.1f}")
+    sample = ("the full workload (index build + map + count), every step; measured" if qs == Q.n else
+              f"EXTRAPOLATED: all {T.n} targets indexed, first {qs} of {Q.n} queries mapped; step time = t_index + t_map * {scale_q:.1f}, "
+              f"overlaps scaled by {scale_q:.1f} (quote the N = 1 line for measured-vs-measured ratios)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": desc, "targets_scale_with_gpus": True},
-        "overlaps_per_step": ovl, "gbases_per_s": (T.total_bases + Q.total_bases) / 1e9 / (ms / 1e3),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": config_dict(desc),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "extrapolated": qs != Q.n, "overlaps_per_step": ovl,
+                         "gbases_per_s": (T.total_bases + Q.total_bases) / 1e9 / (ms / 1e3)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def other_configs(ctx, names, threads, rank, world, dist, shard):
+    """BASELINE.json's other configurations on this box: GPU time (CUDA events, 2 passes after a warm-up) and parity of
+    the per-read counts over ALL reads against the oracle on the host cores."""
+    import lrge_b200
+    import oracle
+    from lrge_b200 import readsim
+    out = {}
+    for name in names:
+        t0 = time.perf_counter()
+        strat, platform, A, B = readsim.make_config(name)
+        gen_s = time.perf_counter() - t0
+        run = (lambda: ctx.twoset_counts(A, B, platform, **shard)) if strat == "twoset" else (lambda: ctx.ava_counts(A, platform, **shard))
+        res = run()
+        ms = []
+        for _ in range(2):
+            res = run()
+            ms.append(res.stats["ms_total"])
+        e = {"strategy": strat, "platform": platform, "n_gpus": world, "reads": A.n + (B.n if B is not None else 0),
+             "mbases": (A.total_bases + (B.total_bases if B is not None else 0)) / 1e6,
+             "gpu_ms_host_buffers_in": round(float(np.mean(ms)), 3), "generate_s": round(gen_s, 1),
+             "n_anchors": res.stats["n_anchors"], "n_overlaps": res.stats["n_overlaps"], "rounds": res.stats["n_batches"],
+             "deferred_queries": res.stats["n_deferred"], "mid_occ": res.stats["mid_occ"]}
+        if world > 1:
+            t = __import__("torch").tensor([e["gpu_ms_host_buffers_in"]], dtype=__import__("torch").float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e["gpu_ms_host_buffers_in"] = float(t[0])
+        e["overlaps_per_s"] = e["n_overlaps"] / (e["gpu_ms_host_buffers_in"] / 1e3)
+        if rank == 0:
+            t0 = time.perf_counter()
+            if strat == "twoset":
+                want, had, st = oracle.twoset_counts(A, B, platform, threads=threads)
+                same = bool(np.array_equal(want, res.counts) and np.array_equal(had, res.had_mapping))
+            else:
+                want, st = oracle.ava_counts(A, platform, threads=threads)
+                same = bool(np.array_equal(want, res.counts))
+            e.update({"oracle_s": round(time.perf_counter() - t0, 1), "oracle_threads": threads,
+                      "counts_identical": same, "reads_compared": int(want.shape[0]),
+                      "anchors_identical": bool(st["n_anchors"] == res.stats["n_anchors"]) if world == 1 else None,
+                      "speedup_vs_oracle": round((time.perf_counter() - t0) * 1e3 / e["gpu_ms_host_buffers_in"], 1)})
+        if dist is not None:
+            dist.barrier()
+        out[name] = e
+        del A, B, res
+    return out
 
 
 def run_ours(args):
@@ -159,9 +216,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=30))
 
     platform, T, Q, desc = workload(args.config, world, args.scale)
     ctx = lrge_b200.Context(local)
@@ -221,7 +279,7 @@ def run_ours(args):
         if i == 0:
             continue                                   # first pass creates the events
         for kt in ctx.kernel_times():
-            a = acc.setdefault(kt["name"], dict(ms=0.0, bytes=0.0, launches=0))
+            a = acc.setdefault(kt["name"], dict(ms=0.0, bytes=0.0, launches=0, passes=kt.get("passes", 1)))
             a["ms"] += kt["ms"]; a["bytes"] += kt["algorithmic_bytes"]; a["launches"] += kt["launches"]
     ctx.set_profiling(False)
     # ---- e2e: host buffers through the C-ABI, H2D + D2H inside ------------------------------------------
@@ -241,22 +299,51 @@ def run_ours(args):
     e2e_ms = float(t[0])
     assert np.array_equal(e2e_last.counts, last.counts)
     lo, hi = T.n * rank // world, T.n * (rank + 1) // world          # a rank copies its own target block + all queries
-    h2d = int(T.off[hi] - T.off[lo]) + int(Q.total_bases)
+    h2d_rank = int(T.off[hi] - T.off[lo]) + int(Q.total_bases)
+    h2d_all = int(T.total_bases) + world * int(Q.total_bases)
     d2h = int(5 * Q.n)
+
+    threads = os.cpu_count() or 1
+    # ---- parity + CPU baseline on rank 0: the oracle port on this box's cores -------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        import oracle
+        t0 = time.perf_counter()
+        oc, oh, ost = oracle.twoset_counts(T, Q, platform, threads=threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": int(oc.sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"the full N = {world} workload once (index build + map + count)", "seconds": dt,
+               "parity": {"counts_identical_to_gpu": bool(np.array_equal(oc, last.counts)),
+                          "had_mapping_identical": bool(np.array_equal(oh, last.had_mapping)),
+                          "reads_compared": int(oc.shape[0]), "overlaps": int(oc.sum())}}
+    if dist is not None:
+        dist.barrier()
+    # ---- the other BASELINE.json configurations, verified over all reads (N = 1: C1, C3, C4; N = 4: C4) -------
+    names = [n for n in args.configs.split(",") if n] if args.configs != "auto" else \
+        (["C1", "C3", "C4"] if world == 1 else ["C4"] if world == 4 else [])
+    if args.no_cpu_baseline:
+        names = []
+    sT.free()
+    sQ.free()
+    cfgs = other_configs(ctx, names, threads, rank, world, dist, shard) if names else {}
 
     if rank != 0:
         ctx.close()
         dist.destroy_process_group()
         return
     st = last.stats
-    # ---- roofline of the dominant kernel (rank 0) ----------------------------------------------------------------------
+    # ---- roofline of the dominant kernel (rank 0): algorithmic bytes per SURVEY.md 8(d) ------------------------------
     peak, peak_src = measured_peak()
     kernels = []
     for name, a in acc.items():
         ms = a["ms"] / prof_steps
         gbs = a["bytes"] / 1e9 / (a["ms"] / 1e3) if a["ms"] > 0 else 0.0
-        kernels.append({"name": name, "ms_per_step": round(ms, 4), "launches_per_step": a["launches"] / prof_steps,
-                        "algorithmic_bytes_per_step": a["bytes"] / prof_steps, "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+        k = {"name": name, "ms_per_step": round(ms, 4), "launches_per_step": a["launches"] / prof_steps,
+             "algorithmic_bytes_per_step": a["bytes"] / prof_steps, "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        if a["passes"] > 1:                      # a library radix sort: what one of its passes moves per second
+            k["passes"] = a["passes"]
+            k["per_pass_gbs"] = round(gbs * a["passes"], 1)
+        kernels.append(k)
     kernels.sort(key=lambda k: -k["ms_per_step"])
     dom = kernels[0]
     traffic = None
@@ -268,6 +355,7 @@ def run_ours(args):
                 traffic = tj.get("dram_bytes_per_launch", {}).get(dom["name"])
         except Exception:
             pass
+    ksum = sum(k["ms_per_step"] for k in kernels)
     roofline = {"kernel": dom["name"], "bound": "hbm",
                 "achieved": dom["algorithmic_bytes_per_step"] / dom["launches_per_step"] / 1e9 /
                             (dom["ms_per_step"] / dom["launches_per_step"] / 1e3),
@@ -275,50 +363,39 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_step"] / dom["launches_per_step"],
                 "kernel_ms_per_launch": dom["ms_per_step"] / dom["launches_per_step"],
                 "share_of_step": dom["ms_per_step"] / ms_per_step,
-                "note": "a CUB radix sort counts as one launch per sort (histogram + ceil(bits/8) onesweep passes); "
-                        "its algorithmic bytes are one read + one write of keys and values per pass"}
+                "whole_step": {"algorithmic_bytes": sum(k["algorithmic_bytes_per_step"] for k in kernels),
+                               "gbs": sum(k["algorithmic_bytes_per_step"] for k in kernels) / 1e9 / (ms_per_step / 1e3),
+                               "kernel_ms_sum": round(ksum, 4), "kernel_time_share_of_step": round(ksum / ms_per_step, 4)},
+                "note": "algorithmic bytes per SURVEY.md 8(d): a sort counts one read + one write of its records; the fused "
+                        "map kernel counts the K4 hit-list + anchor bytes, K5 and K6 (8H + 64A + 4NQ) although its anchors "
+                        "never leave shared memory, so `traffic` (ncu DRAM bytes) is far below it",
+                "kernels": kernels,
+                "stage_ms": {k: st[k] for k in st if k.startswith("ms_")},
+                "counts": {k: st[k] for k in ("n_target_minimizers", "n_query_minimizers", "n_keys", "n_seeds", "n_hits", "n_anchors",
+                                              "n_pairs", "mid_occ", "n_batches", "n_deferred")}}
     roofline["frac"] = roofline["achieved"] / peak
-    # ---- CPU baseline: the oracle port on this box's cores, rank 0, N = 1 only ------------------------------
-    cpu = None
-    if world > 1 and args.verify:
-        import oracle
-        oc, oh, ost = oracle.twoset_counts(T, Q, platform, threads=os.cpu_count() or 1)
-        cpu = {"verify_only": True, "counts_identical_to_gpu": bool(np.array_equal(oc, last.counts)),
-               "had_mapping_identical": bool(np.array_equal(oh, last.had_mapping))}
-    if world == 1 and not args.no_cpu_baseline:
-        import oracle
-        threads = os.cpu_count() or 1
-        t0 = time.perf_counter()
-        oc, oh, ost = oracle.twoset_counts(T, Q, platform, threads=threads)
-        dt = time.perf_counter() - t0
-        cpu = {"value": int(oc.sum()) / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "the full workload once (index build + map + count)", "seconds": dt,
-               "counts_identical_to_gpu": bool(np.array_equal(oc, last.counts))}
+    roofline["whole_step"]["frac"] = roofline["whole_step"]["gbs"] / peak
+    if cpu is not None:
+        cpu["configs"] = cfgs
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": desc, "targets_scale_with_gpus": True, "sharding": f"{world} contiguous target blocks",
-                   "l2": "256 MiB memset between steps; index + anchors (>1 GB) exceed L2"},
+        "config": config_dict(desc),
         "overlaps_per_step": overlaps,
         "gbases_per_s": (T.total_bases + Q.total_bases) / 1e9 / (ms_per_step / 1e3),
         "candidate_pairs_per_s": T.n * Q.n / (ms_per_step / 1e3),
         "wall_ms_per_step": wall_ms / args.steps, "step_ms": step_ms,
-        "stage_ms": {k: st[k] for k in st if k.startswith("ms_")},
-        "counts": {k: st[k] for k in ("n_target_minimizers", "n_query_minimizers", "n_keys", "n_seeds", "n_hits", "n_anchors",
-                                      "n_pairs", "mid_occ", "n_batches")},
-        "roofline": roofline, "kernels": kernels,
+        "roofline": roofline,
         "cpu_baseline": cpu,
-        "e2e": {"value": overlaps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms},
+        "e2e": {"value": overlaps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h * world,
+                "h2d_bytes_per_step_per_rank": h2d_rank, "d2h_bytes_per_step_per_rank": d2h, "ms_per_step": e2e_ms},
         "gpu_launches": launches,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     for b in (bT, bQ):
         b.free()
-    sT.free()
-    sQ.free()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -332,8 +409,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=WORKLOAD)
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--verify", action="store_true", help="N > 1: check the reduced counts against the oracle on rank 0")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every oracle run (profiling passes)")
+    ap.add_argument("--configs", default="auto", help="other BASELINE.json configurations to run and verify "
+                    "(comma list; auto = C1,C3,C4 at N=1, C4 at N=4, none otherwise; '' = none)")
+    ap.add_argument("--verify", action="store_true", help="kept for compatibility: parity is always checked now")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     need = [os.path.join(ROOT, "lrge_b200", "csrc", "liblrge_b200.so"), os.path.join(ROOT, "lrge_b200", "csrc", "libreadsim.so"),

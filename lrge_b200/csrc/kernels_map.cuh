@@ -28,8 +28,7 @@
 
 namespace lrge {
 
-constexpr int MAP_THREADS = 512;
-constexpr int MAP_WARPS = MAP_THREADS / 32;
+constexpr int MAP_MAX_WARPS = 32;
 constexpr int MAP_BINS = 1024;         // target-id histogram bins for round planning
 constexpr int MAP_MAX_ROUNDS = 255;
 constexpr int SL_ILP = 4;              // independent probes per thread in seed_lookup_kernel
@@ -115,8 +114,10 @@ struct MapArgs {
     unsigned long long *cyc;         // optional: SM cycles per phase summed over CTAs: [0] plan [1] expand [2] sort [3] chain [4] total
 };
 
-// exclusive scan of one value per thread over the CTA; total = sum.  wsum: MAP_WARPS + 1 words of smem.
+// exclusive scan of one value per thread over the CTA (NT threads); total = sum.  wsum: NT / 32 + 1 words of smem.
+template <int NT>
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, uint32_t &total) {
+    constexpr int MAP_WARPS = NT / 32;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t incl = v;
 #pragma unroll
@@ -144,16 +145,18 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, 
     return r;
 }
 
-// Stable LSD radix sort of N (key, payload) records in shared memory, ceil(key_bits / 8) passes of <= 8 bits.
-// Every warp owns a contiguous slice; per pass: (1) rank of each record among the records of its slice with the same
-// digit -- peers by one ballot per digit bit, no atomics -- plus per-(warp, digit) counts, (2) column scan of the
-// counts in (digit, warp) order, (3) scatter.  rank[] is N words of scratch.  Returns 1 if the result is in (kB, vB).
-template <typename KT>
-__device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint32_t N, int key_bits,
+// Stable LSD radix sort of N (key, payload) records in shared memory on key bits [lo_bit, lo_bit + n_bits), in
+// ceil(n_bits / 8) passes of <= 8 bits.  Every warp owns a contiguous slice; per pass: (1) rank of each record among the
+// records of its slice with the same digit (peers by __match_any_sync, no atomics) plus per-(warp, digit) counts,
+// (2) column scan of the counts in (digit, warp) order, (3) scatter.  rank[] is N words of scratch.
+// Returns 1 if the result is in (kB, vB).
+template <typename KT, int NT>
+__device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint32_t N, int lo_bit, int n_bits,
                                 uint16_t *hist, uint32_t *rank, uint32_t *wsum) {
+    constexpr int MAP_THREADS = NT, MAP_WARPS = NT / 32;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int passes = key_bits > 8 ? (key_bits + 7) / 8 : 1;
-    const int dbits = (key_bits + passes - 1) / passes;
+    const int passes = n_bits > 8 ? (n_bits + 7) / 8 : 1;
+    const int dbits = (n_bits + passes - 1) / passes;
     const uint32_t per_warp = ((N + MAP_THREADS - 1) / MAP_THREADS) * 32;
     const uint32_t lo = min(warp * per_warp, N), hi = min(lo + per_warp, N);
     const uint32_t lt = (1u << lane) - 1;
@@ -161,8 +164,8 @@ __device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint
     KT *ks = kA, *kd = kB;
     uint32_t *vs = vA, *vd = vB;
     for (int pass = 0; pass < passes; ++pass) {
-        const int shift = pass * dbits;
-        const int nb = min(dbits, key_bits - shift);
+        const int shift = lo_bit + pass * dbits;
+        const int nb = min(dbits, n_bits - pass * dbits);
         const uint32_t dmask = (1u << nb) - 1;
         for (uint32_t i = tid; i < MAP_WARPS * 128; i += MAP_THREADS) reinterpret_cast<uint32_t *>(hist)[i] = 0;
         __syncthreads();
@@ -170,12 +173,7 @@ __device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint
             const uint32_t e = b + lane;
             const bool valid = e < hi;
             const uint32_t d = valid ? (uint32_t)(ks[e] >> shift) & dmask : 0;
-            uint32_t peers = __ballot_sync(0xffffffffu, valid);
-            for (int bit = 0; bit < nb; ++bit) {
-                const bool one = (d >> bit) & 1;
-                const uint32_t m = __ballot_sync(0xffffffffu, one);
-                peers &= one ? m : ~m;
-            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);   // lanes holding the same digit
             if (valid) rank[e] = (uint32_t)myh[d] + __popc(peers & lt);
             __syncwarp();
             if (valid && (peers & lt) == 0) myh[d] = (uint16_t)(myh[d] + __popc(peers));     // lowest peer updates the count
@@ -188,7 +186,7 @@ __device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint
             for (int w = 0; w < MAP_WARPS; ++w) tot += hist[w * 256 + tid];
         }
         uint32_t total;
-        uint32_t run = block_excl_scan(tot, wsum, total);
+        uint32_t run = block_excl_scan<NT>(tot, wsum, total);
         if (tid < 256) {
 #pragma unroll
             for (int w = 0; w < MAP_WARPS; ++w) {
@@ -211,15 +209,110 @@ __device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint
     return passes & 1;
 }
 
+// One warp brings the n anchors of a (target, strand) group -- contiguous in (K, V), in generation order after the
+// block sort on (target, strand) -- into ascending target-position order, stably.  Anchors of a colinear overlap are
+// generated in ascending query position, i.e. already ascending (+ strand) or strictly descending (- strand) in target
+// position: those cases cost one read.  Anything else (repeats) is sorted by a warp-level LSD radix sort on the PB
+// position bits, with scr (8 bytes per anchor) as the second buffer, myh (256 counters) and rank (n words) as scratch.
 template <typename KT>
-__global__ void __launch_bounds__(MAP_THREADS, 1) map_query_kernel(MapArgs A) {
+__device__ void warp_sort_group(KT *K, uint32_t *V, int32_t n, int PB, uint2 *scr, uint16_t *myh, uint32_t *rank, uint32_t lane) {
+    const KT posmask = (KT)(((KT)1 << PB) - 1);
+    bool asc = true, desc = true;
+    for (int32_t b = 0; b + 1 < n; b += 32) {
+        const int32_t i = b + (int32_t)lane;
+        if (i + 1 < n) {
+            const uint32_t a = (uint32_t)(K[i] & posmask), c = (uint32_t)(K[i + 1] & posmask);
+            if (a > c) asc = false;
+            if (a <= c) desc = false;
+        }
+    }
+    asc = __all_sync(0xffffffffu, asc);
+    desc = __all_sync(0xffffffffu, desc);
+    if (asc) return;
+    if (desc) {                                                         // all positions distinct: the reversal is THE sorted order
+        for (int32_t i = lane; i < n / 2; i += 32) {
+            const KT ka = K[i], kb = K[n - 1 - i];
+            const uint32_t va = V[i], vb = V[n - 1 - i];
+            K[i] = kb; K[n - 1 - i] = ka; V[i] = vb; V[n - 1 - i] = va;
+        }
+        __syncwarp();
+        return;
+    }
+    const KT high = K[0] & ~posmask;
+    const uint32_t lt = (1u << lane) - 1;
+    const int passes = (PB + 7) / 8;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = pass * 8;
+        const bool from_k = (pass & 1) == 0;                             // even passes read (K, V), odd passes read scr
+        for (uint32_t i = lane; i < 128; i += 32) reinterpret_cast<uint32_t *>(myh)[i] = 0;
+        __syncwarp();
+        for (int32_t b = 0; b < n; b += 32) {
+            const int32_t e = b + (int32_t)lane;
+            const bool valid = e < n;
+            uint32_t pos = 0;
+            if (valid) pos = from_k ? (uint32_t)(K[e] & posmask) : scr[e].x;
+            const uint32_t d = (pos >> shift) & 255u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
+            if (valid) rank[e] = (uint32_t)myh[d] + __popc(peers & lt);
+            __syncwarp();
+            if (valid && (peers & lt) == 0) myh[d] = (uint16_t)(myh[d] + __popc(peers));
+            __syncwarp();
+        }
+        // exclusive scan of the 256 counters: 8 per lane
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = myh[lane * 8 + j]; sum += c[j]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += u; }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { myh[lane * 8 + j] = (uint16_t)run; run += c[j]; }
+        __syncwarp();
+        for (int32_t e = lane; e < n; e += 32) {
+            uint32_t pos, val;
+            if (from_k) { pos = (uint32_t)(K[e] & posmask); val = V[e]; } else { pos = scr[e].x; val = scr[e].y; }
+            const uint32_t at = (uint32_t)myh[(pos >> shift) & 255u] + rank[e];
+            if (from_k) scr[at] = make_uint2(pos, val); else { K[at] = high | (KT)pos; V[at] = val; }
+        }
+        __syncwarp();
+    }
+    if (passes & 1) {                                                    // result sits in scr
+        for (int32_t e = lane; e < n; e += 32) { const uint2 r = scr[e]; K[e] = high | (KT)r.x; V[e] = r.y; }
+        __syncwarp();
+    }
+    for (int32_t e = lane; e < n; e += 32) rank[e] = 0;                   // rank aliases the DP's mark array
+    __syncwarp();
+}
+
+// per-lane walk over one hit list with four independent 128-bit loads (two 8-byte entries each) in flight;
+// fn(entry, j) is called in ascending j
+template <typename F>
+__device__ __forceinline__ void for_hits(const uint4 *__restrict__ ty4, uint32_t start, uint32_t n, F fn) {
+    const uint32_t p1 = (start + n + 1) >> 1;
+    for (uint32_t p = start >> 1; p < p1; p += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = p + u < p1 ? __ldg(ty4 + p + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t e0 = 2 * (p + u), e1 = e0 + 1;
+            if (e0 >= start && e0 < start + n) fn((uint64_t)v[u].y << 32 | v[u].x, e0 - start);
+            if (e1 >= start && e1 < start + n) fn((uint64_t)v[u].w << 32 | v[u].z, e1 - start);
+        }
+    }
+}
+
+template <typename KT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) map_query_kernel(MapArgs A) {
+    constexpr int MAP_THREADS = NT, MAP_WARPS = NT / 32;
     extern __shared__ __align__(16) uint8_t map_smem[];
     __shared__ uint32_t s_wsum[MAP_WARPS + 1];
     __shared__ uint32_t s_rbound[MAP_MAX_ROUNDS + 2];
-    __shared__ uint32_t s_q, s_nrounds, s_unit, s_cnt, s_kept;
+    __shared__ uint32_t s_q, s_qn, s_nrounds, s_unit, s_cnt, s_kept;
     __shared__ uint8_t s_pen[2048];
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t cap = A.cap;
     KT *kX = reinterpret_cast<KT *>(map_smem);
     uint32_t *vX = reinterpret_cast<uint32_t *>(map_smem + (size_t)cap * sizeof(KT));
@@ -237,21 +330,60 @@ __global__ void __launch_bounds__(MAP_THREADS, 1) map_query_kernel(MapArgs A) {
     long long cy[5] = {0, 0, 0, 0, 0};                                    // thread 0: cycles per phase
     const long long t_begin = clock64();
 
+    // exclusive scan of one total per warp: returns this warp's base, *total = sum (two barriers)
+    auto scan_warp_totals = [&](uint32_t wt, uint32_t *total) -> uint32_t {
+        if (lane == 0) s_wsum[warp] = wt;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t x = lane < MAP_WARPS ? s_wsum[lane] : 0;
+            uint32_t xi = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, xi, o); if ((int)lane >= o) xi += u; }
+            if (lane < MAP_WARPS) s_wsum[lane] = xi - x;
+            if (lane == MAP_WARPS - 1) s_wsum[MAP_WARPS] = xi;
+        }
+        __syncthreads();
+        *total = s_wsum[MAP_WARPS];
+        const uint32_t base = s_wsum[warp];
+        __syncthreads();
+        return base;
+    };
+
+    // Work is pulled one query ahead: while the current query is sorted and chained, the hit lists of the next one are
+    // brought into L2 (prefetch.global.L2), so that its expansion does not wait on first-touch DRAM latency.
+    if (tid == 0) s_qn = atomicAdd(A.work_ctr, 1u);
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_q = atomicAdd(A.work_ctr, 1u); s_cnt = 0; s_kept = 0; }
+        if (tid == 0) { s_q = s_qn; s_qn = s_qn < A.nq ? atomicAdd(A.work_ctr, 1u) : s_qn; s_cnt = 0; s_kept = 0; }
         __syncthreads();
         if (s_q >= A.nq) break;
         long long tc = clock64();
         const uint32_t qid = A.qorder[s_q];
+        if (s_qn < A.nq) {
+            const uint32_t qn = A.qorder[s_qn];
+            const uint32_t e1 = A.moff[qn + 1];
+            for (uint32_t i = A.moff[qn] + tid; i < e1; i += MAP_THREADS) {
+                const uint32_t n = A.hn[i];
+                if (n) {
+                    const uint64_t *p0 = A.I.ty + A.hstart[i];
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p0));
+                    if ((((uintptr_t)p0) & 127) + (size_t)n * 8 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + n - 1));
+                }
+            }
+        }
         const uint32_t m0 = A.moff[qid], m1 = A.moff[qid + 1];
         const uint32_t qlen = A.S.len_q[qid];
+        // every warp owns a contiguous slice of the query's minimizers: expansion needs one block-wide scan per round
+        const uint32_t slice = ((m1 - m0 + MAP_WARPS - 1) / MAP_WARPS + 31) / 32 * 32;
+        const uint32_t w0 = min(m0 + warp * slice, m1), w1 = min(w0 + slice, m1);
 
-        // total hit-list entries of this query: an upper bound of its anchors
-        uint32_t h = 0;
-        for (uint32_t i = m0 + tid; i < m1; i += MAP_THREADS) h += A.hn[i];
+        // total hit-list entries of this query (an upper bound of its anchors) and of every warp's slice
+        uint32_t wt = 0;
+        for (uint32_t b = w0; b < w1; b += 32) wt += b + lane < w1 ? A.hn[b + lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
         uint32_t H;
-        block_excl_scan(h, s_wsum, H);
+        uint32_t wbase = scan_warp_totals(wt, &H);
         if (H == 0) continue;
 
         // does a hit survive skip_seed and belong to the target range [rlo, rhi) (ids relative to rid_base)?
@@ -268,14 +400,14 @@ __global__ void __launch_bounds__(MAP_THREADS, 1) map_query_kernel(MapArgs A) {
             uint32_t *bins = reinterpret_cast<uint32_t *>(t);
             for (uint32_t i = tid; i < MAP_BINS; i += MAP_THREADS) bins[i] = 0;
             __syncthreads();
-            for (uint32_t i = m0 + tid; i < m1; i += MAP_THREADS) {
-                const uint32_t n = A.hn[i];
+            for (uint32_t b = w0; b < w1; b += 32) {
+                const uint32_t i = b + lane;
+                const uint32_t n = i < w1 ? A.hn[i] : 0;
                 if (!n) continue;
                 const uint32_t start = A.hstart[i], q_pos = (uint32_t)A.qy[i];
-                for (uint32_t j = 0; j < n; ++j) {
-                    const uint64_t r = A.I.ty[start + j];
+                for_hits(ty4, start, n, [&](uint64_t r, uint32_t) {
                     if (keep(r, q_pos, 0u, 0xffffffffu)) atomicAdd(&bins[((uint32_t)(r >> 32) - A.rid_base) >> A.hshift], 1u);
-                }
+                });
             }
             __syncthreads();
             if (tid == 0) {
@@ -310,58 +442,63 @@ __global__ void __launch_bounds__(MAP_THREADS, 1) map_query_kernel(MapArgs A) {
         for (uint32_t rd = 0; rd < nrounds; ++rd) {
             const uint32_t rlo = s_rbound[rd], rhi = s_rbound[rd + 1];
             // ---- 1. expand: anchors in minimizer order into (kX, vX) ------------------------------------------
-            uint32_t N = 0;
-            for (uint32_t c0 = m0; c0 < m1; c0 += MAP_THREADS) {
-                const uint32_t i = c0 + tid;
-                uint32_t start = 0, n = 0, q_pos = 0, q_span = 0;
-                if (i < m1) {
-                    n = A.hn[i];
-                    if (n) { start = A.hstart[i]; q_pos = (uint32_t)A.qy[i]; q_span = (uint32_t)(A.qx[i] & 0xff); }
+            uint32_t N = H;
+            if (filtered) {                                               // kept anchors of every warp's slice in this round
+                wt = 0;
+                for (uint32_t b = w0; b < w1; b += 32) {
+                    const uint32_t i = b + lane;
+                    const uint32_t n = i < w1 ? A.hn[i] : 0;
+                    if (!n) continue;
+                    const uint32_t start = A.hstart[i], q_pos = (uint32_t)A.qy[i];
+                    for_hits(ty4, start, n, [&](uint64_t r, uint32_t) { wt += keep(r, q_pos, rlo, rhi); });
                 }
-                uint32_t kept = n;
-                if (filtered && n) {
-                    kept = 0;
-                    for (uint32_t j = 0; j < n; ++j) kept += keep(A.I.ty[start + j], q_pos, rlo, rhi);
-                }
-                uint32_t tot;
-                uint32_t o = N + block_excl_scan(kept, s_wsum, tot);
-                if (kept) {
-                    const uint32_t qp_f = q_pos >> 1, qp_r = qlen - ((q_pos >> 1) + 1 - q_span) - 1;
-                    auto emit = [&](uint64_t r, uint32_t at) {
-                        if (at >= cap) return;                                  // cannot happen (planned); see stats[3]
-                        const uint32_t rev = ((uint32_t)r ^ q_pos) & 1;
-                        const KT rel = (KT)((uint32_t)(r >> 32) - A.rid_base);
-                        kX[at] = (KT)((((rel << 1) | (KT)rev) << PB) | (KT)((uint32_t)r >> 1));
-                        vX[at] = q_span << 24 | (rev ? qp_r : qp_f);
-                    };
-                    if (!filtered) {
-                        // 128-bit loads: two consecutive 8-byte hit-list entries each
-                        const uint32_t p1 = (start + n + 1) >> 1;
-                        for (uint32_t p = start >> 1; p < p1; ++p) {
-                            const uint4 v = __ldg(ty4 + p);
-                            const uint32_t e0 = 2 * p, e1 = 2 * p + 1;
-                            if (e0 >= start && e0 < start + n) emit((uint64_t)v.y << 32 | v.x, o + (e0 - start));
-                            if (e1 >= start && e1 < start + n) emit((uint64_t)v.w << 32 | v.z, o + (e1 - start));
-                        }
-                    } else {
-                        for (uint32_t j = 0; j < n; ++j) {
-                            const uint64_t r = A.I.ty[start + j];
-                            if (keep(r, q_pos, rlo, rhi)) emit(r, o++);
-                        }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
+                wbase = scan_warp_totals(wt, &N);
+            }
+            if (N > cap) { if (tid == 0) atomicAdd(A.stats + 3, 1ull); N = 0; }   // cannot happen (planned)
+            if (N) {
+                uint32_t run = wbase;
+                for (uint32_t b = w0; b < w1; b += 32) {
+                    const uint32_t i = b + lane;
+                    uint32_t start = 0, n = 0, q_pos = 0, q_span = 0;
+                    if (i < w1) {
+                        n = A.hn[i];
+                        if (n) { start = A.hstart[i]; q_pos = (uint32_t)A.qy[i]; q_span = (uint32_t)(A.qx[i] & 0xff); }
+                    }
+                    uint32_t kept = n;
+                    if (filtered && n) {
+                        kept = 0;
+                        for_hits(ty4, start, n, [&](uint64_t r, uint32_t) { kept += keep(r, q_pos, rlo, rhi); });
+                    }
+                    uint32_t incl = kept;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += u; }
+                    uint32_t o = run + incl - kept;
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                    if (kept) {
+                        const uint32_t qp_f = q_pos >> 1, qp_r = qlen - ((q_pos >> 1) + 1 - q_span) - 1;
+                        auto emit = [&](uint64_t r, uint32_t at) {
+                            if (at >= cap) return;
+                            const uint32_t rev = ((uint32_t)r ^ q_pos) & 1;
+                            const KT rel = (KT)((uint32_t)(r >> 32) - A.rid_base);
+                            kX[at] = (KT)((((rel << 1) | (KT)rev) << PB) | (KT)((uint32_t)r >> 1));
+                            vX[at] = q_span << 24 | (rev ? qp_r : qp_f);
+                        };
+                        if (!filtered) for_hits(ty4, start, n, [&](uint64_t r, uint32_t j) { emit(r, o + j); });
+                        else for_hits(ty4, start, n, [&](uint64_t r, uint32_t) { if (keep(r, q_pos, rlo, rhi)) emit(r, o++); });
                     }
                 }
-                N += tot;
             }
             __syncthreads();
             { const long long now = clock64(); cy[1] += now - tc; tc = now; }
             if (N == 0) continue;
-            if (N > cap) { if (tid == 0) atomicAdd(A.stats + 3, 1ull); N = cap; }
             if (tid == 0) { st_anchors += N; ++st_rounds; }
 
-            // ---- 2. sort ---------------------------------------------------------------------------------------
-            const int fin = block_radix_sort<KT>(kX, vX, kY, vY, N, A.key_bits, hist, reinterpret_cast<uint32_t *>(t), s_wsum);
-            const KT *K = fin ? kY : kX;
-            const uint32_t *V = fin ? vY : vX;
+            // ---- 2. sort by (target, strand): groups become contiguous, still in generation order ----------------
+            const int fin = block_radix_sort<KT, NT>(kX, vX, kY, vY, N, PB, A.key_bits - PB, hist, reinterpret_cast<uint32_t *>(t), s_wsum);
+            KT *K = fin ? kY : kX;
+            uint32_t *V = fin ? vY : vX;
             int2 *fp = reinterpret_cast<int2 *>(fin ? map_smem : bufY);           // the other buffer: (f, p) scratch
             for (uint32_t i = tid; i < N; i += MAP_THREADS) t[i] = 0;
             if (tid == 0) s_unit = 0;
@@ -374,14 +511,14 @@ __global__ void __launch_bounds__(MAP_THREADS, 1) map_query_kernel(MapArgs A) {
                 uint32_t u = 0;
                 if (lane == 0) u = atomicAdd(&s_unit, 1u);
                 u = __shfl_sync(0xffffffffu, u, 0);
-                const uint32_t wbase = u * 32;
-                if (wbase >= N) break;
-                const uint32_t i = wbase + lane;
+                const uint32_t wnd = u * 32;
+                if (wnd >= N) break;
+                const uint32_t i = wnd + lane;
                 bool ps = false;
                 if (i < N) ps = i == 0 || (K[i - 1] >> (PB + 1)) != (K[i] >> (PB + 1));
                 uint32_t pm = __ballot_sync(0xffffffffu, ps);
                 while (pm) {
-                    const uint32_t s = wbase + (uint32_t)(__ffs(pm) - 1);
+                    const uint32_t s = wnd + (uint32_t)(__ffs(pm) - 1);
                     pm &= pm - 1;
                     const KT pk = K[s] >> (PB + 1);
                     // pair end and strand split, 32 anchors per step
@@ -393,10 +530,7 @@ __global__ void __launch_bounds__(MAP_THREADS, 1) map_query_kernel(MapArgs A) {
                         const bool same = in && (kk >> (PB + 1)) == pk;
                         const uint32_t diff = __ballot_sync(0xffffffffu, in && !same);
                         const uint32_t rv = __ballot_sync(0xffffffffu, same && ((kk >> PB) & 1));
-                        if (split == 0xffffffffu && rv) {
-                            const uint32_t first_rev = b + (uint32_t)(__ffs(rv) - 1);
-                            if (!diff || first_rev < b + (uint32_t)(__ffs(diff) - 1)) split = first_rev;
-                        }
+                        if (split == 0xffffffffu && rv) split = b + (uint32_t)(__ffs(rv) - 1);
                         if (diff) { e = b + (uint32_t)(__ffs(diff) - 1); break; }
                     }
                     if (split == 0xffffffffu || split > e) split = e;
@@ -409,6 +543,8 @@ __global__ void __launch_bounds__(MAP_THREADS, 1) map_query_kernel(MapArgs A) {
                         if (n == 0) continue;
                         if (lane == 0) ++st_groups;
                         if (n < A.P.min_cnt || (int64_t)n * A.max_span < A.P.min_sc) continue;
+                        warp_sort_group<KT>(K + g0, V + g0, n, PB, reinterpret_cast<uint2 *>(fp + g0), hist + warp * 256,
+                                            reinterpret_cast<uint32_t *>(t + g0), lane);
                         int kept = 0, pass = 0;
                         chain_one_group(AncSoA<KT>{K + g0, V + g0, posmask}, n, fp + g0, t + g0, A.P, s_pen, A.O, lane, qid, rid,
                                         strand, kept, pass);

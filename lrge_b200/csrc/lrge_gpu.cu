@@ -1062,17 +1062,20 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         const int key_bits = RBf + 1 + PB;
         if (key_bits > 64) throw std::length_error("sort key does not fit 64 bits (too many reads x read length)");
         const bool k32 = key_bits <= 32;
-        const void *fn = k32 ? (const void *)map_query_kernel<uint32_t> : (const void *)map_query_kernel<uint64_t>;
+        const bool two = c->map_ctas_per_sm == 2;                                 // 2 CTAs of 512 threads, else 1 CTA of 1024
+        const int NT = two ? 512 : 1024, NW = NT / 32;
+        const void *fn = two ? (k32 ? (const void *)map_query_kernel<uint32_t, 512, 2> : (const void *)map_query_kernel<uint64_t, 512, 2>)
+                             : (k32 ? (const void *)map_query_kernel<uint32_t, 1024, 1> : (const void *)map_query_kernel<uint64_t, 1024, 1>);
         cudaFuncAttributes fa{};
         CUDA_CHECK(cudaFuncGetAttributes(&fa, fn));
         const size_t rec = (k32 ? 4 : 8) + 4;
         size_t per_cta = (size_t)c->smem_optin;                                   // static + dynamic, one CTA per SM
         if (c->map_ctas_per_sm == 2) per_cta = ((size_t)c->smem_optin + 1024) / 2 - 1024;
-        const size_t fixed = fa.sharedSizeBytes + (size_t)MAP_WARPS * 512;
+        const size_t fixed = fa.sharedSizeBytes + (size_t)NW * 512;
         uint32_t cap = (uint32_t)std::min<size_t>((per_cta - fixed) / (2 * rec + 4), 65504) / 32 * 32;
         if (c->map_cap) cap = std::max(64u, std::min(cap, c->map_cap) / 32 * 32);   // LRGE_MAP_CAP: force many rounds (tests)
         map_cap = cap;
-        const size_t dyn = (size_t)cap * (2 * rec + 4) + (size_t)MAP_WARPS * 512;
+        const size_t dyn = (size_t)cap * (2 * rec + 4) + (size_t)NW * 512;
         CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         h2d(c, c->qorder, str->len_order.data(), str->n);
         c->deferred.reserve(((size_t)str->n + 1) * 4);
@@ -1098,8 +1101,13 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->n_sm * c->map_ctas_per_sm, std::max(str->n, 1u));
         if (str->n && MQ) {
             KLAUNCH(c, "map_query_kernel", 0.0, {
-                if (k32) map_query_kernel<uint32_t><<<grid, MAP_THREADS, dyn, c->stream>>>(A);
-                else map_query_kernel<uint64_t><<<grid, MAP_THREADS, dyn, c->stream>>>(A);
+                if (two) {
+                    if (k32) map_query_kernel<uint32_t, 512, 2><<<grid, 512, dyn, c->stream>>>(A);
+                    else map_query_kernel<uint64_t, 512, 2><<<grid, 512, dyn, c->stream>>>(A);
+                } else {
+                    if (k32) map_query_kernel<uint32_t, 1024, 1><<<grid, 1024, dyn, c->stream>>>(A);
+                    else map_query_kernel<uint64_t, 1024, 1><<<grid, 1024, dyn, c->stream>>>(A);
+                }
             });
         }
         CUDA_CHECK(cudaGetLastError());
