@@ -175,7 +175,7 @@ def other_configs(ctx, names, threads, rank, world, dist, shard):
         e = {"strategy": strat, "platform": platform, "n_gpus": world, "reads": A.n + (B.n if B is not None else 0),
              "mbases": (A.total_bases + (B.total_bases if B is not None else 0)) / 1e6,
              "gpu_ms_host_buffers_in": round(float(np.mean(ms)), 3), "generate_s": round(gen_s, 1),
-             "n_anchors": res.stats["n_anchors"], "n_overlaps": res.stats["n_overlaps"], "rounds": res.stats["n_batches"],
+             "n_anchors": res.stats["n_anchors"], "n_overlaps": res.stats["n_overlaps"], "rounds": res.stats["n_rounds"], "batches": res.stats["n_batches"],
              "deferred_queries": res.stats["n_deferred"], "mid_occ": res.stats["mid_occ"]}
         if world > 1:
             t = __import__("torch").tensor([e["gpu_ms_host_buffers_in"]], dtype=__import__("torch").float64, device="cuda")
@@ -372,7 +372,7 @@ def run_ours(args):
                 "kernels": kernels,
                 "stage_ms": {k: st[k] for k in st if k.startswith("ms_")},
                 "counts": {k: st[k] for k in ("n_target_minimizers", "n_query_minimizers", "n_keys", "n_seeds", "n_hits", "n_anchors",
-                                              "n_pairs", "mid_occ", "n_batches", "n_deferred")}}
+                                              "n_pairs", "mid_occ", "n_batches", "n_rounds", "n_deferred")}}
     roofline["frac"] = roofline["achieved"] / peak
     roofline["whole_step"]["frac"] = roofline["whole_step"]["gbs"] / peak
     if cpu is not None:

@@ -86,14 +86,15 @@ typedef struct lrge_stats {
     uint64_t n_overlaps;         /* pairs with at least one kept chain that passes the -F filter */
     uint32_t no_mapping_count;   /* twoset.rs:303-309 / ava.rs:329-330 semantics */
     int32_t  mid_occ;
-    uint32_t n_batches;          /* shared-memory rounds of the fused kernel + query batches of the global path */
+    uint32_t n_batches;          /* query batches (bounded by anchor memory) */
     uint32_t n_kernel_launches;
     /* device time per stage in ms (CUDA events on the context's stream) */
     float ms_h2d, ms_pack, ms_sketch, ms_index, ms_seed, ms_sort, ms_chain, ms_d2h, ms_total;
     float ms_chain_kernel;       /* the chaining kernel alone, summed over batches (0 unless lrge_gpu_set_profiling is on) */
     float ms_comm;               /* NCCL reduction of the per-read counts */
-    uint32_t n_deferred;         /* queries the fused shared-memory kernel handed to the global-memory path */
-    float reserved[4];
+    uint32_t n_deferred;         /* queries the per-query shared-memory sort handed to the device-wide sort */
+    uint32_t n_rounds;           /* shared-memory rounds of the per-query sort (>= queries holding anchors) */
+    float reserved[3];
 } lrge_stats;
 
 typedef struct lrge_ctx lrge_ctx;
@@ -161,7 +162,7 @@ typedef struct lrge_kernel_time {
     double   ms;                  /* summed over the launches of this kernel in the call */
     double   algorithmic_bytes;   /* summed algorithmic bytes of those launches */
     uint32_t launches;
-    uint32_t reserved;
+    uint32_t passes;              /* a library radix sort makes several passes over its records inside one launch; else 1 */
 } lrge_kernel_time;
 int  lrge_gpu_set_profiling(lrge_ctx *ctx, int on);
 int  lrge_gpu_kernel_times(lrge_ctx *ctx, lrge_kernel_time *out, int cap);

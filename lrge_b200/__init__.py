@@ -61,7 +61,7 @@ OVERLAP_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("rev", "<i4"), (
 
 class KernelTime(ctypes.Structure):
     _fields_ = [("name", ctypes.c_char * 64), ("ms", ctypes.c_double), ("algorithmic_bytes", ctypes.c_double),
-                ("launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("launches", ctypes.c_uint32), ("passes", ctypes.c_uint32)]
 
 
 class Stats(ctypes.Structure):
@@ -76,7 +76,7 @@ class Stats(ctypes.Structure):
         ("ms_index", ctypes.c_float), ("ms_seed", ctypes.c_float), ("ms_sort", ctypes.c_float),
         ("ms_chain", ctypes.c_float), ("ms_d2h", ctypes.c_float), ("ms_total", ctypes.c_float),
         ("ms_chain_kernel", ctypes.c_float), ("ms_comm", ctypes.c_float),
-        ("n_deferred", ctypes.c_uint32), ("reserved", ctypes.c_float * 4),
+        ("n_deferred", ctypes.c_uint32), ("n_rounds", ctypes.c_uint32), ("reserved", ctypes.c_float * 3),
     ]
 
     def as_dict(self):
@@ -257,7 +257,7 @@ class Context:
         """Per-kernel device time of the last *_counts call (needs set_profiling(True))."""
         buf = (KernelTime * 64)()
         n = lib().lrge_gpu_kernel_times(self.h, buf, 64)
-        return [dict(name=buf[i].name.decode(), ms=buf[i].ms, algorithmic_bytes=buf[i].algorithmic_bytes, launches=buf[i].launches)
+        return [dict(name=buf[i].name.decode(), ms=buf[i].ms, algorithmic_bytes=buf[i].algorithmic_bytes, launches=buf[i].launches, passes=max(1, buf[i].passes))
                 for i in range(max(0, min(n, 64)))]
 
     def stage(self, rs: ReadSet) -> Staged:

@@ -104,19 +104,27 @@ __device__ __forceinline__ int32_t comput_sc(int32_t ri, int32_t qi, int32_t rj,
 
 constexpr int CG_THREADS = 256;
 
+// One (query, target, strand) group of the sorted anchor array that can hold a chain.  Written by the per-query sort
+// kernel (kernels_map.cuh) or, on the global path, by group_classify_kernel.
+struct GroupDesc {
+    uint32_t start, n;           // anchors [start, start + n) of the batch's sorted anchor array
+    uint32_t qid, rid;           // streamed read, indexed read
+    uint32_t strand;
+    uint32_t pair;               // slot shared by the two strand groups of one (query, target) pair
+};
+
+inline __host__ __device__ int group_class(uint32_t n) { return n >= 2048 ? 0 : n >= 256 ? 1 : n >= 48 ? 2 : 3; }
+
 struct GroupTask {
     const uint2 *anc;            // compact sorted anchors: x = target pos, y = span << 24 | qpos'
-    const uint64_t *akey;        // sorted keys (query / target / strand of a group)
-    const uint32_t *gstart;      // n_groups + 1
-    const uint32_t *glist;       // 4 size classes, each a list of group ids, capacity n_groups
+    const GroupDesc *gl[4];      // 4 size classes, largest first
     const uint32_t *gcount;      // entries per class
-    uint32_t n_groups;
     uint32_t *work_ctr;
     int2 *fp;                    // per anchor (f, p)
     int32_t *t;                  // per anchor marks, zeroed before launch
-    uint32_t *pflag;             // per group: pair-level "already counted"
-    int PB, RB;
-    uint32_t q0;
+    uint32_t *pflag;             // per pair slot: "already counted"
+    uint2 *dd_out;               // duplicate target names (host-side HashSet<name> dedupe): passing (query, target) pairs
+    unsigned long long *dd_n;
 };
 
 __device__ __forceinline__ int32_t warp_prefix_max_incl(int32_t v, uint32_t lane) {
@@ -437,28 +445,20 @@ __global__ void __launch_bounds__(CG_THREADS) chain_group_kernel(GroupTask T, Ch
         if (lane == 0) w = atomicAdd(T.work_ctr, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= total) break;
-        uint32_t g;
-        if (w < c0) g = T.glist[w];
-        else if (w < c1) g = T.glist[(size_t)T.n_groups + (w - c0)];
-        else if (w < c2) g = T.glist[2 * (size_t)T.n_groups + (w - c1)];
-        else g = T.glist[3 * (size_t)T.n_groups + (w - c2)];
-        const uint32_t g0 = T.gstart[g];
-        const int32_t n = (int32_t)(T.gstart[g + 1] - g0);
-        const uint64_t k0 = T.akey[g0];
-        const int strand = (int)((k0 >> T.PB) & 1);
-        const uint32_t rid = (uint32_t)((k0 >> (T.PB + 1)) & ((1ULL << T.RB) - 1));
-        const uint32_t qid = T.q0 + (uint32_t)(k0 >> (T.PB + 1 + T.RB));
+        const GroupDesc *dp = w < c0 ? T.gl[0] + w : w < c1 ? T.gl[1] + (w - c0) : w < c2 ? T.gl[2] + (w - c1) : T.gl[3] + (w - c2);
+        const GroupDesc d = *dp;
         int kept = 0, pass = 0;
-        chain_one_group(AncAoS{T.anc + g0}, n, T.fp + g0, T.t + g0, P, s_pen, O, lane, qid, rid, strand, kept, pass);
+        chain_one_group(AncAoS{T.anc + d.start}, (int32_t)d.n, T.fp + d.start, T.t + d.start, P, s_pen, O, lane, d.qid, d.rid,
+                        (int)d.strand, kept, pass);
         if (lane == 0 && kept) {
-            // the two strand groups of one (query, target) pair share a slot: the forward group's
-            uint32_t slot = g;
-            if (strand && g > 0 && (T.akey[T.gstart[g - 1]] >> (T.PB + 1)) == (k0 >> (T.PB + 1))) slot = g - 1;
-            if (O.mode == 0) O.had_mapping[qid] = 1;
-            if (pass && atomicExch(&T.pflag[slot], 1u) == 0u) {
-                if (O.mode == 0) { if (O.names_unique) atomicAdd(&O.counts[qid], 1u); }
-                else if (O.mode == 1) { if (O.rank_q[qid] != O.rank_t[rid]) { atomicAdd(&O.counts[qid], 1u); atomicAdd(&O.counts[rid], 1u); } }
-                else atomicAdd(&O.counts[rid], 1u);
+            if (O.mode == 0) O.had_mapping[d.qid] = 1;
+            if (pass && atomicExch(&T.pflag[d.pair], 1u) == 0u) {
+                if (O.mode == 0) {
+                    if (O.names_unique) atomicAdd(&O.counts[d.qid], 1u);
+                    else T.dd_out[atomicAdd(T.dd_n, 1ull)] = make_uint2(d.qid, d.rid);
+                } else if (O.mode == 1) {
+                    if (O.rank_q[d.qid] != O.rank_t[d.rid]) { atomicAdd(&O.counts[d.qid], 1u); atomicAdd(&O.counts[d.rid], 1u); }
+                } else atomicAdd(&O.counts[d.rid], 1u);
             }
         }
     }
@@ -474,16 +474,27 @@ __global__ void group_mark_kernel(const uint64_t *__restrict__ akey, const uint3
     flags[i] = (i == 0 || (k >> PB) != (akey[i - 1] >> PB)) ? 1 : 0;
 }
 
-// groups that can hold a chain (n >= min_cnt and n * max_span >= min_sc: f <= sum of spans) -> 4 size classes
-__global__ void group_classify_kernel(const uint32_t *__restrict__ gstart, uint32_t n_groups, int min_cnt, int min_sc,
-                                      int max_span, uint32_t *__restrict__ glist, uint32_t *__restrict__ gcount) {
+// global path: groups that can hold a chain (n >= min_cnt and n * max_span >= min_sc: f <= sum of spans) -> descriptors
+// in 4 size classes.  The pair slot is the index of the pair's forward group (or the group itself).
+struct GroupLists { GroupDesc *gl[4]; uint32_t cap[4]; };
+__global__ void group_classify_kernel(const uint64_t *__restrict__ akey, const uint32_t *__restrict__ gstart, uint32_t n_groups,
+                                      int PB, int RB, uint32_t q0, int min_cnt, int min_sc, int max_span, GroupLists L,
+                                      uint32_t *__restrict__ gcount) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
-    const uint32_t n = gstart[g + 1] - gstart[g];
+    const uint32_t g0 = gstart[g], n = gstart[g + 1] - g0;
     if ((int)n < min_cnt || (int64_t)n * max_span < min_sc) return;
-    const int c = n >= 2048 ? 0 : n >= 256 ? 1 : n >= 48 ? 2 : 3;
+    const uint64_t k0 = akey[g0];
+    GroupDesc d;
+    d.start = g0; d.n = n;
+    d.strand = (uint32_t)((k0 >> PB) & 1);
+    d.rid = (uint32_t)((k0 >> (PB + 1)) & ((1ULL << RB) - 1));
+    d.qid = q0 + (uint32_t)(k0 >> (PB + 1 + RB));
+    d.pair = g;
+    if (d.strand && g > 0 && (akey[gstart[g - 1]] >> (PB + 1)) == (k0 >> (PB + 1))) d.pair = g - 1;
+    const int c = group_class(n);
     const uint32_t slot = atomicAdd(&gcount[c], 1u);
-    glist[(size_t)c * n_groups + slot] = g;
+    if (slot < L.cap[c]) L.gl[c][slot] = d;
 }
 
 }  // namespace lrge

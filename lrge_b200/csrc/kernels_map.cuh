@@ -1,25 +1,25 @@
-// kernels_map.cuh -- K4-K6 fused: one CTA maps one query read end to end in shared memory.
+// kernels_map.cuh -- K4a seed lookup and K5: per-query shared-memory sort of the anchors.
 //
-// Replaces, per query, what minimap2's mm_map_frag does after collect_minimizers (map.c): mm_collect_matches
-// (seed.c), collect_seed_hits + skip_seed + radix_sort_128x (map.c), mg_lchain_dp + mg_chain_backtrack (lchain.c),
-// the coordinate part of mm_gen_regs (hit.c) and liblrge's per-read dedupe + count (twoset.rs:286-302,
-// ava.rs:271-306, twoset.rs:477-525) -- SURVEY.md rows a8-a14 -- without the anchors ever touching HBM:
+// Replaces minimap2's mm_collect_matches lookup (seed.c) and radix_sort_128x in collect_seed_hits (map.c), SURVEY.md rows
+// a8-a9, for ALL queries of a batch:
 //
-//   seed_lookup_kernel   every query minimizer of the batch: bucket table -> compact keys -> (start, n) of its hit list
-//   map_query_kernel     persistent CTAs pull queries (longest first) from a work counter; per query
-//     1. expand   hit lists (128-bit loads, two 8-byte entries each) -> anchors (sort key, payload) staged in smem,
-//                 in minimizer order (the order collect_seed_hits generates them)
-//     2. sort     block-wide stable LSD radix sort in smem by (target, strand, target position)
-//     3. chain    warps claim 32-anchor windows of the sorted array, find the (query, target) pairs that start in
-//                 them and run the chaining DP (+ backtrack where -F / records need it) on the smem-resident anchors
-//     4. count    distinct targets with a kept chain -> counts[], had_mapping[]
-//   A query whose anchors exceed the smem capacity is mapped in ROUNDS over disjoint target-id ranges (groups never
-//   span targets, so rounds are independent); ranges come from a 1024-bin histogram of its hits over target ids.
-//   A query that cannot be planned (one bin alone above capacity, > 255 rounds) is appended to `deferred` and the
-//   host maps it through the global-memory path (kernels_seed.cuh / CUB sort / chain_group_kernel).
+//   seed_lookup_kernel   every query minimizer: bucket table -> compact keys -> (start, n) of its hit list
+//   (anchor_fill_kernel, kernels_seed.cuh: hit lists -> anchors of each query, contiguous, in generation order)
+//   sort_query_kernel    persistent CTAs pull queries (longest first) from a work counter; per query
+//     1. stage   its anchors HBM -> shared memory (coalesced), as (sort key, payload)
+//     2. sort    block-wide stable LSD radix sort in smem on the (target, strand) bits: groups become contiguous and keep
+//                their generation order
+//     3. groups  warps claim 32-anchor windows of the sorted array, find the (query, target) pairs that start in them and,
+//                for every strand group that can hold a chain, bring it into target-position order (already ascending /
+//                strictly descending for a colinear overlap; warp-level radix sort otherwise), write it back as compact
+//                anchors and append a group descriptor for the chaining kernel (chain_group_kernel, kernels_chain.cuh)
+//   A query whose anchors exceed the smem capacity is sorted in ROUNDS over disjoint target-id ranges (groups never span
+//   targets, so rounds are independent); ranges come from a 1024-bin histogram of its anchors over target ids.
+//   A query that cannot be planned (one bin alone above capacity, > 255 rounds) is appended to `deferred` and the host
+//   sorts it with the device-wide radix sort of the global path.
 //
-// Stable sort + minimizer-order generation = the tie order of the global path (ksort's radix
-// sort is unstable; ties are equal (target, strand, position) anchors from repeated query k-mers).
+// Stable sort + generation order = the tie order of the global path (ksort's radix sort is
+// unstable; ties are equal (target, strand, position) anchors from repeated query k-mers).
 #pragma once
 #include "common.cuh"
 #include "kernels_index.cuh"
@@ -29,7 +29,7 @@
 namespace lrge {
 
 constexpr int MAP_MAX_WARPS = 32;
-constexpr int MAP_BINS = 1024;         // target-id histogram bins for round planning
+constexpr int MAP_BINS = 512;          // target-id histogram bins for round planning
 constexpr int MAP_MAX_ROUNDS = 255;
 constexpr int SL_ILP = 4;              // independent probes per thread in seed_lookup_kernel
 constexpr int SL_THREADS = 256;
@@ -41,6 +41,7 @@ constexpr int SL_THREADS = 256;
 __global__ void __launch_bounds__(SL_THREADS) seed_lookup_kernel(const uint64_t *__restrict__ qx, const uint8_t *__restrict__ flt,
                                                                  uint64_t MQ, IndexView I, int mid_occ,
                                                                  uint32_t *__restrict__ hstart, uint32_t *__restrict__ hn,
+                                                                 uint32_t *__restrict__ acnt,
                                                                  unsigned long long *n_seeds, unsigned long long *n_hits) {
     const uint64_t base = (uint64_t)blockIdx.x * (SL_THREADS * SL_ILP) + threadIdx.x;
     uint64_t key[SL_ILP];
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(SL_THREADS) seed_lookup_kernel(const uint64_t 
         }
         hstart[i] = start;
         hn[i] = n;
+        acnt[i] = n;                                                            // no skip_seed condition can apply (host decides)
         seeds += n ? 1 : 0;
         hits += n;
     }
@@ -92,26 +94,27 @@ __global__ void __launch_bounds__(SL_THREADS) seed_lookup_kernel(const uint64_t 
     if ((threadIdx.x & 31) == 0 && hits) { atomicAdd(n_seeds, (unsigned long long)seeds); atomicAdd(n_hits, (unsigned long long)hits); }
 }
 
-// ---- K4b-K6 fused ------------------------------------------------------------------------------------------------
-struct MapArgs {
-    const uint64_t *qx, *qy;         // query minimizers (read, position) order
-    const uint32_t *moff;            // nq + 1
-    const uint32_t *hstart, *hn;     // seed_lookup_kernel
-    IndexView I;
-    SkipCtx S;
-    ChainParams P;
-    CountOut O;
-    const uint32_t *qorder;          // queries, longest first
+// ---- K5: per-query shared-memory sort ---------------------------------------------------------------------------
+struct SortArgs {
+    const void *akey;                // anchors of the batch, per query contiguous, in generation order (anchor_fill_kernel):
+    const uint32_t *aval;            //   key (KT) = ((rid - rid_base) << 1 | rev) << PB | target pos, val = span << 24 | qpos'
+    const uint64_t *qaoff;           // per query (absolute id): anchors before it
+    uint64_t a_base;                 // qaoff of the batch's first query: akey[0] is anchor a_base
+    const uint32_t *qorder;          // queries of the batch, longest first
     uint32_t nq;
     uint32_t *work_ctr;
     uint32_t cap;                    // anchors per round (smem capacity), multiple of 32, < 65536
-    int PB, key_bits;                // key = ((rid - rid_base) << 1 | rev) << PB | target position
+    int PB, key_bits;                // key_bits = bits of (rid - rid_base) + 1 + PB
     uint32_t rid_base;               // first target id held by this index (sharded index: the rank's block)
     int hshift;                      // histogram bin = (rid - rid_base) >> hshift
-    int max_span;                    // k, or 255 with HPC: a group of n anchors scores at most n * max_span
+    int max_span, min_cnt, min_sc;   // a group of n anchors scores at most n * max_span
+    uint2 *anc;                      // out: sorted compact anchors (target pos, payload), same offsets as akey
+    GroupLists L;                    // out: descriptors of the groups that can hold a chain, 4 size classes
+    uint32_t *gcount;                //      entries per class
+    uint32_t *pair_ctr;              //      pair slots handed out
     uint32_t *deferred, *n_deferred; // queries left to the global path
     unsigned long long *stats;       // [0] anchors [1] (query, target, strand) groups [2] rounds [3] capacity violations
-    unsigned long long *cyc;         // optional: SM cycles per phase summed over CTAs: [0] plan [1] expand [2] sort [3] chain [4] total
+    unsigned long long *cyc;         // optional: SM cycles per phase summed over CTAs: [0] plan [1] stage [2] sort [3] groups [4] total
 };
 
 // exclusive scan of one value per thread over the CTA (NT threads); total = sum.  wsum: NT / 32 + 1 words of smem.
@@ -152,7 +155,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *wsum, 
 // Returns 1 if the result is in (kB, vB).
 template <typename KT, int NT>
 __device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint32_t N, int lo_bit, int n_bits,
-                                uint16_t *hist, uint32_t *rank, uint32_t *wsum) {
+                                uint16_t *hist, uint16_t *rank, uint32_t *wsum) {
     constexpr int MAP_THREADS = NT, MAP_WARPS = NT / 32;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int passes = n_bits > 8 ? (n_bits + 7) / 8 : 1;
@@ -174,7 +177,7 @@ __device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint
             const bool valid = e < hi;
             const uint32_t d = valid ? (uint32_t)(ks[e] >> shift) & dmask : 0;
             const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);   // lanes holding the same digit
-            if (valid) rank[e] = (uint32_t)myh[d] + __popc(peers & lt);
+            if (valid) rank[e] = (uint16_t)(myh[d] + __popc(peers & lt));
             __syncwarp();
             if (valid && (peers & lt) == 0) myh[d] = (uint16_t)(myh[d] + __popc(peers));     // lowest peer updates the count
             __syncwarp();
@@ -215,7 +218,7 @@ __device__ int block_radix_sort(KT *kA, uint32_t *vA, KT *kB, uint32_t *vB, uint
 // position: those cases cost one read.  Anything else (repeats) is sorted by a warp-level LSD radix sort on the PB
 // position bits, with scr (8 bytes per anchor) as the second buffer, myh (256 counters) and rank (n words) as scratch.
 template <typename KT>
-__device__ void warp_sort_group(KT *K, uint32_t *V, int32_t n, int PB, uint2 *scr, uint16_t *myh, uint32_t *rank, uint32_t lane) {
+__device__ void warp_sort_group(KT *K, uint32_t *V, int32_t n, int PB, uint2 *scr, uint16_t *myh, uint16_t *rank, uint32_t lane) {
     const KT posmask = (KT)(((KT)1 << PB) - 1);
     bool asc = true, desc = true;
     for (int32_t b = 0; b + 1 < n; b += 32) {
@@ -253,7 +256,7 @@ __device__ void warp_sort_group(KT *K, uint32_t *V, int32_t n, int PB, uint2 *sc
             if (valid) pos = from_k ? (uint32_t)(K[e] & posmask) : scr[e].x;
             const uint32_t d = (pos >> shift) & 255u;
             const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
-            if (valid) rank[e] = (uint32_t)myh[d] + __popc(peers & lt);
+            if (valid) rank[e] = (uint16_t)(myh[d] + __popc(peers & lt));
             __syncwarp();
             if (valid && (peers & lt) == 0) myh[d] = (uint16_t)(myh[d] + __popc(peers));
             __syncwarp();
@@ -281,36 +284,15 @@ __device__ void warp_sort_group(KT *K, uint32_t *V, int32_t n, int PB, uint2 *sc
         for (int32_t e = lane; e < n; e += 32) { const uint2 r = scr[e]; K[e] = high | (KT)r.x; V[e] = r.y; }
         __syncwarp();
     }
-    for (int32_t e = lane; e < n; e += 32) rank[e] = 0;                   // rank aliases the DP's mark array
-    __syncwarp();
-}
-
-// per-lane walk over one hit list with four independent 128-bit loads (two 8-byte entries each) in flight;
-// fn(entry, j) is called in ascending j
-template <typename F>
-__device__ __forceinline__ void for_hits(const uint4 *__restrict__ ty4, uint32_t start, uint32_t n, F fn) {
-    const uint32_t p1 = (start + n + 1) >> 1;
-    for (uint32_t p = start >> 1; p < p1; p += 4) {
-        uint4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = p + u < p1 ? __ldg(ty4 + p + u) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint32_t e0 = 2 * (p + u), e1 = e0 + 1;
-            if (e0 >= start && e0 < start + n) fn((uint64_t)v[u].y << 32 | v[u].x, e0 - start);
-            if (e1 >= start && e1 < start + n) fn((uint64_t)v[u].w << 32 | v[u].z, e1 - start);
-        }
-    }
 }
 
 template <typename KT, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) map_query_kernel(MapArgs A) {
+__global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
     constexpr int MAP_THREADS = NT, MAP_WARPS = NT / 32;
     extern __shared__ __align__(16) uint8_t map_smem[];
     __shared__ uint32_t s_wsum[MAP_WARPS + 1];
     __shared__ uint32_t s_rbound[MAP_MAX_ROUNDS + 2];
-    __shared__ uint32_t s_q, s_qn, s_nrounds, s_unit, s_cnt, s_kept;
-    __shared__ uint8_t s_pen[2048];
+    __shared__ uint32_t s_q, s_nrounds, s_unit;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t cap = A.cap;
@@ -319,18 +301,16 @@ __global__ void __launch_bounds__(NT, MINB) map_query_kernel(MapArgs A) {
     uint8_t *bufY = map_smem + (size_t)cap * (sizeof(KT) + 4);
     KT *kY = reinterpret_cast<KT *>(bufY);
     uint32_t *vY = reinterpret_cast<uint32_t *>(bufY + (size_t)cap * sizeof(KT));
-    int32_t *t = reinterpret_cast<int32_t *>(bufY + (size_t)cap * (sizeof(KT) + 4));
-    uint16_t *hist = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(t) + (size_t)cap * 4);
+    uint16_t *rank = reinterpret_cast<uint16_t *>(bufY + (size_t)cap * (sizeof(KT) + 4));
+    uint16_t *hist = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(rank) + (size_t)cap * 2);
+    uint32_t *bins = reinterpret_cast<uint32_t *>(kY);                    // round planning only (before staging)
 
-    for (int i = tid; i <= A.P.bw && i < 2048; i += MAP_THREADS) s_pen[i] = (uint8_t)A.P.pen[i];
     const int PB = A.PB;
-    const KT posmask = (KT)(((KT)1 << PB) - 1);
-    const uint4 *ty4 = reinterpret_cast<const uint4 *>(A.I.ty);
     unsigned long long st_anchors = 0, st_groups = 0, st_rounds = 0;     // st_groups: per warp (lane 0), others: thread 0
     long long cy[5] = {0, 0, 0, 0, 0};                                    // thread 0: cycles per phase
     const long long t_begin = clock64();
 
-    // exclusive scan of one total per warp: returns this warp's base, *total = sum (two barriers)
+    // exclusive scan of one total per warp: returns this warp's base, *total = sum
     auto scan_warp_totals = [&](uint32_t wt, uint32_t *total) -> uint32_t {
         if (lane == 0) s_wsum[warp] = wt;
         __syncthreads();
@@ -349,144 +329,115 @@ __global__ void __launch_bounds__(NT, MINB) map_query_kernel(MapArgs A) {
         return base;
     };
 
-    // Work is pulled one query ahead: while the current query is sorted and chained, the hit lists of the next one are
-    // brought into L2 (prefetch.global.L2), so that its expansion does not wait on first-touch DRAM latency.
-    if (tid == 0) s_qn = atomicAdd(A.work_ctr, 1u);
     for (;;) {
         __syncthreads();
-        if (tid == 0) { s_q = s_qn; s_qn = s_qn < A.nq ? atomicAdd(A.work_ctr, 1u) : s_qn; s_cnt = 0; s_kept = 0; }
+        if (tid == 0) s_q = atomicAdd(A.work_ctr, 1u);
         __syncthreads();
         if (s_q >= A.nq) break;
         long long tc = clock64();
         const uint32_t qid = A.qorder[s_q];
-        if (s_qn < A.nq) {
-            const uint32_t qn = A.qorder[s_qn];
-            const uint32_t e1 = A.moff[qn + 1];
-            for (uint32_t i = A.moff[qn] + tid; i < e1; i += MAP_THREADS) {
-                const uint32_t n = A.hn[i];
-                if (n) {
-                    const uint64_t *p0 = A.I.ty + A.hstart[i];
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p0));
-                    if ((((uintptr_t)p0) & 127) + (size_t)n * 8 > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + n - 1));
-                }
-            }
-        }
-        const uint32_t m0 = A.moff[qid], m1 = A.moff[qid + 1];
-        const uint32_t qlen = A.S.len_q[qid];
-        // every warp owns a contiguous slice of the query's minimizers: expansion needs one block-wide scan per round
-        const uint32_t slice = ((m1 - m0 + MAP_WARPS - 1) / MAP_WARPS + 31) / 32 * 32;
-        const uint32_t w0 = min(m0 + warp * slice, m1), w1 = min(w0 + slice, m1);
+        const uint64_t a0 = A.qaoff[qid] - A.a_base;
+        const uint32_t Aq = (uint32_t)(A.qaoff[qid + 1] - A.qaoff[qid]);
+        if (Aq == 0) continue;
+        const KT *gk = reinterpret_cast<const KT *>(A.akey) + a0;
+        const uint32_t *gv = A.aval + a0;
+        // every warp owns a contiguous slice of the query's anchors (order-preserving compaction in multi-round mode)
+        const uint32_t slice = ((Aq + MAP_WARPS - 1) / MAP_WARPS + 31) / 32 * 32;
+        const uint32_t w0 = min(warp * slice, Aq), w1 = min(w0 + slice, Aq);
 
-        // total hit-list entries of this query (an upper bound of its anchors) and of every warp's slice
-        uint32_t wt = 0;
-        for (uint32_t b = w0; b < w1; b += 32) wt += b + lane < w1 ? A.hn[b + lane] : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
-        uint32_t H;
-        uint32_t wbase = scan_warp_totals(wt, &H);
-        if (H == 0) continue;
-
-        // does a hit survive skip_seed and belong to the target range [rlo, rhi) (ids relative to rid_base)?
-        auto keep = [&](uint64_t r, uint32_t q_pos, uint32_t rlo, uint32_t rhi) -> bool {
-            const uint32_t rel = (uint32_t)(r >> 32) - A.rid_base;
-            if (rel < rlo || rel >= rhi) return false;
-            return !skip_hit(r, qid, q_pos, A.S);
-        };
-
-        const bool filtered = A.S.check_names || A.S.sharded || H > cap;
         uint32_t nrounds = 1;
-        if (H > cap) {
-            // plan rounds: histogram of the kept hits over target ids, then greedy ranges of <= cap anchors
-            uint32_t *bins = reinterpret_cast<uint32_t *>(t);
+        if (Aq > cap) {
+            // plan rounds: histogram of the anchors over target ids (MAP_BINS bins), prefix sums, then R ranges of about
+            // Aq / R anchors each (R sized for 85 % fill); every range is checked against the capacity, and a plan that
+            // does not fit falls back to the exact greedy partition
             for (uint32_t i = tid; i < MAP_BINS; i += MAP_THREADS) bins[i] = 0;
             __syncthreads();
-            for (uint32_t b = w0; b < w1; b += 32) {
-                const uint32_t i = b + lane;
-                const uint32_t n = i < w1 ? A.hn[i] : 0;
-                if (!n) continue;
-                const uint32_t start = A.hstart[i], q_pos = (uint32_t)A.qy[i];
-                for_hits(ty4, start, n, [&](uint64_t r, uint32_t) {
-                    if (keep(r, q_pos, 0u, 0xffffffffu)) atomicAdd(&bins[((uint32_t)(r >> 32) - A.rid_base) >> A.hshift], 1u);
-                });
-            }
+            for (uint32_t i = tid; i < Aq; i += MAP_THREADS) atomicAdd(&bins[(uint32_t)(gk[i] >> (PB + 1)) >> A.hshift], 1u);
             __syncthreads();
-            if (tid == 0) {
-                uint32_t r = 0, acc = 0;
-                bool ok = true;
-                s_rbound[0] = 0;
-                for (uint32_t b = 0; b < MAP_BINS; ++b) {
-                    const uint32_t c = bins[b];
-                    if (c > cap) { ok = false; break; }
-                    if (acc + c > cap) {
-                        if (++r >= MAP_MAX_ROUNDS) { ok = false; break; }
-                        s_rbound[r] = b << A.hshift;
-                        acc = 0;
-                    }
-                    acc += c;
+            const uint32_t mine = tid < MAP_BINS ? bins[tid] : 0;
+            uint32_t tot;
+            const uint32_t excl = block_excl_scan<NT>(mine, s_wsum, tot);  // anchors in the bins before bin `tid`
+            const uint32_t R = (uint32_t)(((uint64_t)Aq * 100 + (uint64_t)cap * 85 - 1) / ((uint64_t)cap * 85));
+            const uint32_t tgt = (Aq + R - 1) / R;
+            const bool quick = R <= MAP_MAX_ROUNDS;
+            if (quick) {
+                for (uint32_t k = tid; k <= R; k += MAP_THREADS) s_rbound[k] = k == 0 ? 0u : k == R ? 0xffffffffu : 0xfffffffeu;
+                __syncthreads();
+                if (tid > 0 && tid < MAP_BINS) {                           // range k starts at the first bin b with excl[b] >= k * tgt
+                    const uint32_t ex_prev = excl - bins[tid - 1];
+                    for (uint32_t k = ex_prev / tgt + 1; k <= excl / tgt && k < R; ++k) s_rbound[k] = tid << A.hshift;
                 }
-                s_rbound[r + 1] = 0xffffffffu;
-                s_nrounds = ok ? r + 1 : 0;
-            }
+                __syncthreads();
+                bool bad = false;                                          // a range left unset (0xfffffffe) is an empty tail round
+                if (tid < R) {
+                    const uint32_t b0 = s_rbound[tid] >= 0xfffffffeu ? MAP_BINS : s_rbound[tid] >> A.hshift;
+                    const uint32_t b1 = s_rbound[tid + 1] >= 0xfffffffeu ? MAP_BINS : s_rbound[tid + 1] >> A.hshift;
+                    uint32_t cnt = 0;
+                    for (uint32_t bb = b0; bb < b1; ++bb) cnt += bins[bb];
+                    bad = cnt > cap;
+                }
+                const int any_bad = __syncthreads_or(bad);
+                if (tid == 0) s_nrounds = any_bad ? 0 : R;
+            } else if (tid == 0) s_nrounds = 0;
             __syncthreads();
+            if (s_nrounds == 0) {                                         // exact greedy partition (serial, rare)
+                if (tid == 0) {
+                    uint32_t r = 0, acc = 0;
+                    bool ok = true;
+                    s_rbound[0] = 0;
+                    for (uint32_t b = 0; b < MAP_BINS; ++b) {
+                        const uint32_t c = bins[b];
+                        if (c > cap) { ok = false; break; }
+                        if (acc + c > cap) {
+                            if (++r >= MAP_MAX_ROUNDS) { ok = false; break; }
+                            s_rbound[r] = b << A.hshift;
+                            acc = 0;
+                        }
+                        acc += c;
+                    }
+                    s_rbound[r + 1] = 0xffffffffu;
+                    s_nrounds = ok ? r + 1 : 0;
+                }
+                __syncthreads();
+            }
             nrounds = s_nrounds;
             if (nrounds == 0) {
                 if (tid == 0) A.deferred[atomicAdd(A.n_deferred, 1u)] = qid;
                 continue;
             }
-        } else {
-            if (tid == 0) { s_rbound[0] = 0; s_rbound[1] = 0xffffffffu; }
-            __syncthreads();
         }
-
         { const long long now = clock64(); cy[0] += now - tc; tc = now; }
+        uint32_t round_base = 0;                                         // anchors written back by earlier rounds
         for (uint32_t rd = 0; rd < nrounds; ++rd) {
-            const uint32_t rlo = s_rbound[rd], rhi = s_rbound[rd + 1];
-            // ---- 1. expand: anchors in minimizer order into (kX, vX) ------------------------------------------
-            uint32_t N = H;
-            if (filtered) {                                               // kept anchors of every warp's slice in this round
-                wt = 0;
-                for (uint32_t b = w0; b < w1; b += 32) {
-                    const uint32_t i = b + lane;
-                    const uint32_t n = i < w1 ? A.hn[i] : 0;
-                    if (!n) continue;
-                    const uint32_t start = A.hstart[i], q_pos = (uint32_t)A.qy[i];
-                    for_hits(ty4, start, n, [&](uint64_t r, uint32_t) { wt += keep(r, q_pos, rlo, rhi); });
+            // ---- 1. stage: HBM -> smem, generation order kept --------------------------------------------------
+            uint32_t N = Aq;
+            if (nrounds == 1) {
+                // straight copy, eight independent coalesced loads in flight per thread
+                for (uint32_t b = 0; b < Aq; b += 4 * MAP_THREADS) {
+                    KT k[4]; uint32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const uint32_t i = b + u * MAP_THREADS + tid; if (i < Aq) { k[u] = gk[i]; v[u] = gv[i]; } }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const uint32_t i = b + u * MAP_THREADS + tid; if (i < Aq) { kX[i] = k[u]; vX[i] = v[u]; } }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
-                wbase = scan_warp_totals(wt, &N);
-            }
-            if (N > cap) { if (tid == 0) atomicAdd(A.stats + 3, 1ull); N = 0; }   // cannot happen (planned)
-            if (N) {
-                uint32_t run = wbase;
-                for (uint32_t b = w0; b < w1; b += 32) {
-                    const uint32_t i = b + lane;
-                    uint32_t start = 0, n = 0, q_pos = 0, q_span = 0;
-                    if (i < w1) {
-                        n = A.hn[i];
-                        if (n) { start = A.hstart[i]; q_pos = (uint32_t)A.qy[i]; q_span = (uint32_t)(A.qx[i] & 0xff); }
-                    }
-                    uint32_t kept = n;
-                    if (filtered && n) {
-                        kept = 0;
-                        for_hits(ty4, start, n, [&](uint64_t r, uint32_t) { kept += keep(r, q_pos, rlo, rhi); });
-                    }
-                    uint32_t incl = kept;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += u; }
-                    uint32_t o = run + incl - kept;
-                    run += __shfl_sync(0xffffffffu, incl, 31);
-                    if (kept) {
-                        const uint32_t qp_f = q_pos >> 1, qp_r = qlen - ((q_pos >> 1) + 1 - q_span) - 1;
-                        auto emit = [&](uint64_t r, uint32_t at) {
-                            if (at >= cap) return;
-                            const uint32_t rev = ((uint32_t)r ^ q_pos) & 1;
-                            const KT rel = (KT)((uint32_t)(r >> 32) - A.rid_base);
-                            kX[at] = (KT)((((rel << 1) | (KT)rev) << PB) | (KT)((uint32_t)r >> 1));
-                            vX[at] = q_span << 24 | (rev ? qp_r : qp_f);
-                        };
-                        if (!filtered) for_hits(ty4, start, n, [&](uint64_t r, uint32_t j) { emit(r, o + j); });
-                        else for_hits(ty4, start, n, [&](uint64_t r, uint32_t) { if (keep(r, q_pos, rlo, rhi)) emit(r, o++); });
+            } else {
+                const uint32_t rlo = s_rbound[rd], rhi = s_rbound[rd + 1];
+                auto in_round = [&](KT k) -> bool {
+                    const uint32_t rel = (uint32_t)(k >> (PB + 1));
+                    return rel >= rlo && rel < rhi;
+                };
+                uint32_t wt = 0;
+                for (uint32_t b = w0; b < w1; b += 32) wt += __popc(__ballot_sync(0xffffffffu, b + lane < w1 && in_round(gk[b + lane])));
+                uint32_t run = scan_warp_totals(wt, &N);
+                if (N > cap) { if (tid == 0) atomicAdd(A.stats + 3, 1ull); N = 0; }   // cannot happen (planned)
+                if (N) {
+                    for (uint32_t b = w0; b < w1; b += 32) {
+                        const uint32_t i = b + lane;
+                        const KT k = i < w1 ? gk[i] : (KT)0;
+                        const bool in = i < w1 && in_round(k);
+                        const uint32_t m = __ballot_sync(0xffffffffu, in);
+                        if (in) { const uint32_t at = run + __popc(m & ((1u << lane) - 1)); kX[at] = k; vX[at] = gv[i]; }
+                        run += __popc(m);
                     }
                 }
             }
@@ -496,17 +447,16 @@ __global__ void __launch_bounds__(NT, MINB) map_query_kernel(MapArgs A) {
             if (tid == 0) { st_anchors += N; ++st_rounds; }
 
             // ---- 2. sort by (target, strand): groups become contiguous, still in generation order ----------------
-            const int fin = block_radix_sort<KT, NT>(kX, vX, kY, vY, N, PB, A.key_bits - PB, hist, reinterpret_cast<uint32_t *>(t), s_wsum);
+            const int fin = block_radix_sort<KT, NT>(kX, vX, kY, vY, N, PB, A.key_bits - PB, hist, rank, s_wsum);
             KT *K = fin ? kY : kX;
             uint32_t *V = fin ? vY : vX;
-            int2 *fp = reinterpret_cast<int2 *>(fin ? map_smem : bufY);           // the other buffer: (f, p) scratch
-            for (uint32_t i = tid; i < N; i += MAP_THREADS) t[i] = 0;
+            uint2 *scr = reinterpret_cast<uint2 *>(fin ? map_smem : bufY);        // the other buffer: scratch of the group sorts
             if (tid == 0) s_unit = 0;
             __syncthreads();
             { const long long now = clock64(); cy[2] += now - tc; tc = now; }
 
-            // ---- 3. chain: warps claim 32-anchor windows; the (query, target) pairs starting there are theirs ---
-            uint32_t my_cnt = 0;
+            // ---- 3. groups: warps claim 32-anchor windows; the (query, target) pairs starting there are theirs ---
+            uint2 *out = A.anc + a0 + round_base;
             for (;;) {
                 uint32_t u = 0;
                 if (lane == 0) u = atomicAdd(&s_unit, 1u);
@@ -534,41 +484,35 @@ __global__ void __launch_bounds__(NT, MINB) map_query_kernel(MapArgs A) {
                         if (diff) { e = b + (uint32_t)(__ffs(diff) - 1); break; }
                     }
                     if (split == 0xffffffffu || split > e) split = e;
-                    const uint32_t rid = (uint32_t)pk + A.rid_base;
-                    int kept_any = 0, pass_any = 0;
+                    const uint32_t nf = split - s, nr = e - split;
+                    if (lane == 0) st_groups += (nf > 0) + (nr > 0);
+                    const bool vf = (int32_t)nf >= A.min_cnt && (int64_t)nf * A.max_span >= A.min_sc;
+                    const bool vr = (int32_t)nr >= A.min_cnt && (int64_t)nr * A.max_span >= A.min_sc;
+                    if (!vf && !vr) continue;
+                    uint32_t pair = 0;
+                    if (lane == 0) pair = atomicAdd(A.pair_ctr, 1u);
+                    pair = __shfl_sync(0xffffffffu, pair, 0);
 #pragma unroll 1
                     for (int strand = 0; strand < 2; ++strand) {
-                        const uint32_t g0 = strand ? split : s;
-                        const int32_t n = (int32_t)(strand ? e - split : split - s);
-                        if (n == 0) continue;
-                        if (lane == 0) ++st_groups;
-                        if (n < A.P.min_cnt || (int64_t)n * A.max_span < A.P.min_sc) continue;
-                        warp_sort_group<KT>(K + g0, V + g0, n, PB, reinterpret_cast<uint2 *>(fp + g0), hist + warp * 256,
-                                            reinterpret_cast<uint32_t *>(t + g0), lane);
-                        int kept = 0, pass = 0;
-                        chain_one_group(AncSoA<KT>{K + g0, V + g0, posmask}, n, fp + g0, t + g0, A.P, s_pen, A.O, lane, qid, rid,
-                                        strand, kept, pass);
-                        kept_any |= kept; pass_any |= pass;
-                    }
-                    if (lane == 0) {
-                        if (kept_any) s_kept = 1;
-                        if (pass_any) {
-                            if (A.O.mode == 0) ++my_cnt;
-                            else if (A.O.mode == 1) {
-                                if (A.O.rank_q[qid] != A.O.rank_t[rid]) { atomicAdd(&A.O.counts[qid], 1u); atomicAdd(&A.O.counts[rid], 1u); }
-                            } else atomicAdd(&A.O.counts[rid], 1u);
+                        if (!(strand ? vr : vf)) continue;
+                        const uint32_t g0 = strand ? split : s, n = strand ? nr : nf;
+                        warp_sort_group<KT>(K + g0, V + g0, (int32_t)n, PB, scr + g0, hist + warp * 256, rank + g0, lane);
+                        for (uint32_t j = lane; j < n; j += 32)
+                            out[g0 + j] = make_uint2((uint32_t)(K[g0 + j] & (KT)(((KT)1 << PB) - 1)), V[g0 + j]);
+                        if (lane == 0) {
+                            GroupDesc d;
+                            d.start = (uint32_t)(a0 + round_base + g0); d.n = n; d.qid = qid; d.rid = (uint32_t)pk + A.rid_base;
+                            d.strand = (uint32_t)strand; d.pair = pair;
+                            const int c = group_class(n);
+                            const uint32_t slot = atomicAdd(&A.gcount[c], 1u);
+                            if (slot < A.L.cap[c]) A.L.gl[c][slot] = d; else atomicAdd(A.stats + 3, 1ull);
                         }
                     }
                 }
             }
-            if (lane == 0 && my_cnt) atomicAdd(&s_cnt, my_cnt);
+            round_base += N;
             __syncthreads();
             { const long long now = clock64(); cy[3] += now - tc; tc = now; }
-        }
-        // ---- 4. per-query results ------------------------------------------------------------------------------
-        if (tid == 0 && A.O.mode == 0) {
-            A.O.counts[qid] = s_cnt;
-            if (s_kept) A.O.had_mapping[qid] = 1;
         }
     }
     if (tid == 0) {

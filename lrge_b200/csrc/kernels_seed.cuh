@@ -90,15 +90,20 @@ __global__ void seed_count_kernel(const uint64_t *__restrict__ qx, const uint64_
     if ((threadIdx.x & 31) == 0 && hits) { atomicAdd(n_seeds, (unsigned long long)seeds); atomicAdd(n_hits, (unsigned long long)hits); }
 }
 
-struct KeyLayout { int PB, RB; };   // bits of target position / target id in the sort key
+struct KeyLayout { int PB, RB; uint32_t rid_base; };   // bits of target position / target id in the sort key; first local target id
 
-// One thread per query minimizer of the batch [m0, m1): expands its hit list to anchors.
+// One thread per query minimizer of the batch [m0, m1): expands its hit list to anchors, in hit-list order, so that a
+// query's anchors are contiguous and in the order collect_seed_hits generates them.  The hit list (8-byte entries) is
+// read with 128-bit loads, two entries each, four loads in flight per thread.
 // aoff = exclusive scan of anchor counts over ALL query minimizers (64-bit); a0 = aoff[m0].
-__global__ void anchor_fill_kernel(const uint64_t *__restrict__ qx, const uint64_t *__restrict__ qy,
+// WITH_QID: the 64-bit key of the device-wide sort (query bits on top).  Otherwise the key the per-query kernel sorts in
+// shared memory: ((rid - K.rid_base) << 1 | rev) << PB | target pos, as KT.
+template <typename KT, bool WITH_QID>
+__global__ void __launch_bounds__(256) anchor_fill_kernel(const uint64_t *__restrict__ qx, const uint64_t *__restrict__ qy,
                                    const uint32_t *__restrict__ hstart, const uint32_t *__restrict__ hn,
                                    const uint32_t *__restrict__ acnt, const uint64_t *__restrict__ aoff, uint64_t m0, uint64_t m1, uint64_t a0,
                                    uint32_t q0, IndexView I, SkipCtx S, KeyLayout K,
-                                   uint64_t *__restrict__ akey, uint32_t *__restrict__ aval) {
+                                   KT *__restrict__ akey, uint32_t *__restrict__ aval) {
     const uint64_t i = m0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m1) return;
     if (acnt[i] == 0) return;
@@ -110,15 +115,28 @@ __global__ void anchor_fill_kernel(const uint64_t *__restrict__ qx, const uint64
     const bool scan = S.check_names || S.sharded;
     uint64_t o = aoff[i] - a0;
     const uint32_t start = hstart[i];
-    for (uint32_t j = 0; j < n; ++j) {
-        const uint64_t r = I.ty[start + j];
-        if (scan && skip_hit(r, qid, q_pos, S)) continue;
-        const uint32_t rpos = (uint32_t)r >> 1;
-        const uint32_t rev = ((uint32_t)r ^ q_pos) & 1;
-        const uint32_t qp = rev ? (qlen - ((q_pos >> 1) + 1 - q_span) - 1) : (q_pos >> 1);
-        akey[o] = (((qpart | (r >> 32)) << 1 | rev) << K.PB) | rpos;
-        aval[o] = q_span << 24 | qp;
-        ++o;
+    const uint32_t qp_f = q_pos >> 1, qp_r = qlen - ((q_pos >> 1) + 1 - q_span) - 1;
+    const uint4 *ty4 = reinterpret_cast<const uint4 *>(I.ty);
+    const uint32_t p1 = (start + n + 1) >> 1;
+    for (uint32_t p = start >> 1; p < p1; p += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = p + u < p1 ? __ldg(ty4 + p + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t e = 2 * (p + u) + h;
+                if (e < start || e >= start + n) continue;
+                const uint64_t r = h ? ((uint64_t)v[u].w << 32 | v[u].z) : ((uint64_t)v[u].y << 32 | v[u].x);
+                if (scan && skip_hit(r, qid, q_pos, S)) continue;
+                const uint32_t rev = ((uint32_t)r ^ q_pos) & 1;
+                if (WITH_QID) akey[o] = (KT)((((qpart | (r >> 32)) << 1 | rev) << K.PB) | ((uint32_t)r >> 1));
+                else akey[o] = (KT)(((((KT)((uint32_t)(r >> 32) - K.rid_base)) << 1 | (KT)rev) << K.PB) | (KT)((uint32_t)r >> 1));
+                aval[o] = q_span << 24 | (rev ? qp_r : qp_f);
+                ++o;
+            }
+        }
     }
 }
 

@@ -115,7 +115,7 @@ struct Prof {
     std::vector<Span> spans;
     std::vector<std::string> names;                    // kernel spans: id = ST_COUNT + index into names
     std::vector<double> ms, bytes;
-    std::vector<uint32_t> count;
+    std::vector<uint32_t> count, passes;
     int open_kernel = -1;
     cudaEvent_t open_ev = nullptr;
     cudaEvent_t stage_ev[ST_COUNT] = {};
@@ -127,10 +127,11 @@ struct Prof {
     void reset() {
         used = 0; spans.clear(); open_kernel = -1;
         ms.assign(ST_COUNT + names.size(), 0.0); bytes.assign(ST_COUNT + names.size(), 0.0); count.assign(ST_COUNT + names.size(), 0);
+        passes.resize(ST_COUNT + names.size(), 1);
     }
     int kid(const char *name) {
         for (size_t i = 0; i < names.size(); ++i) if (names[i] == name) return ST_COUNT + (int)i;
-        names.emplace_back(name); ms.push_back(0); bytes.push_back(0); count.push_back(0);
+        names.emplace_back(name); ms.push_back(0); bytes.push_back(0); count.push_back(0); passes.push_back(1);
         return ST_COUNT + (int)names.size() - 1;
     }
     void sbegin(Stage st) { stage_ev[st] = get(); cudaEventRecord(stage_ev[st], s); }
@@ -144,9 +145,9 @@ struct Prof {
         if (!kernels || open_kernel < 0) return;
         cudaEvent_t b = get(); cudaEventRecord(b, s); spans.push_back({open_kernel, open_ev, b}); open_kernel = -1;
     }
-    void set_bytes(const char *name, double nbytes) {  // algorithmic bytes known only after the run (device-side counts)
+    void set_passes(const char *name, uint32_t n) {    // a library radix sort: passes over the data inside one "launch"
         if (!kernels) return;
-        for (size_t i = 0; i < names.size(); ++i) if (names[i] == name) bytes[ST_COUNT + i] = nbytes;
+        for (size_t i = 0; i < names.size(); ++i) if (names[i] == name) passes[ST_COUNT + i] = n;
     }
     void resolve() {                                   // the stream must be idle
         for (auto &sp : spans) { float t = 0; cudaEventElapsedTime(&t, sp.a, sp.b); ms[sp.id] += t; ++count[sp.id]; }
@@ -210,7 +211,7 @@ struct lrge_ctx {
     int map_ctas_per_sm = 1;               // LRGE_MAP_CTAS=1|2
     int smem_optin = 0;                    // cudaDevAttrMaxSharedMemoryPerBlockOptin
     int n_sm = 148;
-    DevBuf qorder, deferred, mapctr;
+    DevBuf qorder, deferred, mapctr, ddbuf;
     uint64_t max_anchors = 0;              // LRGE_MAX_ANCHORS=n: cap anchors per query batch
     bool sketch_two_pass = false;          // LRGE_SKETCH_TWO_PASS=1: count + emit instead of stage + compact
     size_t free_at_create = 0, held_at_create = 0;
@@ -471,10 +472,11 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
         size_t tb = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
                                         c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
-        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", ((2 * o.k + 7) / 8) * 32.0 * M + 8.0 * M,
+        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", 32.0 * M,
                 cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
                                                 c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
         c->launches += (2 * o.k + 7) / 8;
+        c->prof.set_passes("cub::DeviceRadixSort(index: u64 key, u64 value)", (2 * o.k + 7) / 8);
     }
     // ~8 entries per bucket: the table (4 B x 2^bits) stays L2-resident, a lookup bisects <= 3 steps
     int bits = 8;
@@ -540,7 +542,7 @@ BuiltIndex build_index_sharded(lrge_ctx *c, const Sketch &sk, const MapOpt &o, l
     if (M) {
         cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
                                         c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
-        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", ((2 * o.k + 7) / 8) * 32.0 * M + 8.0 * M,
+        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", 32.0 * M,
                 cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
                                                 c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
         c->launches += (2 * o.k + 7) / 8;
@@ -839,299 +841,311 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     if (host_dedupe) dedupe_sets.resize(str->n);
     c->prof.send(ST_SEED);
 
-    // ---- global-memory path: anchors of a batch of queries are written to HBM, sorted with one device-wide radix
-    // sort and chained one warp per group.  Used for every query with LRGE_FORCE_GLOBAL=1 or duplicate target names
-    // (host-side HashSet<name> dedupe), and for the queries the fused kernel defers (`only`).
-    auto global_path = [&](const std::vector<uint32_t> *only) {
-        // K4 part 1: filter + lookup + count
-        c->prof.sbegin(ST_SEED);
-        c->flt.reserve(MQ + 1);
-        c->hstart.reserve((MQ + 1) * 4); c->hn.reserve((MQ + 1) * 4); c->acnt.reserve((MQ + 1) * 4);
-        c->aoff.reserve((MQ + 2) * 8);
-        c->qaoff.reserve(((size_t)str->n + 2) * 8);
-        CUDA_CHECK(cudaMemsetAsync(c->flt.p, 0, MQ + 1, c->stream));
-        CUDA_CHECK(cudaMemsetAsync(c->acnt.p, 0, (MQ + 1) * 4, c->stream));
-        std::vector<uint64_t> qa((size_t)str->n + 1, 0);
-        std::vector<uint32_t> moff_h((size_t)str->n + 1, 0);
-        if (MQ) {
-            KLAUNCH(c, "mz_flt_kernel", 16.0 * MQ,
-                    mz_flt_kernel<<<str->n, 256, 0, c->stream>>>(sq->x.as<uint64_t>(), sq->moff.as<uint32_t>(), B.mid_occ, o.q_occ_frac, c->flt.as<uint8_t>()));
+    // ---- K4-K6 --------------------------------------------------------------------------------------------------------
+    // seed stage for all queries (mm_seed_mz_flt, index lookup, anchors per minimizer and their prefix sums), then per
+    // batch of queries bounded by anchor memory: anchor_fill -> sort + group -> chain.
+    //   sort + group = sort_query_kernel, the per-query shared-memory sort (kernels_map.cuh), by default;
+    //                  the device-wide radix sort + group_mark / select / classify with LRGE_FORCE_GLOBAL=1 and for the
+    //                  queries the per-query kernel defers.
+    const bool use_smem_sort = !c->force_global;
+    std::vector<uint64_t> qa((size_t)str->n + 1, 0);
+    std::vector<uint32_t> moff_h((size_t)str->n + 1, 0);
+    c->prof.sbegin(ST_SEED);
+    c->flt.reserve(MQ + 1);
+    c->hstart.reserve((MQ + 8) * 4); c->hn.reserve((MQ + 8) * 4); c->acnt.reserve((MQ + 8) * 4);
+    c->aoff.reserve((MQ + 2) * 8);
+    c->qaoff.reserve(((size_t)str->n + 2) * 8);
+    CUDA_CHECK(cudaMemsetAsync(c->flt.p, 0, MQ + 1, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->acnt.p, 0, (MQ + 8) * 4, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->qaoff.p, 0, ((size_t)str->n + 2) * 8, c->stream));
+    if (MQ) {
+        KLAUNCH(c, "mz_flt_kernel", 16.0 * MQ,
+                mz_flt_kernel<<<str->n, 256, 0, c->stream>>>(sq->x.as<uint64_t>(), sq->moff.as<uint32_t>(), B.mid_occ, o.q_occ_frac, c->flt.as<uint8_t>()));
+        if (K.check_names || K.sharded) {            // skip_seed / shard membership is decided per hit: walk the lists
             KLAUNCH(c, "seed_count_kernel", 28.0 * MQ,
                     seed_count_kernel<<<(unsigned)((MQ + 255) / 256), 256, 0, c->stream>>>(
                         sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->flt.as<uint8_t>(), MQ, B.view, B.mid_occ, K,
-                        c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(), only ? ctr + 8 : ctr, only ? ctr + 9 : ctr + 1));
-            size_t tb = 0;
-            cub::TransformInputIterator<uint64_t, WidenU32, const uint32_t *> in(c->acnt.as<uint32_t>(), WidenU32());
-            cub::DeviceScan::ExclusiveSum(nullptr, tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream);
-            KLAUNCH(c, "cub::DeviceScan(u64)", 12.0 * MQ,
-                    cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream));
-            // anchors before each query: aoff[moff[q]]
-            CUDA_CHECK(cudaMemcpyAsync(moff_h.data(), sq->moff.p, ((size_t)str->n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-            KLAUNCH(c, "gather_kernel", 20.0 * str->n,
-                    gather_u64_kernel<<<(str->n + 1 + 255) / 256, 256, 0, c->stream>>>(c->aoff.as<uint64_t>(), sq->moff.as<uint32_t>(), str->n + 1,
-                                                                                      c->qaoff.as<uint64_t>()));
-            CUDA_CHECK(cudaMemcpyAsync(qa.data(), c->qaoff.p, ((size_t)str->n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        }
-        CUDA_CHECK(cudaGetLastError());
-        c->prof.send(ST_SEED);
-        if (!only) S.n_anchors = qa[str->n];
-
-        // batches of queries bounded by anchor memory
-        const size_t free_b = free_estimate(c);
-        size_t reusable = c->akey0.cap + c->akey1.cap + c->aval0.cap + c->aval1.cap + c->flags.cap + c->pstart.cap +
-                          c->f.cap + c->p.cap + c->t.cap + c->pair_res.cap;
-        reusable += c->anc.cap + c->fp.cap;
-        uint64_t a_max = (uint64_t)((free_b + reusable) * 0.7 / 56.0);
-        a_max = std::min<uint64_t>(a_max, (1ull << 31) - 1024);
-        if (c->max_anchors) a_max = std::min<uint64_t>(a_max, c->max_anchors);   // LRGE_MAX_ANCHORS: force small batches (tests)
-        uint32_t q0 = 0;
-        size_t oi = 0;
-        for (;;) {
-            uint32_t q1;
-            if (only) {                                                    // deferred queries of the fused path, one per batch
-                if (oi >= only->size()) break;
-                q0 = (*only)[oi++]; q1 = q0 + 1;
-            } else {
-                if (q0 >= str->n) break;
-                q1 = q0 + 1;
-                while (q1 < str->n && qa[q1 + 1] - qa[q0] <= a_max) ++q1;
-            }
-            const uint64_t nA = qa[q1] - qa[q0];
-            if (only) S.n_anchors += nA;
-            if (nA > a_max) throw std::length_error("a single read yields more anchors than fit in device memory");
-            const int QB = bits_for(q1 - q0 - 1);
-            if (QB + RB + 1 + PB > 64) throw std::length_error("sort key does not fit 64 bits (too many reads x read length)");
-            if (nA) {
-                ++S.n_batches;
-                c->prof.sbegin(ST_SEED);
-                c->akey0.reserve(nA * 8); c->akey1.reserve(nA * 8); c->aval0.reserve(nA * 4); c->aval1.reserve(nA * 4);
-                const uint64_t m0 = moff_h[q0], m1 = moff_h[q1];
-                KeyLayout KL{PB, RB};
-                KLAUNCH(c, "anchor_fill_kernel", 20.0 * nA + 28.0 * (m1 - m0),
-                        anchor_fill_kernel<<<(unsigned)((m1 - m0 + 255) / 256), 256, 0, c->stream>>>(
-                            sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
-                            c->aoff.as<uint64_t>(), m0, m1, qa[q0], q0, B.view, K, KL, c->akey0.as<uint64_t>(), c->aval0.as<uint32_t>()));
-                c->prof.send(ST_SEED);
-
-                c->prof.sbegin(ST_SORT);
-                size_t tb = 0;
-                const int sort_bits = QB + RB + 1 + PB;
-                cub::DeviceRadixSort::SortPairs(nullptr, tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
-                                                c->aval1.as<uint32_t>(), (int64_t)nA, 0, sort_bits, c->stream);
-                KLAUNCH(c, "cub::DeviceRadixSort(anchors: u64 key, u32 value)", ((sort_bits + 7) / 8) * 24.0 * nA + 8.0 * nA,
-                        cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
-                                                        c->aval1.as<uint32_t>(), (int64_t)nA, 0, sort_bits, c->stream));
-                c->launches += (sort_bits + 7) / 8;
-                CountOut O{};
-                O.counts = c->counts.as<uint32_t>(); O.had_mapping = c->had.as<uint8_t>();
-                O.len_q = K.len_q; O.len_t = K.len_t; O.rank_q = K.rank_q; O.rank_t = K.rank_t;
-                O.mode = mode; O.remove_internal = opts.remove_internal; O.ratio = opts.max_overhang_ratio;
-                O.names_unique = !host_dedupe;
-                if (want_regs) { O.regs = c->regs.as<RegOut>(); O.n_regs = ctr + 2; O.regs_cap = rq->cap; }
-                c->flags.reserve(nA + 1);
-                c->npairs.reserve(16);
-#ifdef LRGE_TEST_KERNELS
-                if (c->chain_v1) {
-                    // ---- v1 (debug cross-check, LRGE_CHAIN_V1=1): one thread per (query, target) pair ----
-                    c->pstart.reserve((nA + 2) * 4);
-                    KLAUNCH(c, "pair_flag_kernel", 9.0 * nA,
-                            pair_flag_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), nA, PB + 1, c->flags.as<uint8_t>()));
-                    cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
-                                               c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
-                    cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
-                                               c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
-                    c->launches += 2;
-                    uint32_t n_pairs = 0;
-                    CUDA_CHECK(cudaMemcpyAsync(&n_pairs, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
-                    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-                    const uint32_t sentinel = (uint32_t)nA;
-                    CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_pairs, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
-                    c->prof.send(ST_SORT);
-                    S.n_pairs += n_pairs;
-                    c->prof.sbegin(ST_CHAIN);
-                    c->f.reserve(nA * 4); c->p.reserve(nA * 4); c->t.reserve(nA * 4);
-                    c->pair_res.reserve((size_t)n_pairs + 1);
-                    CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
-                    PairTask T{};
-                    T.akey = c->akey1.as<uint64_t>(); T.aval = c->aval1.as<uint32_t>(); T.pstart = c->pstart.as<uint32_t>();
-                    T.n_pairs = n_pairs; T.PB = PB; T.RB = RB; T.q0 = q0;
-                    T.f = c->f.as<int32_t>(); T.p = c->p.as<int32_t>(); T.t = c->t.as<int32_t>();
-                    O.pair_res = c->pair_res.as<uint8_t>();
-                    KLAUNCH(c, "chain_pair_kernel", 16.0 * nA + 4.0 * str->n, chain_pair_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(T, P, O));
-                    CUDA_CHECK(cudaGetLastError());
-                    if (host_dedupe) {
-                        std::vector<uint8_t> res(n_pairs);
-                        std::vector<uint32_t> ps((size_t)n_pairs + 1);
-                        std::vector<uint64_t> keys(nA);
-                        CUDA_CHECK(cudaMemcpyAsync(res.data(), c->pair_res.p, n_pairs, cudaMemcpyDeviceToHost, c->stream));
-                        CUDA_CHECK(cudaMemcpyAsync(ps.data(), c->pstart.p, ((size_t)n_pairs + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-                        CUDA_CHECK(cudaMemcpyAsync(keys.data(), c->akey1.p, nA * 8, cudaMemcpyDeviceToHost, c->stream));
-                        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-                        for (uint32_t i = 0; i < n_pairs; ++i) if (res[i] & 2) {
-                            const uint64_t kk = keys[ps[i]];
-                            const uint32_t rid = (uint32_t)((kk >> (PB + 1)) & ((1ull << RB) - 1)), qid = q0 + (uint32_t)(kk >> (PB + 1 + RB));
-                            dedupe_sets[qid].push_back(rank_idx[rid]);
-                        }
-                    }
-                } else
-#endif
-                {
-                    // ---- one warp per (query, target, strand) group --------------------------------------------
-                    c->anc.reserve(nA * 8);
-                    c->pstart.reserve((nA + 2) * 4);
-                    KLAUNCH(c, "group_mark_kernel", 21.0 * nA,
-                            group_mark_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), c->aval1.as<uint32_t>(), nA, PB,
-                                                                                                   c->anc.as<uint2>(), c->flags.as<uint8_t>()));
-                    cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
-                                               c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
-                    KLAUNCH(c, "cub::DeviceSelect(group starts)", 1.0 * nA,
-                            cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
-                                                       c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream));
-                    uint32_t n_groups = 0;
-                    CUDA_CHECK(cudaMemcpyAsync(&n_groups, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
-                    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-                    const uint32_t sentinel = (uint32_t)nA;
-                    CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_groups, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
-                    c->glist.reserve((size_t)n_groups * 16 + 16);
-                    c->gmeta.reserve(64);
-                    c->pflag.reserve((size_t)n_groups * 4 + 4);
-                    CUDA_CHECK(cudaMemsetAsync(c->gmeta.p, 0, 64, c->stream));
-                    CUDA_CHECK(cudaMemsetAsync(c->pflag.p, 0, (size_t)n_groups * 4 + 4, c->stream));
-                    KLAUNCH(c, "group_classify_kernel", 8.0 * n_groups,
-                            group_classify_kernel<<<(n_groups + 255) / 256, 256, 0, c->stream>>>(c->pstart.as<uint32_t>(), n_groups, P.min_cnt, P.min_sc,
-                                                                                                o.is_hpc ? 255 : o.k, c->glist.as<uint32_t>(),
-                                                                                                c->gmeta.as<uint32_t>()));
-                    c->prof.send(ST_SORT);
-                    S.n_pairs += n_groups;
-                    c->prof.sbegin(ST_CHAIN);
-                    c->fp.reserve(nA * 8); c->t.reserve(nA * 4);
-                    CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
-                    GroupTask T{};
-                    T.anc = c->anc.as<uint2>(); T.akey = c->akey1.as<uint64_t>(); T.gstart = c->pstart.as<uint32_t>();
-                    T.glist = c->glist.as<uint32_t>(); T.gcount = c->gmeta.as<uint32_t>(); T.n_groups = n_groups;
-                    T.work_ctr = c->gmeta.as<uint32_t>() + 8;
-                    T.fp = c->fp.as<int2>(); T.t = c->t.as<int32_t>(); T.pflag = c->pflag.as<uint32_t>();
-                    T.PB = PB; T.RB = RB; T.q0 = q0;
-                    KLAUNCH(c, "chain_group_kernel", 16.0 * nA + 4.0 * str->n,
-                            chain_group_kernel<<<148 * (2048 / CG_THREADS), CG_THREADS, 0, c->stream>>>(T, P, O));
-                    CUDA_CHECK(cudaGetLastError());
-                    if (host_dedupe) {
-                        std::vector<uint32_t> pf(n_groups), gs((size_t)n_groups + 1);
-                        std::vector<uint64_t> keys(nA);
-                        CUDA_CHECK(cudaMemcpyAsync(pf.data(), c->pflag.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, c->stream));
-                        CUDA_CHECK(cudaMemcpyAsync(gs.data(), c->pstart.p, ((size_t)n_groups + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-                        CUDA_CHECK(cudaMemcpyAsync(keys.data(), c->akey1.p, nA * 8, cudaMemcpyDeviceToHost, c->stream));
-                        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-                        for (uint32_t g = 0; g < n_groups; ++g) if (pf[g]) {
-                            const uint64_t kk = keys[gs[g]];
-                            const uint32_t rid = (uint32_t)((kk >> (PB + 1)) & ((1ull << RB) - 1)), qid = q0 + (uint32_t)(kk >> (PB + 1 + RB));
-                            dedupe_sets[qid].push_back(rank_idx[rid]);
-                        }
-                    }
-                }
-                c->prof.send(ST_CHAIN);
-            }
-            q0 = q1;
-        }
-
-    };
-
-    // ---- fused path (default): seed lookup, then one CTA per query does expand -> sort -> chain -> count in shared
-    // memory (kernels_map.cuh).  No host synchronisation inside; queries it cannot plan come back in `deferred`.
-    const bool use_fused = !c->force_global && !host_dedupe;
-    uint32_t map_cap = 0;
-    auto fused_path = [&]() {
-        c->prof.sbegin(ST_SEED);
-        c->flt.reserve(MQ + 1);
-        c->hstart.reserve((MQ + 8) * 4); c->hn.reserve((MQ + 8) * 4);
-        CUDA_CHECK(cudaMemsetAsync(c->flt.p, 0, MQ + 1, c->stream));
-        if (MQ) {
-            KLAUNCH(c, "mz_flt_kernel", 16.0 * MQ,
-                    mz_flt_kernel<<<str->n, 256, 0, c->stream>>>(sq->x.as<uint64_t>(), sq->moff.as<uint32_t>(), B.mid_occ, o.q_occ_frac, c->flt.as<uint8_t>()));
+                        c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(), ctr, ctr + 1));
+        } else {
             KLAUNCH(c, "seed_lookup_kernel", 28.0 * MQ,
                     seed_lookup_kernel<<<(unsigned)((MQ + SL_THREADS * SL_ILP - 1) / (SL_THREADS * SL_ILP)), SL_THREADS, 0, c->stream>>>(
-                        sq->x.as<uint64_t>(), c->flt.as<uint8_t>(), MQ, B.view, B.mid_occ, c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), ctr, ctr + 1));
+                        sq->x.as<uint64_t>(), c->flt.as<uint8_t>(), MQ, B.view, B.mid_occ, c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(),
+                        c->acnt.as<uint32_t>(), ctr, ctr + 1));
         }
-        c->prof.send(ST_SEED);
-        c->prof.sbegin(ST_CHAIN);
-        uint32_t r0 = 0, r1 = idx->n;
-        if (sharded_index) shard_range(idx->n, c->rank, world, &r0, &r1);
-        const uint32_t n_local = r1 - r0;
-        const int RBf = bits_for(n_local ? n_local - 1 : 0);
-        const int key_bits = RBf + 1 + PB;
-        if (key_bits > 64) throw std::length_error("sort key does not fit 64 bits (too many reads x read length)");
-        const bool k32 = key_bits <= 32;
-        const bool two = c->map_ctas_per_sm == 2;                                 // 2 CTAs of 512 threads, else 1 CTA of 1024
-        const int NT = two ? 512 : 1024, NW = NT / 32;
-        const void *fn = two ? (k32 ? (const void *)map_query_kernel<uint32_t, 512, 2> : (const void *)map_query_kernel<uint64_t, 512, 2>)
-                             : (k32 ? (const void *)map_query_kernel<uint32_t, 1024, 1> : (const void *)map_query_kernel<uint64_t, 1024, 1>);
+        size_t tb = 0;
+        cub::TransformInputIterator<uint64_t, WidenU32, const uint32_t *> in(c->acnt.as<uint32_t>(), WidenU32());
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream);
+        KLAUNCH(c, "cub::DeviceScan(u64)", 12.0 * MQ,
+                cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, in, c->aoff.as<uint64_t>(), MQ + 1, c->stream));
+        // anchors before each query: aoff[moff[q]]
+        CUDA_CHECK(cudaMemcpyAsync(moff_h.data(), sq->moff.p, ((size_t)str->n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        KLAUNCH(c, "gather_kernel", 20.0 * str->n,
+                gather_u64_kernel<<<(str->n + 1 + 255) / 256, 256, 0, c->stream>>>(c->aoff.as<uint64_t>(), sq->moff.as<uint32_t>(), str->n + 1,
+                                                                                  c->qaoff.as<uint64_t>()));
+        CUDA_CHECK(cudaMemcpyAsync(qa.data(), c->qaoff.p, ((size_t)str->n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    CUDA_CHECK(cudaGetLastError());
+    c->prof.send(ST_SEED);
+    S.n_anchors = qa[str->n];
+
+    // batches of queries bounded by anchor memory (34 bytes per anchor: unsorted 12, sorted 8, DP scratch 12, lists 2)
+    const size_t free_b = free_estimate(c);
+    size_t reusable = c->akey0.cap + c->akey1.cap + c->aval0.cap + c->aval1.cap + c->flags.cap + c->pstart.cap +
+                      c->f.cap + c->p.cap + c->t.cap + c->pair_res.cap + c->anc.cap + c->fp.cap + c->glist.cap + c->pflag.cap;
+    uint64_t a_max = (uint64_t)((free_b + reusable) * 0.7 / 56.0);
+    a_max = std::min<uint64_t>(a_max, (1ull << 31) - 1024);
+    if (c->max_anchors) a_max = std::min<uint64_t>(a_max, c->max_anchors);   // LRGE_MAX_ANCHORS: force small batches (tests)
+
+    // per-query sort kernel configuration
+    uint32_t r0 = 0, r1 = idx->n;
+    if (sharded_index) shard_range(idx->n, c->rank, world, &r0, &r1);
+    const uint32_t n_local = r1 - r0;
+    const int key_bits = bits_for(n_local ? n_local - 1 : 0) + 1 + PB;
+    const bool k32 = key_bits <= 32, two = c->map_ctas_per_sm == 2;          // 2 CTAs of 512 threads, else 1 CTA of 1024
+    const int NT = two ? 512 : 1024, NW = NT / 32;
+    const void *sort_fn = two ? (k32 ? (const void *)sort_query_kernel<uint32_t, 512, 2> : (const void *)sort_query_kernel<uint64_t, 512, 2>)
+                              : (k32 ? (const void *)sort_query_kernel<uint32_t, 1024, 1> : (const void *)sort_query_kernel<uint64_t, 1024, 1>);
+    uint32_t map_cap = 0;
+    size_t map_dyn = 0;
+    if (use_smem_sort) {
         cudaFuncAttributes fa{};
-        CUDA_CHECK(cudaFuncGetAttributes(&fa, fn));
+        CUDA_CHECK(cudaFuncGetAttributes(&fa, sort_fn));
         const size_t rec = (k32 ? 4 : 8) + 4;
-        size_t per_cta = (size_t)c->smem_optin;                                   // static + dynamic, one CTA per SM
-        if (c->map_ctas_per_sm == 2) per_cta = ((size_t)c->smem_optin + 1024) / 2 - 1024;
+        size_t per_cta = (size_t)c->smem_optin;                                // static + dynamic, one CTA per SM
+        if (two) per_cta = ((size_t)c->smem_optin + 1024) / 2 - 1024;
         const size_t fixed = fa.sharedSizeBytes + (size_t)NW * 512;
-        uint32_t cap = (uint32_t)std::min<size_t>((per_cta - fixed) / (2 * rec + 4), 65504) / 32 * 32;
-        if (c->map_cap) cap = std::max(64u, std::min(cap, c->map_cap) / 32 * 32);   // LRGE_MAP_CAP: force many rounds (tests)
-        map_cap = cap;
-        const size_t dyn = (size_t)cap * (2 * rec + 4) + (size_t)NW * 512;
-        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        h2d(c, c->qorder, str->len_order.data(), str->n);
+        map_cap = (uint32_t)std::min<size_t>((per_cta - fixed) / (2 * rec + 2), 65504) / 32 * 32;
+        if (c->map_cap) map_cap = std::max(64u, std::min(map_cap, c->map_cap) / 32 * 32);   // LRGE_MAP_CAP: force many rounds (tests)
+        map_dyn = (size_t)map_cap * (2 * rec + 2) + (size_t)NW * 512;
+        CUDA_CHECK(cudaFuncSetAttribute(sort_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)map_dyn));
         c->deferred.reserve(((size_t)str->n + 1) * 4);
         c->mapctr.reserve(64);
-        CUDA_CHECK(cudaMemsetAsync(c->mapctr.p, 0, 64, c->stream));
-        MapArgs A{};
-        A.qx = sq->x.as<uint64_t>(); A.qy = sq->y.as<uint64_t>(); A.moff = sq->moff.as<uint32_t>();
-        A.hstart = c->hstart.as<uint32_t>(); A.hn = c->hn.as<uint32_t>();
-        A.I = B.view; A.S = K; A.P = P;
-        A.O.counts = c->counts.as<uint32_t>(); A.O.had_mapping = c->had.as<uint8_t>();
-        A.O.len_q = K.len_q; A.O.len_t = K.len_t; A.O.rank_q = K.rank_q; A.O.rank_t = K.rank_t;
-        A.O.mode = mode; A.O.remove_internal = opts.remove_internal; A.O.ratio = opts.max_overhang_ratio; A.O.names_unique = 1;
-        if (want_regs) { A.O.regs = c->regs.as<RegOut>(); A.O.n_regs = ctr + 2; A.O.regs_cap = rq->cap; }
-        A.qorder = c->qorder.as<uint32_t>(); A.nq = str->n;
-        A.work_ctr = c->mapctr.as<uint32_t>(); A.n_deferred = c->mapctr.as<uint32_t>() + 1; A.deferred = c->deferred.as<uint32_t>();
-        A.cap = cap; A.PB = PB; A.key_bits = key_bits; A.rid_base = r0;
-        int hshift = 0;
-        while (n_local && ((n_local - 1) >> hshift) >= (uint32_t)MAP_BINS) ++hshift;
-        A.hshift = hshift;
-        A.max_span = o.is_hpc ? 255 : o.k;
-        A.stats = ctr + 3;
-        A.cyc = c->prof.kernels ? ctr + 10 : nullptr;                       // [10..14]: cycles per phase (profiling only)
-        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->n_sm * c->map_ctas_per_sm, std::max(str->n, 1u));
-        if (str->n && MQ) {
-            KLAUNCH(c, "map_query_kernel", 0.0, {
+        CUDA_CHECK(cudaMemsetAsync(c->mapctr.p, 0, 64, c->stream));     // [0] work counter (per batch) [1] deferred queries
+    }
+    const int min_viable = std::max({o.min_cnt, (o.min_chain_score + (o.is_hpc ? 255 : o.k) - 1) / (o.is_hpc ? 255 : o.k), 1});
+
+    CountOut O{};
+    O.counts = c->counts.as<uint32_t>(); O.had_mapping = c->had.as<uint8_t>();
+    O.len_q = K.len_q; O.len_t = K.len_t; O.rank_q = K.rank_q; O.rank_t = K.rank_t;
+    O.mode = mode; O.remove_internal = opts.remove_internal; O.ratio = opts.max_overhang_ratio;
+    O.names_unique = !host_dedupe;
+    if (want_regs) { O.regs = c->regs.as<RegOut>(); O.n_regs = ctr + 2; O.regs_cap = rq->cap; }
+
+    auto run_batch = [&](uint32_t q0, uint32_t q1, bool smem_sort) {
+        const uint64_t nA = qa[q1] - qa[q0];
+        if (nA > a_max) throw std::length_error("a single read yields more anchors than fit in device memory");
+        const int QB = bits_for(q1 - q0 - 1);
+        if (QB + RB + 1 + PB > 64) throw std::length_error("sort key does not fit 64 bits (too many reads x read length)");
+        if (!nA) return;
+        c->prof.sbegin(ST_SEED);
+        c->akey0.reserve(nA * 8); c->aval0.reserve(nA * 4);
+        const uint64_t m0 = moff_h[q0], m1 = moff_h[q1];
+        KeyLayout KL{PB, RB, r0};
+        // SURVEY.md 8(d) K4 without the probes (seed_lookup_kernel): hit lists 8H + anchors 16A
+        KLAUNCH(c, "anchor_fill_kernel", 8.0 * nA + 16.0 * nA, {
+            const unsigned fg = (unsigned)((m1 - m0 + 255) / 256);
+            if (!smem_sort)
+                anchor_fill_kernel<uint64_t, true><<<fg, 256, 0, c->stream>>>(
+                    sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
+                    c->aoff.as<uint64_t>(), m0, m1, qa[q0], q0, B.view, K, KL, c->akey0.as<uint64_t>(), c->aval0.as<uint32_t>());
+            else if (k32)
+                anchor_fill_kernel<uint32_t, false><<<fg, 256, 0, c->stream>>>(
+                    sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
+                    c->aoff.as<uint64_t>(), m0, m1, qa[q0], q0, B.view, K, KL, c->akey0.as<uint32_t>(), c->aval0.as<uint32_t>());
+            else
+                anchor_fill_kernel<uint64_t, false><<<fg, 256, 0, c->stream>>>(
+                    sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
+                    c->aoff.as<uint64_t>(), m0, m1, qa[q0], q0, B.view, K, KL, c->akey0.as<uint64_t>(), c->aval0.as<uint32_t>());
+        });
+        c->prof.send(ST_SEED);
+
+        c->prof.sbegin(ST_SORT);
+        // group descriptor lists, 4 size classes; a class holding groups of >= lb anchors has at most nA / lb entries
+        const uint32_t lb[4] = {2048, 256, 48, (uint32_t)min_viable};
+        GroupLists GL{};
+        size_t n_desc = 0;
+        for (int k = 0; k < 4; ++k) { GL.cap[k] = (uint32_t)(nA / lb[k] + 1); n_desc += GL.cap[k]; }
+        c->glist.reserve(n_desc * sizeof(GroupDesc));
+        { size_t off = 0; for (int k = 0; k < 4; ++k) { GL.gl[k] = c->glist.as<GroupDesc>() + off; off += GL.cap[k]; } }
+        c->gmeta.reserve(64);
+        c->pflag.reserve((n_desc + 1) * 4);
+        c->anc.reserve(nA * 8);
+        CUDA_CHECK(cudaMemsetAsync(c->gmeta.p, 0, 64, c->stream));          // [0..3] class counts [8] chain work counter [9] pair slots
+        CUDA_CHECK(cudaMemsetAsync(c->pflag.p, 0, (n_desc + 1) * 4, c->stream));
+        size_t tb = 0;
+        bool v1_done = false;
+        if (smem_sort) {
+            std::vector<uint32_t> order;
+            const uint32_t *order_p = str->len_order.data();
+            if (q0 != 0 || q1 != str->n) {
+                order.reserve(q1 - q0);
+                for (uint32_t q : str->len_order) if (q >= q0 && q < q1) order.push_back(q);
+                order_p = order.data();
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));               // `order` is a temporary: previous batch's copy must be done
+            }
+            h2d(c, c->qorder, order_p, q1 - q0);
+            if (order_p != str->len_order.data()) CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            CUDA_CHECK(cudaMemsetAsync(c->mapctr.p, 0, 4, c->stream));
+            SortArgs A{};
+            A.akey = c->akey0.p; A.aval = c->aval0.as<uint32_t>(); A.qaoff = c->qaoff.as<uint64_t>(); A.a_base = qa[q0];
+            A.qorder = c->qorder.as<uint32_t>(); A.nq = q1 - q0;
+            A.work_ctr = c->mapctr.as<uint32_t>(); A.n_deferred = c->mapctr.as<uint32_t>() + 1; A.deferred = c->deferred.as<uint32_t>();
+            A.cap = map_cap; A.PB = PB; A.key_bits = key_bits; A.rid_base = r0;
+            int hshift = 0;
+            while (n_local && ((n_local - 1) >> hshift) >= (uint32_t)MAP_BINS) ++hshift;
+            A.hshift = hshift;
+            A.max_span = o.is_hpc ? 255 : o.k; A.min_cnt = o.min_cnt; A.min_sc = o.min_chain_score;
+            A.anc = c->anc.as<uint2>(); A.L = GL; A.gcount = c->gmeta.as<uint32_t>(); A.pair_ctr = c->gmeta.as<uint32_t>() + 9;
+            A.stats = ctr + 3;
+            A.cyc = c->prof.kernels ? ctr + 10 : nullptr;                   // [10..14]: cycles per phase (profiling only)
+            const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c->n_sm * (two ? 2 : 1), q1 - q0);
+            // one read + one write of the 16-byte anchor records
+            KLAUNCH(c, "sort_query_kernel", 32.0 * nA, {
                 if (two) {
-                    if (k32) map_query_kernel<uint32_t, 512, 2><<<grid, 512, dyn, c->stream>>>(A);
-                    else map_query_kernel<uint64_t, 512, 2><<<grid, 512, dyn, c->stream>>>(A);
+                    if (k32) sort_query_kernel<uint32_t, 512, 2><<<grid, 512, map_dyn, c->stream>>>(A);
+                    else sort_query_kernel<uint64_t, 512, 2><<<grid, 512, map_dyn, c->stream>>>(A);
                 } else {
-                    if (k32) map_query_kernel<uint32_t, 1024, 1><<<grid, 1024, dyn, c->stream>>>(A);
-                    else map_query_kernel<uint64_t, 1024, 1><<<grid, 1024, dyn, c->stream>>>(A);
+                    if (k32) sort_query_kernel<uint32_t, 1024, 1><<<grid, 1024, map_dyn, c->stream>>>(A);
+                    else sort_query_kernel<uint64_t, 1024, 1><<<grid, 1024, map_dyn, c->stream>>>(A);
                 }
             });
+            CUDA_CHECK(cudaGetLastError());
+        } else {
+            c->akey1.reserve(nA * 8); c->aval1.reserve(nA * 4);
+            const int sort_bits = QB + RB + 1 + PB;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
+                                            c->aval1.as<uint32_t>(), (int64_t)nA, 0, sort_bits, c->stream);
+            KLAUNCH(c, "cub::DeviceRadixSort(anchors: u64 key, u32 value)", 32.0 * nA,
+                    cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->akey0.as<uint64_t>(), c->akey1.as<uint64_t>(), c->aval0.as<uint32_t>(),
+                                                    c->aval1.as<uint32_t>(), (int64_t)nA, 0, sort_bits, c->stream));
+            c->prof.set_passes("cub::DeviceRadixSort(anchors: u64 key, u32 value)", (sort_bits + 7) / 8);
+            c->launches += (sort_bits + 7) / 8;
+            c->flags.reserve(nA + 1);
+            c->npairs.reserve(16);
+#ifdef LRGE_TEST_KERNELS
+            if (c->chain_v1) {
+                v1_done = true;
+                // ---- v1 (debug cross-check, LRGE_CHAIN_V1=1): one thread per (query, target) pair ----
+                c->pstart.reserve((nA + 2) * 4);
+                KLAUNCH(c, "pair_flag_kernel", 9.0 * nA,
+                        pair_flag_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), nA, PB + 1, c->flags.as<uint8_t>()));
+                cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
+                                           c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+                cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                           c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+                c->launches += 2;
+                uint32_t n_pairs = 0;
+                CUDA_CHECK(cudaMemcpyAsync(&n_pairs, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                const uint32_t sentinel = (uint32_t)nA;
+                CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_pairs, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
+                S.n_pairs += n_pairs;
+                c->f.reserve(nA * 4); c->p.reserve(nA * 4); c->t.reserve(nA * 4);
+                c->pair_res.reserve((size_t)n_pairs + 1);
+                CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
+                PairTask T{};
+                T.akey = c->akey1.as<uint64_t>(); T.aval = c->aval1.as<uint32_t>(); T.pstart = c->pstart.as<uint32_t>();
+                T.n_pairs = n_pairs; T.PB = PB; T.RB = RB; T.q0 = q0;
+                T.f = c->f.as<int32_t>(); T.p = c->p.as<int32_t>(); T.t = c->t.as<int32_t>();
+                O.pair_res = c->pair_res.as<uint8_t>();
+                KLAUNCH(c, "chain_pair_kernel", 16.0 * nA + 4.0 * str->n, chain_pair_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(T, P, O));
+                CUDA_CHECK(cudaGetLastError());
+                if (host_dedupe) {
+                    std::vector<uint8_t> res(n_pairs);
+                    std::vector<uint32_t> ps((size_t)n_pairs + 1);
+                    std::vector<uint64_t> keys(nA);
+                    CUDA_CHECK(cudaMemcpyAsync(res.data(), c->pair_res.p, n_pairs, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaMemcpyAsync(ps.data(), c->pstart.p, ((size_t)n_pairs + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaMemcpyAsync(keys.data(), c->akey1.p, nA * 8, cudaMemcpyDeviceToHost, c->stream));
+                    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                    for (uint32_t i = 0; i < n_pairs; ++i) if (res[i] & 2) {
+                        const uint64_t kk = keys[ps[i]];
+                        const uint32_t rid = (uint32_t)((kk >> (PB + 1)) & ((1ull << RB) - 1)), qid = q0 + (uint32_t)(kk >> (PB + 1 + RB));
+                        dedupe_sets[qid].push_back(rank_idx[rid]);
+                    }
+                }
+            }
+#endif
+            if (!v1_done) {
+                c->pstart.reserve((nA + 2) * 4);
+                KLAUNCH(c, "group_mark_kernel", 21.0 * nA,
+                        group_mark_kernel<<<(unsigned)((nA + 255) / 256), 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), c->aval1.as<uint32_t>(), nA, PB,
+                                                                                               c->anc.as<uint2>(), c->flags.as<uint8_t>()));
+                cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
+                                           c->npairs.as<uint32_t>(), (int64_t)nA, c->stream);
+                KLAUNCH(c, "cub::DeviceSelect(group starts)", 1.0 * nA,
+                        cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                                   c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)nA, c->stream));
+                uint32_t n_groups = 0;
+                CUDA_CHECK(cudaMemcpyAsync(&n_groups, c->npairs.p, 4, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaStreamSynchronize(c->stream));
+                const uint32_t sentinel = (uint32_t)nA;
+                CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_groups, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
+                if ((size_t)n_groups + 1 > n_desc) { c->pflag.reserve(((size_t)n_groups + 2) * 4); CUDA_CHECK(cudaMemsetAsync(c->pflag.p, 0, ((size_t)n_groups + 2) * 4, c->stream)); }
+                KLAUNCH(c, "group_classify_kernel", 8.0 * n_groups,
+                        group_classify_kernel<<<(n_groups + 255) / 256, 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), c->pstart.as<uint32_t>(), n_groups, PB, RB,
+                                                                                            q0, P.min_cnt, P.min_sc, o.is_hpc ? 255 : o.k, GL,
+                                                                                            c->gmeta.as<uint32_t>()));
+                S.n_pairs += n_groups;
+            }
         }
+        c->prof.send(ST_SORT);
+        if (v1_done) return;
+
+        // ---- K6: one warp per (query, target, strand) group, persistent CTAs, largest groups first -------------------
+        c->prof.sbegin(ST_CHAIN);
+        c->fp.reserve(nA * 8); c->t.reserve(nA * 4);
+        CUDA_CHECK(cudaMemsetAsync(c->t.p, 0, nA * 4, c->stream));
+        GroupTask T{};
+        T.anc = c->anc.as<uint2>();
+        for (int k = 0; k < 4; ++k) T.gl[k] = GL.gl[k];
+        T.gcount = c->gmeta.as<uint32_t>(); T.work_ctr = c->gmeta.as<uint32_t>() + 8;
+        T.fp = c->fp.as<int2>(); T.t = c->t.as<int32_t>(); T.pflag = c->pflag.as<uint32_t>();
+        if (host_dedupe) {
+            c->ddbuf.reserve((n_desc + 1) * 8);
+            CUDA_CHECK(cudaMemsetAsync(ctr + 9, 0, 8, c->stream));
+            T.dd_out = c->ddbuf.as<uint2>(); T.dd_n = ctr + 9;
+        }
+        KLAUNCH(c, "chain_group_kernel", 16.0 * nA + 4.0 * (q1 - q0),
+                chain_group_kernel<<<c->n_sm * (2048 / CG_THREADS), CG_THREADS, 0, c->stream>>>(T, P, O));
         CUDA_CHECK(cudaGetLastError());
+        if (host_dedupe) {                                                   // passing (query, target) pairs -> HashSet<name> per query
+            unsigned long long n_dd = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&n_dd, ctr + 9, 8, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            std::vector<uint2> dd(n_dd);
+            if (n_dd) CUDA_CHECK(cudaMemcpyAsync(dd.data(), c->ddbuf.p, n_dd * 8, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            for (const uint2 &e : dd) dedupe_sets[e.x].push_back(rank_idx[e.y]);
+        }
         c->prof.send(ST_CHAIN);
     };
+
+    {
+        uint32_t q0 = 0;
+        while (q0 < str->n) {
+            uint32_t q1 = q0 + 1;
+            while (q1 < str->n && qa[q1 + 1] - qa[q0] <= a_max) ++q1;
+            if (qa[q1] > qa[q0]) ++S.n_batches;
+            run_batch(q0, q1, use_smem_sort);
+            q0 = q1;
+        }
+    }
+    // queries the per-query kernel could not plan (one target bin above the smem capacity): device-wide sort, one per batch
     std::vector<uint32_t> deferred;
-    uint32_t mapctr_h[2] = {0, 0};
-    auto fetch_deferred = [&]() {                                        // mapctr_h already on the host
+    if (use_smem_sort && str->n && MQ) {
+        uint32_t mapctr_h[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(mapctr_h, c->mapctr.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
         deferred.resize(mapctr_h[1]);
         if (mapctr_h[1]) {
             CUDA_CHECK(cudaMemcpyAsync(deferred.data(), c->deferred.p, (size_t)mapctr_h[1] * 4, cudaMemcpyDeviceToHost, c->stream));
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
             std::sort(deferred.begin(), deferred.end());
+            for (uint32_t q : deferred) { ++S.n_batches; run_batch(q, q + 1, false); }
         }
-    };
-    if (use_fused) {
-        fused_path();
-        if (sharded_index) {                                              // the count reduction must see the deferred queries
-            CUDA_CHECK(cudaMemcpyAsync(mapctr_h, c->mapctr.p, 8, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            fetch_deferred();
-            if (!deferred.empty()) global_path(&deferred);
-        }
-    } else global_path(nullptr);
+    }
 
     // one exchange on the query path: sum the per-read counts of all target shards over NVLink
     if (sharded_index) {
@@ -1151,17 +1165,10 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         if (n_counts) CUDA_CHECK(cudaMemcpyAsync(counts.data(), c->counts.p, (size_t)n_counts * 4, cudaMemcpyDeviceToHost, c->stream));
         if (str->n) CUDA_CHECK(cudaMemcpyAsync(had.data(), c->had.p, str->n, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaMemcpyAsync(ctr_h, ctr, 128, cudaMemcpyDeviceToHost, c->stream));
-        if (use_fused && !sharded_index) CUDA_CHECK(cudaMemcpyAsync(mapctr_h, c->mapctr.p, 8, cudaMemcpyDeviceToHost, c->stream));
         c->prof.send(ST_D2H);
     };
     fetch_results();
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (use_fused && !sharded_index && mapctr_h[1]) {                    // rare: queries the fused kernel could not plan
-        fetch_deferred();
-        global_path(&deferred);
-        fetch_results();
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    }
     if (want_regs) {
 #ifdef LRGE_TEST_KERNELS
         if (c->chain_v1) throw std::runtime_error("overlap records need the warp-per-group kernel (unset LRGE_CHAIN_V1)");
@@ -1172,15 +1179,13 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     }
     c->prof.send(ST_TOTAL);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (use_fused) {
-        if (ctr_h[6]) throw std::runtime_error("internal: a round of the fused map kernel exceeded its shared-memory capacity");
-        S.n_anchors += ctr_h[3]; S.n_pairs += ctr_h[4]; S.n_batches += (uint32_t)ctr_h[5];
+    if (use_smem_sort) {
+        if (ctr_h[6]) throw std::runtime_error("internal: the per-query sort kernel exceeded a capacity it had planned for");
+        S.n_pairs += ctr_h[4]; S.n_rounds = (uint32_t)ctr_h[5];
         S.n_deferred = (uint32_t)deferred.size();
-        // SURVEY.md 8(d) bytes of the fused stages: K4 hit lists + anchors (8H + 16A), K5 (2*16*A), K6 (16A + 8C + 4NQ)
-        c->prof.set_bytes("map_query_kernel", 8.0 * ctr_h[1] + 64.0 * ctr_h[3] + 4.0 * str->n);
-        if (c->prof.kernels && ctr_h[14]) {                                // phase shares of the fused kernel (SM cycles)
+        if (c->prof.kernels && ctr_h[14]) {                                // phase shares of the per-query sort kernel (SM cycles)
             const double tot = (double)ctr_h[14];
-            fprintf(stderr, "[lrge] map_query_kernel phases: plan %.3f expand %.3f sort %.3f chain %.3f (of CTA lifetime), rounds %llu\n",
+            fprintf(stderr, "[lrge] sort_query_kernel phases: plan %.3f stage %.3f sort %.3f groups %.3f (of CTA lifetime), rounds %llu\n",
                     ctr_h[10] / tot, ctr_h[11] / tot, ctr_h[12] / tot, ctr_h[13] / tot, (unsigned long long)ctr_h[5]);
         }
     }
@@ -1431,6 +1436,7 @@ int lrge_gpu_kernel_times(lrge_ctx *ctx, lrge_kernel_time *out, int cap) {
         out[i].ms = ctx->prof.ms[ST_COUNT + i];
         out[i].algorithmic_bytes = ctx->prof.bytes[ST_COUNT + i];
         out[i].launches = ctx->prof.count[ST_COUNT + i];
+        out[i].passes = ctx->prof.passes[ST_COUNT + i];
     }
     return n;
 }

@@ -361,8 +361,8 @@ def _ctx_with(monkeypatch, **env):
 
 @pytest.mark.parametrize("platform", ["ont", "pb"])
 def test_global_path_parity(ctx, monkeypatch, platform):
-    """LRGE_FORCE_GLOBAL=1 sends every query through the global-memory pipeline (device-wide sort, warp per group):
-    counts, had_mapping, anchor totals and overlap records must equal the fused path's and the oracle's."""
+    """LRGE_FORCE_GLOBAL=1 replaces the per-query shared-memory sort by the device-wide radix sort + group kernels:
+    counts, had_mapping, anchor totals and overlap records must equal the default path's and the oracle's."""
     T, Q = small_sets(nt=300, nq=120, mean=4000, gsize=250_000, err=readsim.ONT if platform == "ont" else readsim.HIFI)
     want, had, st = oracle.twoset_counts(T, Q, platform, threads=8)
     a = ctx.twoset_counts(T, Q, platform)
@@ -387,9 +387,9 @@ def test_global_path_parity(ctx, monkeypatch, platform):
 
 @pytest.mark.parametrize("cap", [2048, 256])
 def test_fused_rounds_and_deferral(ctx, monkeypatch, cap):
-    """LRGE_MAP_CAP shrinks the shared-memory capacity of the fused kernel: queries are mapped in several rounds over
-    disjoint target ranges, and a query holding one (query, target) bin above the capacity is deferred to the global
-    path.  Results must not change."""
+    """LRGE_MAP_CAP shrinks the shared-memory capacity of the per-query sort kernel: queries are sorted in several rounds
+    over disjoint target ranges, and a query holding one target bin above the capacity is deferred to the device-wide
+    sort.  Results must not change."""
     T, Q = small_sets()
     want, had, st = oracle.twoset_counts(T, Q, "ont", threads=8)
     g = readsim.genome(200_000)
@@ -406,7 +406,7 @@ def test_fused_rounds_and_deferral(ctx, monkeypatch, cap):
         c1.close()
     assert np.array_equal(b.counts, want) and np.array_equal(b.had_mapping, had)
     assert b.stats["n_anchors"] == st["n_anchors"]
-    assert b.stats["n_batches"] > Q.n                       # several rounds per query
+    assert b.stats["n_rounds"] > Q.n                        # several rounds per query
     if cap == 256:
         assert b.stats["n_deferred"] > 0                    # 4 kb overlaps hold > 256 anchors of one target
     else:
