@@ -337,6 +337,188 @@ __global__ void __launch_bounds__(SK_THREADS) sketch_kernel(SketchArgs A) {
     }
 }
 
+// ---- K1, lane-serial form (no HPC, 2k <= 32) ---------------------------------------------------------------------------
+// Replaces pack_kernel + sketch_kernel<stage> for ava-ont:
+//   * the CTA stages the raw ASCII bases of its tile (8 192 steps of one read, 32 bases of history in front) with one TMA
+//     bulk copy (cp.async.bulk, 16-byte aligned source) -- no packed copy of the reads in HBM;
+//   * every lane runs mm_sketch's state machine SEQUENTIALLY over 32 consecutive steps, after a warm-up of w + k steps:
+//     rolling forward / reverse k-mers, hash, the w + 1 most recent infos in registers, m[t-1] carried over from the
+//     previous step.  The push rules are the ones of sketch_kernel above, evaluated on registers instead of warp
+//     shuffles (3x fewer instructions per base);
+//   * pushes are recorded as a bit mask over the positions [first step - w, first step + 32): mm_sketch pushes in
+//     ascending position and never twice ("these two loops make sure the output is sorted", sketch.c), so the mask IS
+//     the output order; the infos of those positions sit in shared memory for the emission;
+//   * output goes to the per-sub-tile staging slots of the single-pass path (SK_CAP minimizers per 1 024 steps, wcnt[]),
+//     which compact_kernel packs.  (An ordered single-kernel variant with a decoupled look-back over the tiles was
+//     measured slower: tiles of one read set differ in length, and every tile waits for its predecessors.)
+constexpr int SK2_S = 32;                         // steps per lane
+constexpr int SK2_HALO = 32;                      // history staged in front of a tile (>= w + k)
+constexpr int SK2_STRIDE = SK2_S + MAXW;          // infos kept per lane (odd: conflict-free)
+constexpr int SK2_RAW = TILE_POS + SK2_HALO + 32; // staged ASCII bytes incl. alignment slack
+
+struct Sketch2Args {
+    const uint8_t *asc;        // ASCII bases of the resident reads
+    const uint64_t *off;       // start of each entry in asc
+    const uint32_t *len;       // length of each entry
+    const uint32_t *rid_map;   // read id of each entry (NULL: entry index)
+    const uint32_t *tile_off;  // n + 1: tiles before entry r
+    const uint32_t *tile_read; // entry of each tile
+    uint32_t tile0;            // first tile of this launch (one launch per staged chunk)
+    uint64_t *ox, *oy;         // staging slots: SK_CAP entries per warp sub-tile
+    uint32_t *wcnt;            // minimizers per warp sub-tile
+    uint32_t *overflow;        // set when a sub-tile does not fit its slot
+};
+
+// ASCII base -> 0..3, or 4 for anything that is not ACGTU in either case (the seq_nt4_table of minimap2), without a
+// table lookup: (b >> 1) & 3 maps A C G T/U to 0 1 3 2, the xor swaps 2 and 3; valid letters are 0x40-0x7f with
+// (b & 31) in {1, 3, 7, 20, 21}.
+__device__ __forceinline__ uint32_t nt4_code(uint32_t b) {
+    const uint32_t c = (b >> 1) & 3u;
+    const bool ok = (b & 0xc0u) == 0x40u && ((0x0030008au >> (b & 31u)) & 1u);
+    return ok ? (c ^ (c >> 1)) : b < 4u ? b : 4u;                       // bytes 0..3 are accepted as codes, like the table
+}
+
+template <int K>
+__global__ void __launch_bounds__(SK_THREADS) sketch2_kernel(Sketch2Args A) {
+    constexpr int W = MAXW;
+    static_assert(2 * K <= 32 && (K & 1), "32-bit k-mers, odd k");
+    static_assert(SK2_HALO >= W + K, "history");
+    constexpr uint32_t KMASK = 2 * K == 32 ? 0xffffffffu : ((1u << (2 * K)) - 1);
+    constexpr uint32_t XMAX = 0xffffffffu;
+    __shared__ alignas(16) uint8_t sRaw[SK2_RAW];                        // the tile's ASCII bases (+ history, + alignment slack)
+    __shared__ uint32_t sInfo[SK_THREADS * SK2_STRIDE];                  // infos of every lane's steps, for the emission
+    __shared__ alignas(8) uint64_t bar;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const uint32_t tile = A.tile0 + blockIdx.x, r = A.tile_read[tile];
+    const int32_t len = (int32_t)A.len[r];
+    const int32_t s = (int32_t)(tile - A.tile_off[r]) * TILE_POS;       // first step of the tile; < len unless len == 0
+    const uint32_t rid = A.rid_map ? A.rid_map[r] : r;
+    const int32_t halo = s ? SK2_HALO : 0;
+    const int32_t nb = max(0, min(TILE_POS, len - s)) + halo;            // staged steps: [s - halo, s - halo + nb)
+    const uint8_t *src = A.asc + A.off[r] + s - halo;
+    const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+    if (tid == 0 && nb > 0) {
+        const uint32_t bytes = (shift + (uint32_t)nb + 15u) & ~15u;
+        mbar_expect_tx(&bar, bytes);
+        tma_load_1d(sRaw, src - shift, bytes, &bar);
+    }
+    if (nb > 0) mbar_wait(&bar, 0);
+
+    // ---- lane-serial state machine, straight from the staged bytes -----------------------------------------------------
+    const int32_t seg = s + (int32_t)(warp * WARP_POS + lane * SK2_S);     // first step of this lane
+    uint64_t pm = 0, zm = 0;                                               // pushed positions / strands, bit i = step seg - W + i
+    uint32_t *myInfo = sInfo + tid * SK2_STRIDE;
+    if (seg < len) {
+        const uint8_t *base = sRaw + shift + (seg - (s - halo));           // byte of step seg
+        uint32_t fwd = 0, rev = 0;
+        int32_t l = 0;
+        uint32_t xs[W + 1];
+#pragma unroll
+        for (int d = 0; d <= W; ++d) xs[d] = XMAX;
+        uint32_t zwarm = 0, zcur = 0;
+        // warm-up: the W + K steps before seg (ambiguous where the read has not started)
+        const bool have_prev = seg - (W + K) >= s - halo;                  // false only at the start of a read
+#pragma unroll
+        for (int i = -(W + K); i < 0; ++i) {
+            const uint32_t c = have_prev ? nt4_code(base[i]) : 4u;
+            fwd = ((fwd << 2) | (c & 3u)) & KMASK;
+            rev = (rev >> 2) | ((3u - (c & 3u)) << (2 * (K - 1)));
+            l = c > 3u ? 0 : l + 1;
+            if (i >= -W) {                                                 // infos of steps seg - W .. seg - 1
+                uint32_t x = XMAX;
+                if (l >= K) {
+                    const uint32_t z = fwd < rev ? 0u : 1u;
+                    x = hash32_masked(z ? rev : fwd, KMASK);
+                    zwarm |= z << (i + W);
+                }
+                myInfo[i + W] = x;
+#pragma unroll
+                for (int d = W; d >= 1; --d) xs[d] = xs[d - 1];
+                xs[0] = x;
+            }
+        }
+        // m[t-1] for t = seg: rightmost minimum of steps seg - W .. seg - 1 (xs[W-1] .. xs[0] before t enters)
+        uint32_t xm1 = xs[W - 1];
+        int dm1 = W;
+#pragma unroll
+        for (int d = W - 1; d >= 1; --d) if (xs[d - 1] <= xm1) { xm1 = xs[d - 1]; dm1 = d; }
+        const int32_t n_steps = min(SK2_S, len - seg);
+#pragma unroll 4
+        for (int i = 0; i < SK2_S; ++i) {
+            if (i >= n_steps) break;
+            const uint32_t c = nt4_code(base[i]);
+            fwd = ((fwd << 2) | (c & 3u)) & KMASK;
+            rev = (rev >> 2) | ((3u - (c & 3u)) << (2 * (K - 1)));
+            l = c > 3u ? 0 : min(l + 1, W + K);
+            uint32_t x = XMAX;
+            if (l >= K) {
+                const uint32_t z = fwd < rev ? 0u : 1u;
+                x = hash32_masked(z ? rev : fwd, KMASK);
+                zcur |= z << i;
+            }
+            myInfo[i + W] = x;
+#pragma unroll
+            for (int d = W; d >= 1; --d) xs[d] = xs[d - 1];
+            xs[0] = x;
+            // m[t]: rightmost minimum of steps t-W+1 .. t
+            uint32_t xm = xs[W - 1]; int dm = W - 1;
+#pragma unroll
+            for (int d = W - 2; d >= 0; --d) if (xs[d] <= xm) { xm = xs[d]; dm = d; }
+            // pushes of this step as a mask over d: bit (W - d) = step t - d; OR-ed into pm at bit i (= step seg - W + i)
+            uint32_t m = 0;
+            const bool full1 = l >= W + K - 1;
+            if (l == W + K - 1 && xm1 != XMAX) {                           // first full window: ties of the old minimum
+#pragma unroll
+                for (int d = W - 1; d >= 1; --d) m |= (uint32_t)(xs[d] == xm1) << (W - d);
+                m &= ~(1u << (W - dm1));
+            }
+            if (x <= xm1) {                                                // new minimum replaces the old one
+                if (l >= W + K && xm1 != XMAX) m |= 1u << (W - dm1);
+            } else if (dm1 == W) {                                         // old minimum left the window
+                if (full1 && xm1 != XMAX) m |= 1u;
+                if (full1 && xm != XMAX) {
+                    uint32_t ties = 0;
+#pragma unroll
+                    for (int d = W - 1; d >= 0; --d) ties |= (uint32_t)(xs[d] == xm) << (W - d);
+                    m |= ties & ~(1u << (W - dm));
+                }
+            }
+            if (seg + i == len - 1 && xm != XMAX) m |= 1u << (W - dm);     // final flush
+            pm |= (uint64_t)m << i;
+            xm1 = xm; dm1 = dm + 1;                                        // m[t] is m[t-1] of the next step
+        }
+        zm = (uint64_t)zwarm | (uint64_t)zcur << W;
+    }
+    // ---- emission into the sub-tile's staging slot: ascending position = mm_sketch's push order ----------------------
+    const uint32_t cnt = (uint32_t)__popcll(pm);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += u; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t sub = tile * (SK_THREADS / 32) + warp;
+    if (lane == 0) {
+        A.wcnt[sub] = total;
+        if (total > SK_CAP) *A.overflow = 1;
+    }
+    uint32_t o = incl - cnt;
+    uint64_t *ox = A.ox + (uint64_t)sub * SK_CAP, *oy = A.oy + (uint64_t)sub * SK_CAP;
+    while (pm && o < SK_CAP) {
+        const int b = __ffsll((long long)pm) - 1;
+        pm &= pm - 1;
+        const uint32_t x = myInfo[b];
+        const uint64_t z = (zm >> b) & 1ull;
+        const uint64_t pos = (uint64_t)(seg - W + b);
+        ox[o] = (uint64_t)x << 8 | (uint64_t)K;
+        oy[o] = (uint64_t)rid << 32 | pos << 1 | z;
+        ++o;
+    }
+}
+
 // MODE 2 follow-up: pack the staging slots into the contiguous (rid, position)-ordered arrays. One warp per sub-tile.
 __global__ void __launch_bounds__(256) compact_kernel(const uint64_t *__restrict__ sx, const uint64_t *__restrict__ sy,
                                                       const uint32_t *__restrict__ wcnt, const uint32_t *__restrict__ woff, uint32_t nw,

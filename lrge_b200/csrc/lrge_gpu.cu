@@ -145,6 +145,10 @@ struct Prof {
         if (!kernels || open_kernel < 0) return;
         cudaEvent_t b = get(); cudaEventRecord(b, s); spans.push_back({open_kernel, open_ev, b}); open_kernel = -1;
     }
+    void set_bytes(const char *name, double nbytes, bool add) {   // algorithmic bytes known only after the launch
+        if (!kernels) return;
+        for (size_t i = 0; i < names.size(); ++i) if (names[i] == name) bytes[ST_COUNT + i] = (add ? bytes[ST_COUNT + i] : 0.0) + nbytes;
+    }
     void set_passes(const char *name, uint32_t n) {    // a library radix sort: passes over the data inside one "launch"
         if (!kernels) return;
         for (size_t i = 0; i < names.size(); ++i) if (names[i] == name) passes[ST_COUNT + i] = n;
@@ -178,13 +182,18 @@ struct lrge_staged {
     std::vector<uint32_t> len_order;                       // reads, longest first (work order of the fused map kernel)
     cudaEvent_t ready = nullptr;                           // async staging: recorded on the copy stream after the H2D copies
     bool pending = false;
-    ~lrge_staged() { if (ready) cudaEventDestroy(ready); }
+    // async staging copies the block in chunks of whole reads, one event each, so that the sketch of chunk i overlaps the
+    // copy of chunk i + 1: chunk j = reads [chunk_hi[j-1], chunk_hi[j]) (absolute read ids)
+    std::vector<uint32_t> chunk_hi;
+    std::vector<cudaEvent_t> chunk_ev;
+    ~lrge_staged() { if (ready) cudaEventDestroy(ready); for (auto e : chunk_ev) cudaEventDestroy(e); }
 };
 
 struct Sketch {                            // minimizers of a read set, (rid, position) order
     DevBuf x, y, moff;                     // moff: n+1 u32 per-read offsets
     uint64_t M = 0;
 };
+
 
 struct lrge_ctx {
     int device = 0;
@@ -214,6 +223,8 @@ struct lrge_ctx {
     DevBuf qorder, deferred, mapctr, ddbuf;
     uint64_t max_anchors = 0;              // LRGE_MAX_ANCHORS=n: cap anchors per query batch
     bool sketch_two_pass = false;          // LRGE_SKETCH_TWO_PASS=1: count + emit instead of stage + compact
+    bool sketch_legacy = false;            // LRGE_SKETCH_LEGACY=1: pack + warp-shuffle sketch + compact instead of the lane-serial kernel
+    DevBuf tile_read;                      // lane-serial sketch: tile -> entry
     size_t free_at_create = 0, held_at_create = 0;
     DevBuf stg_x, stg_y, xflag;
     lrge_staged tmp_a, tmp_b;              // device staging of the host-buffer entry points (reused across calls)
@@ -260,10 +271,31 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool asy
     s->blk_first = blk_first; s->blk_count = blk_count;
     const uint64_t b0 = rs->n ? rs->off[blk_first] : 0, b1 = rs->n ? rs->off[blk_first + blk_count] : 0;
     s->blk_base = rs->n ? b0 - rs->off[0] : 0;
-    // start the big copy first; the host-side bookkeeping below overlaps with it
+    // start the copies first; the host-side bookkeeping below overlaps with them
     s->asc.reserve((b1 - b0) + 64);
-    if (b1 > b0)
-        CUDA_CHECK(cudaMemcpyAsync(s->asc.p, rs->bases + b0, b1 - b0, cudaMemcpyHostToDevice, c->copy_stream));
+    s->chunk_hi.clear();
+    if (b1 > b0) {
+        const uint64_t min_chunk = 8ull << 20;
+        const uint32_t n_chunks = async ? (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, (b1 - b0) / min_chunk)) : 1;
+        uint32_t lo = blk_first;
+        for (uint32_t j = 0; j < n_chunks && lo < blk_first + blk_count; ++j) {
+            uint32_t hi = blk_first + blk_count;
+            if (j + 1 < n_chunks) {
+                const uint64_t want = b0 + (b1 - b0) * (j + 1) / n_chunks;
+                hi = (uint32_t)(std::upper_bound(rs->off + lo + 1, rs->off + blk_first + blk_count, want) - rs->off);
+                hi = std::min(hi, blk_first + blk_count);
+            }
+            if (hi <= lo) continue;
+            CUDA_CHECK(cudaMemcpyAsync(s->asc.as<uint8_t>() + (rs->off[lo] - b0), rs->bases + rs->off[lo], rs->off[hi] - rs->off[lo],
+                                       cudaMemcpyHostToDevice, c->copy_stream));
+            if (async) {
+                if (s->chunk_ev.size() <= s->chunk_hi.size()) { cudaEvent_t e; CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); s->chunk_ev.push_back(e); }
+                CUDA_CHECK(cudaEventRecord(s->chunk_ev[s->chunk_hi.size()], c->copy_stream));
+            }
+            s->chunk_hi.push_back(hi);
+            lo = hi;
+        }
+    }
     s->h_off.assign(rs->off, rs->off + rs->n + 1);
     if (rs->n && rs->off[0] != 0) {
         const uint64_t b = rs->off[0];
@@ -318,12 +350,102 @@ __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32
     if (i < n) dst[i] = src[idx[i]];
 }
 
+// K1, lane-serial form (kernels_sketch.cuh: sketch2_kernel): ava-ont only (no HPC, k = 15).  One launch per staged
+// chunk straight from the ASCII bases (no pack kernel), staging slots + compact_kernel as in the single-pass path.
+// Returns false if a sub-tile overflowed its slot (very dense reads): the caller falls back to the exact two-pass path.
+bool sketch_readset2(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first, uint32_t count) {
+    const uint32_t n = count;
+    std::vector<uint64_t> soff(n);
+    std::vector<uint32_t> tile_off((size_t)n + 1), slen(n), rid_map(n);
+    uint32_t tiles = 0;
+    uint64_t nbases = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t r = first + i;
+        tile_off[i] = tiles;
+        soff[i] = s->h_off[r] - s->blk_base;
+        slen[i] = s->h_len[r];
+        rid_map[i] = r;
+        nbases += s->h_len[r];
+        tiles += (s->h_len[r] + TILE_POS - 1) / TILE_POS;
+    }
+    tile_off[n] = tiles;
+    std::vector<uint32_t> tile_read(tiles);
+    for (uint32_t i = 0; i < n; ++i) for (uint32_t t = tile_off[i]; t < tile_off[i + 1]; ++t) tile_read[t] = i;
+    const bool subset = first != 0 || count != s->n;
+    const uint32_t nw = tiles * (SK_THREADS / 32);
+    const uint64_t stage_bytes = (uint64_t)nw * SK_CAP * 16;
+    if (stage_bytes > (8ull << 30) || stage_bytes > (free_estimate(c) + c->stg_x.cap + c->stg_y.cap) / 4) return false;
+    c->prof.sbegin(ST_SKETCH);
+    h2d(c, c->tile_off, tile_off.data(), (size_t)n + 1);
+    h2d(c, c->tile_read, tile_read.data(), tiles);
+    h2d(c, c->sub_off, soff.data(), n);
+    h2d(c, c->len0, slen.data(), n);
+    if (subset) h2d(c, c->rid_map, rid_map.data(), n);
+    out->moff.reserve(((size_t)n + 1) * 4);
+    out->M = 0;
+    c->wcnt.reserve(((size_t)nw + 1) * 4);
+    c->woff.reserve(((size_t)nw + 1) * 4);
+    if (tiles == 0) { CUDA_CHECK(cudaMemsetAsync(out->moff.p, 0, ((size_t)n + 1) * 4, c->stream)); c->prof.send(ST_SKETCH); return true; }
+    c->stg_x.reserve(stage_bytes / 2 + 64); c->stg_y.reserve(stage_bytes / 2 + 64);
+    c->xflag.reserve(16);
+    CUDA_CHECK(cudaMemsetAsync(c->xflag.p, 0, 16, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->wcnt.as<uint32_t>() + nw, 0, 4, c->stream));
+    Sketch2Args A{};
+    A.asc = s->asc.as<uint8_t>(); A.off = c->sub_off.as<uint64_t>(); A.len = c->len0.as<uint32_t>();
+    A.rid_map = subset ? c->rid_map.as<uint32_t>() : nullptr; A.tile_off = c->tile_off.as<uint32_t>();
+    A.tile_read = c->tile_read.as<uint32_t>();
+    A.ox = c->stg_x.as<uint64_t>(); A.oy = c->stg_y.as<uint64_t>(); A.wcnt = c->wcnt.as<uint32_t>(); A.overflow = c->xflag.as<uint32_t>();
+    KLAUNCH(c, "sketch2_kernel", (double)nbases / 4 + 16.0 * nbases / 3, {     // SURVEY.md 8(d) K1 (M ~ bases / 3 at launch time)
+        if (s->pending && !s->chunk_hi.empty()) {
+            // one launch per staged chunk, each waiting only for its own copy
+            uint32_t lo = first;
+            for (size_t j = 0; j < s->chunk_hi.size() && lo < first + count; ++j) {
+                const uint32_t hi = std::min(s->chunk_hi[j], first + count);
+                CUDA_CHECK(cudaStreamWaitEvent(c->stream, s->chunk_ev[j], 0));
+                if (hi <= lo) continue;
+                A.tile0 = tile_off[lo - first];
+                const uint32_t t = tile_off[hi - first] - A.tile0;
+                if (t) sketch2_kernel<15><<<t, SK_THREADS, 0, c->stream>>>(A);
+                lo = hi;
+            }
+        } else {
+            if (s->pending) CUDA_CHECK(cudaStreamWaitEvent(c->stream, s->ready, 0));
+            A.tile0 = 0;
+            sketch2_kernel<15><<<tiles, SK_THREADS, 0, c->stream>>>(A);
+        }
+    });
+    CUDA_CHECK(cudaGetLastError());
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream);
+    KLAUNCH(c, "cub::DeviceScan(u32)", 8.0 * nw,
+            cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream));
+    uint32_t total = 0, ovf = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&total, c->woff.as<uint32_t>() + nw, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&ovf, c->xflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (ovf) { c->prof.send(ST_SKETCH); return false; }
+    out->M = total;
+    out->x.reserve(((size_t)total + 1) * 8);
+    out->y.reserve(((size_t)total + 1) * 8);
+    KLAUNCH(c, "compact_kernel", 32.0 * total,
+            compact_kernel<<<(nw + 7) / 8, 256, 0, c->stream>>>(c->stg_x.as<uint64_t>(), c->stg_y.as<uint64_t>(), c->wcnt.as<uint32_t>(),
+                                                               c->woff.as<uint32_t>(), nw, SK_CAP, out->x.as<uint64_t>(), out->y.as<uint64_t>()));
+    // per-read minimizer offsets: woff at the first warp sub-tile of every read
+    KLAUNCH(c, "gather_kernel", 12.0 * n,
+            gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), c->tile_off.as<uint32_t>(),
+                                                                         SK_THREADS / 32, n + 1, out->moff.as<uint32_t>()));
+    CUDA_CHECK(cudaGetLastError());
+    c->prof.send(ST_SKETCH);
+    return true;
+}
+
 // K0 + K1: sketch a staged read set, or only its reads [first, first + count), into `out`
 void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first = 0, uint32_t count = 0xffffffffu) {
     if (first > s->n) first = s->n;
     if (count > s->n - first) count = s->n - first;
     if (count && (first < s->blk_first || first + count > s->blk_first + s->blk_count))
         throw std::runtime_error("internal: sketch of reads that were not staged");
+    if (!o.is_hpc && o.k == 15 && !c->sketch_legacy && sketch_readset2(c, s, o, out, first, count)) return;
     const bool subset = first != 0 || count != s->n;
     const uint32_t n = count;
     std::vector<uint64_t> poff(n), soff(n);
@@ -1274,6 +1396,7 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         CUDA_CHECK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CUDA_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, device));
         { const char *e = getenv("LRGE_SKETCH_TWO_PASS"); c->sketch_two_pass = e && e[0] == '1'; }
+        { const char *e = getenv("LRGE_SKETCH_LEGACY"); c->sketch_legacy = (e && e[0] == '1') || c->sketch_two_pass; }
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         c->prof.s = c->stream;

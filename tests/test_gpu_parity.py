@@ -58,6 +58,31 @@ def test_sketch_parity_ambiguous_and_short(ctx, platform):
     check_minimizers(ctx, ReadSet.from_records(recs), platform)
 
 
+def test_sketch_legacy_single_pass_path(monkeypatch):
+    """ava-ont defaults to the lane-serial single-kernel sketch; LRGE_SKETCH_LEGACY=1 selects the warp-shuffle kernel with
+    staging slots + compaction (what ava-pb always uses)."""
+    monkeypatch.setenv("LRGE_SKETCH_LEGACY", "1")
+    c1 = lrge_b200.Context(0)
+    try:
+        T, _ = small_sets(n_rate=0.002)
+        check_minimizers(c1, T, "ont")
+    finally:
+        c1.close()
+
+
+def test_sketch_long_reads_and_many_tiles(ctx):
+    """Reads spanning many 8 192-step tiles (look-back scan across tiles and reads), with N runs at tile borders."""
+    rng = np.random.default_rng(5)
+    recs = []
+    for i, L in enumerate((70_000, 8192 * 3, 8192 * 3 + 1, 40_001, 123, 8192, 8191, 16_385, 1)):
+        seq = bytearray(rng.choice(list(b"ACGT"), size=L).tolist())
+        for at in (8190, 8192, 16383, 16384, 24576):
+            if at + 3 < L:
+                seq[at:at + 3] = b"NNN"
+        recs.append(("long%d" % i, bytes(seq)))
+    check_minimizers(ctx, ReadSet.from_records(recs), "ont")
+
+
 @pytest.mark.parametrize("platform", ["ont", "pb"])
 def test_sketch_two_pass_path(monkeypatch, platform):
     monkeypatch.setenv("LRGE_SKETCH_TWO_PASS", "1")
