@@ -166,22 +166,29 @@ def other_configs(ctx, names, threads, rank, world, dist, shard):
         t0 = time.perf_counter()
         strat, platform, A, B = readsim.make_config(name)
         gen_s = time.perf_counter() - t0
-        run = (lambda: ctx.twoset_counts(A, B, platform, **shard)) if strat == "twoset" else (lambda: ctx.ava_counts(A, platform, **shard))
+        # read sets resident in HBM, like `value`; time = CUDA events around the whole path (2 passes after a warm-up)
+        sA = ctx.stage(A)
+        sB = ctx.stage(B) if B is not None else None
+        run = (lambda: ctx.twoset_counts(sA, sB, platform, **shard)) if strat == "twoset" else (lambda: ctx.ava_counts(sA, platform, **shard))
         res = run()
         ms = []
         for _ in range(2):
             res = run()
             ms.append(res.stats["ms_total"])
+        sA.free()
+        if sB is not None:
+            sB.free()
         e = {"strategy": strat, "platform": platform, "n_gpus": world, "reads": A.n + (B.n if B is not None else 0),
              "mbases": (A.total_bases + (B.total_bases if B is not None else 0)) / 1e6,
-             "gpu_ms_host_buffers_in": round(float(np.mean(ms)), 3), "generate_s": round(gen_s, 1),
+             "gpu_ms": round(float(np.mean(ms)), 3), "generate_s": round(gen_s, 1),
              "n_anchors": res.stats["n_anchors"], "n_overlaps": res.stats["n_overlaps"], "rounds": res.stats["n_rounds"], "batches": res.stats["n_batches"],
-             "deferred_queries": res.stats["n_deferred"], "mid_occ": res.stats["mid_occ"]}
+             "deferred_queries": res.stats["n_deferred"], "mid_occ": res.stats["mid_occ"],
+             "stage_ms": {k[3:]: round(v, 2) for k, v in res.stats.items() if k.startswith("ms_") and v}}
         if world > 1:
-            t = __import__("torch").tensor([e["gpu_ms_host_buffers_in"]], dtype=__import__("torch").float64, device="cuda")
+            t = __import__("torch").tensor([e["gpu_ms"]], dtype=__import__("torch").float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e["gpu_ms_host_buffers_in"] = float(t[0])
-        e["overlaps_per_s"] = e["n_overlaps"] / (e["gpu_ms_host_buffers_in"] / 1e3)
+            e["gpu_ms"] = float(t[0])
+        e["overlaps_per_s"] = e["n_overlaps"] / (e["gpu_ms"] / 1e3)
         if rank == 0:
             t0 = time.perf_counter()
             if strat == "twoset":
@@ -193,7 +200,7 @@ def other_configs(ctx, names, threads, rank, world, dist, shard):
             e.update({"oracle_s": round(time.perf_counter() - t0, 1), "oracle_threads": threads,
                       "counts_identical": same, "reads_compared": int(want.shape[0]),
                       "anchors_identical": bool(st["n_anchors"] == res.stats["n_anchors"]) if world == 1 else None,
-                      "speedup_vs_oracle": round((time.perf_counter() - t0) * 1e3 / e["gpu_ms_host_buffers_in"], 1)})
+                      "speedup_vs_oracle": round((time.perf_counter() - t0) * 1e3 / e["gpu_ms"], 1)})
         if dist is not None:
             dist.barrier()
         out[name] = e

@@ -186,9 +186,11 @@ int  lrge_gpu_dump_mid_occ(lrge_ctx *ctx, const lrge_readset *T, int32_t platfor
 /* Plain or gzip FASTA / FASTQ ingestion on the host (io::count_records / io::iter_records, io.rs:121-184; the read id
  * is the header up to the first whitespace, io.rs:192-205).  bzip2 / zstd / xz / BAM inputs -> LRGE_ERR_UNSUPPORTED;
  * an unreadable or empty file -> LRGE_ERR_IO; a malformed record -> LRGE_ERR_FASTQ_PARSE.
- * lrge_fastx_load fills buffers sized from lrge_fastx_count in the lrge_readset layout (off[n+1], name_off[n+1]). */
+ * lrge_fastx_load fills buffers sized from lrge_fastx_count in the lrge_readset layout (off[n+1], name_off[n+1]); the
+ * capacities are checked while the file is parsed again (LRGE_ERR_INVALID_ARG if it no longer fits). */
 int  lrge_fastx_count(const char *path, uint64_t *n_records, uint64_t *n_bases, uint64_t *n_name_bytes);
-int  lrge_fastx_load(const char *path, uint8_t *bases, uint64_t *off, char *names, uint32_t *name_off);
+int  lrge_fastx_load(const char *path, uint8_t *bases, uint64_t cap_bases, uint64_t *off, uint64_t cap_records,
+                     char *names, uint64_t cap_name_bytes, uint32_t *name_off);
 
 /* host-side estimator arithmetic (f32, evaluation order of estimate.rs) */
 float lrge_per_read_estimate(uint64_t read_len, float avg_target_len, uint64_t n_target_reads,

@@ -73,7 +73,7 @@ struct ReadSet {
         if (rc != LRGE_OK) throw LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: " + path);
         ReadSet rs;
         rs.bases.resize(nb); rs.off.resize(n + 1); rs.names.resize(nn); rs.name_off.resize(n + 1);
-        rc = lrge_fastx_load(path.c_str(), rs.bases.data(), rs.off.data(), rs.names.data(), rs.name_off.data());
+        rc = lrge_fastx_load(path.c_str(), rs.bases.data(), rs.bases.size(), rs.off.data(), rs.off.size() - 1, rs.names.data(), rs.names.size(), rs.name_off.data());
         if (rc != LRGE_OK) throw LrgeError((lrge_status)rc, "FASTQ parse error: " + path);
         return rs;
     }

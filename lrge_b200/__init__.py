@@ -124,7 +124,7 @@ def lib():
         L.lrge_paf_format.argtypes = [vp, ctypes.c_char_p, ctypes.c_int, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int, ctypes.c_int32,
                                       ctypes.c_float, ctypes.c_int32, ctypes.c_char_p, ctypes.c_size_t]
         L.lrge_fastx_count.argtypes = [ctypes.c_char_p, P(ctypes.c_uint64), P(ctypes.c_uint64), P(ctypes.c_uint64)]
-        L.lrge_fastx_load.argtypes = [ctypes.c_char_p, vp, vp, vp, vp]
+        L.lrge_fastx_load.argtypes = [ctypes.c_char_p, vp, ctypes.c_uint64, vp, ctypes.c_uint64, vp, ctypes.c_uint64, vp]
         L.lrge_gpu_host_alloc.argtypes = [ctypes.c_size_t, P(vp)]
         L.lrge_gpu_host_free.argtypes = [vp]
         L.lrge_gpu_host_free.restype = None
@@ -356,7 +356,7 @@ def read_fastx(path: str) -> ReadSet:
         raise LrgeError(rc, path)
     bases, off = np.zeros(max(nb.value, 1), np.uint8), np.zeros(n.value + 1, np.uint64)
     names, noff = np.zeros(max(nn.value, 1), np.uint8), np.zeros(n.value + 1, np.uint32)
-    rc = lib().lrge_fastx_load(path.encode(), bases.ctypes.data, off.ctypes.data, names.ctypes.data, noff.ctypes.data)
+    rc = lib().lrge_fastx_load(path.encode(), bases.ctypes.data, nb.value, off.ctypes.data, n.value, names.ctypes.data, nn.value, noff.ctypes.data)
     if rc != 0:
         raise LrgeError(rc, path)
     return ReadSet(bases[:nb.value], off, names[:nn.value], noff)

@@ -105,18 +105,25 @@ int lrge_fastx_count(const char *path, uint64_t *n_records, uint64_t *n_bases, u
     return LRGE_OK;
 }
 
-// Loads every record into caller buffers sized from lrge_fastx_count: bases[n_bases], off[n+1], names[n_name_bytes],
-// name_off[n+1] -- the lrge_readset layout.
-int lrge_fastx_load(const char *path, uint8_t *bases, uint64_t *off, char *names, uint32_t *name_off) {
+// Loads every record into caller buffers sized from lrge_fastx_count: bases[cap_bases], off[cap_records + 1],
+// names[cap_name_bytes], name_off[cap_records + 1] -- the lrge_readset layout.  The file is parsed again, so every write is
+// checked against the capacities (a pipe or a file still being written may have grown): LRGE_ERR_INVALID_ARG if a
+// record does not fit, or if the names exceed the 32-bit offsets of lrge_readset.
+int lrge_fastx_load(const char *path, uint8_t *bases, uint64_t cap_bases, uint64_t *off, uint64_t cap_records,
+                    char *names, uint64_t cap_name_bytes, uint32_t *name_off) {
     if (!path || !bases || !off || !names || !name_off) return LRGE_ERR_INVALID_ARG;
-    uint64_t n = 0, b = 0;
-    uint32_t nb = 0;
+    uint64_t n = 0, b = 0, nb = 0;
+    bool fits = true;
     off[0] = 0; name_off[0] = 0;
-    return for_each_record(path, [&](const char *id, size_t il, const char *seq, size_t sl) {
+    const int rc = for_each_record(path, [&](const char *id, size_t il, const char *seq, size_t sl) {
+        if (!fits) return;
+        if (n + 1 > cap_records || b + sl > cap_bases || nb + il > cap_name_bytes || nb + il > 0xffffffffull) { fits = false; return; }
         memcpy(bases + b, seq, sl); b += sl;
-        memcpy(names + nb, id, il); nb += (uint32_t)il;
-        ++n; off[n] = b; name_off[n] = nb;
+        memcpy(names + nb, id, il); nb += il;
+        ++n; off[n] = b; name_off[n] = (uint32_t)nb;
     });
+    if (rc != LRGE_OK) return rc;
+    return fits ? LRGE_OK : LRGE_ERR_INVALID_ARG;
 }
 
 float lrge_per_read_estimate(uint64_t read_len, float avg_target_len, uint64_t n_target_reads, uint64_t n_ovlaps,

@@ -478,8 +478,8 @@ __global__ void group_mark_kernel(const uint64_t *__restrict__ akey, const uint3
 // in 4 size classes.  The pair slot is the index of the pair's forward group (or the group itself).
 struct GroupLists { GroupDesc *gl[4]; uint32_t cap[4]; };
 __global__ void group_classify_kernel(const uint64_t *__restrict__ akey, const uint32_t *__restrict__ gstart, uint32_t n_groups,
-                                      int PB, int RB, uint32_t q0, int min_cnt, int min_sc, int max_span, GroupLists L,
-                                      uint32_t *__restrict__ gcount) {
+                                      int PB, int RB, uint32_t q0, const uint32_t *__restrict__ qmap, int min_cnt, int min_sc,
+                                      int max_span, GroupLists L, uint32_t *__restrict__ gcount) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     const uint32_t g0 = gstart[g], n = gstart[g + 1] - g0;
@@ -489,7 +489,8 @@ __global__ void group_classify_kernel(const uint64_t *__restrict__ akey, const u
     d.start = g0; d.n = n;
     d.strand = (uint32_t)((k0 >> PB) & 1);
     d.rid = (uint32_t)((k0 >> (PB + 1)) & ((1ULL << RB) - 1));
-    d.qid = q0 + (uint32_t)(k0 >> (PB + 1 + RB));
+    const uint32_t ql = (uint32_t)(k0 >> (PB + 1 + RB));                 // local query id in the batch
+    d.qid = qmap ? qmap[ql] : q0 + ql;
     d.pair = g;
     if (d.strand && g > 0 && (akey[gstart[g - 1]] >> (PB + 1)) == (k0 >> (PB + 1))) d.pair = g - 1;
     const int c = group_class(n);

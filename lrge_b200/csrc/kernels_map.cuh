@@ -29,7 +29,7 @@
 namespace lrge {
 
 constexpr int MAP_MAX_WARPS = 32;
-constexpr int MAP_BINS = 512;          // target-id histogram bins for round planning
+constexpr int MAP_BINS = 2048;         // target-id histogram bins for round planning (fewer when the smem capacity is tiny)
 constexpr int MAP_MAX_ROUNDS = 255;
 constexpr int SL_ILP = 4;              // independent probes per thread in seed_lookup_kernel
 constexpr int SL_THREADS = 256;
@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(SL_THREADS) seed_lookup_kernel(const uint64_t 
 struct SortArgs {
     const void *akey;                // anchors of the batch, per query contiguous, in generation order (anchor_fill_kernel):
     const uint32_t *aval;            //   key (KT) = ((rid - rid_base) << 1 | rev) << PB | target pos, val = span << 24 | qpos'
+    void *akey2;                     // scratch of the same size: a multi-round query's anchors partitioned by round
+    uint32_t *aval2;
     const uint64_t *qaoff;           // per query (absolute id): anchors before it
     uint64_t a_base;                 // qaoff of the batch's first query: akey[0] is anchor a_base
     const uint32_t *qorder;          // queries of the batch, longest first
@@ -106,7 +108,7 @@ struct SortArgs {
     uint32_t cap;                    // anchors per round (smem capacity), multiple of 32, < 65536
     int PB, key_bits;                // key_bits = bits of (rid - rid_base) + 1 + PB
     uint32_t rid_base;               // first target id held by this index (sharded index: the rank's block)
-    int hshift;                      // histogram bin = (rid - rid_base) >> hshift
+    int rel_bits;                    // bits of (rid - rid_base); histogram bin = (rid - rid_base) >> (rel_bits - log2(bins))
     int max_span, min_cnt, min_sc;   // a group of n anchors scores at most n * max_span
     uint2 *anc;                      // out: sorted compact anchors (target pos, payload), same offsets as akey
     GroupLists L;                    // out: descriptors of the groups that can hold a chain, 4 size classes
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
     constexpr int MAP_THREADS = NT, MAP_WARPS = NT / 32;
     extern __shared__ __align__(16) uint8_t map_smem[];
     __shared__ uint32_t s_wsum[MAP_WARPS + 1];
-    __shared__ uint32_t s_rbound[MAP_MAX_ROUNDS + 2];
+    __shared__ uint32_t s_rbound[MAP_MAX_ROUNDS + 2], s_rE[MAP_MAX_ROUNDS + 2], s_rN[MAP_MAX_ROUNDS + 2];
     __shared__ uint32_t s_q, s_nrounds, s_unit;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -303,7 +305,12 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
     uint32_t *vY = reinterpret_cast<uint32_t *>(bufY + (size_t)cap * sizeof(KT));
     uint16_t *rank = reinterpret_cast<uint16_t *>(bufY + (size_t)cap * (sizeof(KT) + 4));
     uint16_t *hist = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(rank) + (size_t)cap * 2);
-    uint32_t *bins = reinterpret_cast<uint32_t *>(kY);                    // round planning only (before staging)
+    uint32_t *bins = reinterpret_cast<uint32_t *>(bufY);                  // round planning only (before staging): <= 8 * cap bytes
+    int nbins_log = 11;                                                   // MAP_BINS = 2^11, fewer if the buffer is smaller
+    while ((4u << nbins_log) > 8u * cap) --nbins_log;
+    const uint32_t nbins = 1u << nbins_log;
+    const int hshift = A.rel_bits > nbins_log ? A.rel_bits - nbins_log : 0;
+    constexpr int BPT = MAP_BINS / MAP_THREADS;                           // bins per thread in the prefix pass
 
     const int PB = A.PB;
     unsigned long long st_anchors = 0, st_groups = 0, st_rounds = 0;     // st_groups: per warp (lane 0), others: thread 0
@@ -347,35 +354,38 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
 
         uint32_t nrounds = 1;
         if (Aq > cap) {
-            // plan rounds: histogram of the anchors over target ids (MAP_BINS bins), prefix sums, then R ranges of about
-            // Aq / R anchors each (R sized for 85 % fill); every range is checked against the capacity, and a plan that
-            // does not fit falls back to the exact greedy partition
-            for (uint32_t i = tid; i < MAP_BINS; i += MAP_THREADS) bins[i] = 0;
+            // plan rounds: histogram of the anchors over target ids, prefix sums, then R ranges of about Aq / R anchors
+            // each (R sized for 85 % fill); every range is checked against the capacity, and a plan that does not fit
+            // falls back to the exact greedy partition
+            for (uint32_t i = tid; i < nbins; i += MAP_THREADS) bins[i] = 0;
             __syncthreads();
-            for (uint32_t i = tid; i < Aq; i += MAP_THREADS) atomicAdd(&bins[(uint32_t)(gk[i] >> (PB + 1)) >> A.hshift], 1u);
+            for (uint32_t i = tid; i < Aq; i += MAP_THREADS) atomicAdd(&bins[(uint32_t)(gk[i] >> (PB + 1)) >> hshift], 1u);
             __syncthreads();
-            const uint32_t mine = tid < MAP_BINS ? bins[tid] : 0;
+            uint32_t mine = 0;
+#pragma unroll
+            for (int j = 0; j < BPT; ++j) { const uint32_t b = tid * BPT + j; mine += b < nbins ? bins[b] : 0; }
             uint32_t tot;
-            const uint32_t excl = block_excl_scan<NT>(mine, s_wsum, tot);  // anchors in the bins before bin `tid`
+            uint32_t E = block_excl_scan<NT>(mine, s_wsum, tot);             // anchors in the bins before this thread's first bin
             const uint32_t R = (uint32_t)(((uint64_t)Aq * 100 + (uint64_t)cap * 85 - 1) / ((uint64_t)cap * 85));
             const uint32_t tgt = (Aq + R - 1) / R;
             const bool quick = R <= MAP_MAX_ROUNDS;
             if (quick) {
-                for (uint32_t k = tid; k <= R; k += MAP_THREADS) s_rbound[k] = k == 0 ? 0u : k == R ? 0xffffffffu : 0xfffffffeu;
-                __syncthreads();
-                if (tid > 0 && tid < MAP_BINS) {                           // range k starts at the first bin b with excl[b] >= k * tgt
-                    const uint32_t ex_prev = excl - bins[tid - 1];
-                    for (uint32_t k = ex_prev / tgt + 1; k <= excl / tgt && k < R; ++k) s_rbound[k] = tid << A.hshift;
+                for (uint32_t k = tid; k <= R; k += MAP_THREADS) {
+                    s_rbound[k] = k == 0 ? 0u : k == R ? 0xffffffffu : 0xfffffffeu;   // 0xfffffffe: range never started (empty tail)
+                    s_rE[k] = k == 0 ? 0u : Aq;
                 }
                 __syncthreads();
-                bool bad = false;                                          // a range left unset (0xfffffffe) is an empty tail round
-                if (tid < R) {
-                    const uint32_t b0 = s_rbound[tid] >= 0xfffffffeu ? MAP_BINS : s_rbound[tid] >> A.hshift;
-                    const uint32_t b1 = s_rbound[tid + 1] >= 0xfffffffeu ? MAP_BINS : s_rbound[tid + 1] >> A.hshift;
-                    uint32_t cnt = 0;
-                    for (uint32_t bb = b0; bb < b1; ++bb) cnt += bins[bb];
-                    bad = cnt > cap;
+#pragma unroll
+                for (int j = 0; j < BPT; ++j) {                            // range k starts at the first bin b with E[b] >= k * tgt
+                    const uint32_t b = tid * BPT + j;
+                    if (b > 0 && b < nbins) {
+                        const uint32_t e_prev = E - bins[b - 1];
+                        for (uint32_t k = e_prev / tgt + 1; k <= E / tgt && k < R; ++k) { s_rbound[k] = b << hshift; s_rE[k] = E; }
+                    }
+                    if (b < nbins) E += bins[b];
                 }
+                __syncthreads();
+                const bool bad = tid < R && s_rE[tid + 1] - s_rE[tid] > cap;   // anchors of range tid
                 const int any_bad = __syncthreads_or(bad);
                 if (tid == 0) s_nrounds = any_bad ? 0 : R;
             } else if (tid == 0) s_nrounds = 0;
@@ -385,12 +395,12 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
                     uint32_t r = 0, acc = 0;
                     bool ok = true;
                     s_rbound[0] = 0;
-                    for (uint32_t b = 0; b < MAP_BINS; ++b) {
+                    for (uint32_t b = 0; b < nbins; ++b) {
                         const uint32_t c = bins[b];
                         if (c > cap) { ok = false; break; }
                         if (acc + c > cap) {
                             if (++r >= MAP_MAX_ROUNDS) { ok = false; break; }
-                            s_rbound[r] = b << A.hshift;
+                            s_rbound[r] = b << hshift;
                             acc = 0;
                         }
                         acc += c;
@@ -406,40 +416,68 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
                 continue;
             }
         }
+        if (nrounds > 1) {
+            // Partition the query's anchors by round ONCE, stably, into the scratch arrays (a counting sort by round id,
+            // every warp over its contiguous slice): each round then stages a contiguous range instead of filtering the
+            // whole query again.  Counters (round, warp) are u16 and alias the radix histogram.
+            uint16_t *cnt = hist;                                          // [round * MAP_WARPS + warp], round < 256
+            for (uint32_t i = tid; i < MAP_WARPS * 128; i += MAP_THREADS) reinterpret_cast<uint32_t *>(hist)[i] = 0;
+            for (uint32_t b = tid; b < nbins; b += MAP_THREADS) {          // bin -> round (boundaries are multiples of a bin)
+                const uint32_t first_rel = b << hshift;
+                uint32_t lo = 0, hi = nrounds;                             // largest k with s_rbound[k] <= first_rel
+                while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (s_rbound[mid] <= first_rel) lo = mid; else hi = mid; }
+                bins[b] = lo;
+            }
+            __syncthreads();
+            const uint32_t lt = (1u << lane) - 1;
+            for (uint32_t b = w0; b < w1; b += 32) {
+                const uint32_t i = b + lane;
+                const uint32_t rd = i < w1 ? bins[(uint32_t)(gk[i] >> (PB + 1)) >> hshift] : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, rd);
+                if (i < w1 && (peers & lt) == 0) cnt[rd * MAP_WARPS + warp] = (uint16_t)(cnt[rd * MAP_WARPS + warp] + __popc(peers));
+                __syncwarp();
+            }
+            __syncthreads();
+            if (tid < nrounds) {                                           // per round: exclusive offsets of the warps, total
+                uint32_t run = 0;
+                for (int w = 0; w < MAP_WARPS; ++w) { const uint32_t v = cnt[tid * MAP_WARPS + w]; cnt[tid * MAP_WARPS + w] = (uint16_t)run; run += v; }
+                s_rN[tid] = run;
+            }
+            __syncthreads();
+            if (tid == 0) { uint32_t run = 0; for (uint32_t k = 0; k < nrounds; ++k) { s_rE[k] = run; run += s_rN[k]; } }   // round starts
+            __syncthreads();
+            KT *gk2 = reinterpret_cast<KT *>(A.akey2) + a0;
+            uint32_t *gv2 = A.aval2 + a0;
+            for (uint32_t b = w0; b < w1; b += 32) {
+                const uint32_t i = b + lane;
+                const KT k = i < w1 ? gk[i] : (KT)0;
+                const uint32_t rd = i < w1 ? bins[(uint32_t)(k >> (PB + 1)) >> hshift] : 0xffffffffu;
+                const uint32_t peers = __match_any_sync(0xffffffffu, rd);
+                if (i < w1) {
+                    const uint32_t at = s_rE[rd] + cnt[rd * MAP_WARPS + warp] + __popc(peers & lt);
+                    gk2[at] = k; gv2[at] = gv[i];
+                }
+                __syncwarp();
+                if (i < w1 && (peers & lt) == 0) cnt[rd * MAP_WARPS + warp] = (uint16_t)(cnt[rd * MAP_WARPS + warp] + __popc(peers));
+                __syncwarp();
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
         { const long long now = clock64(); cy[0] += now - tc; tc = now; }
         uint32_t round_base = 0;                                         // anchors written back by earlier rounds
         for (uint32_t rd = 0; rd < nrounds; ++rd) {
-            // ---- 1. stage: HBM -> smem, generation order kept --------------------------------------------------
-            uint32_t N = Aq;
-            if (nrounds == 1) {
-                // straight copy, eight independent coalesced loads in flight per thread
-                for (uint32_t b = 0; b < Aq; b += 4 * MAP_THREADS) {
-                    KT k[4]; uint32_t v[4];
+            // ---- 1. stage: HBM -> smem, generation order kept: a straight copy, eight coalesced loads in flight per thread
+            const uint32_t N = nrounds == 1 ? Aq : s_rN[rd];
+            if (N > cap) { if (tid == 0) atomicAdd(A.stats + 3, 1ull); continue; }   // cannot happen (planned)
+            const KT *sk = nrounds == 1 ? gk : reinterpret_cast<const KT *>(A.akey2) + a0 + s_rE[rd];
+            const uint32_t *sv = nrounds == 1 ? gv : A.aval2 + a0 + s_rE[rd];
+            for (uint32_t b = 0; b < N; b += 4 * MAP_THREADS) {
+                KT k[4]; uint32_t v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const uint32_t i = b + u * MAP_THREADS + tid; if (i < Aq) { k[u] = gk[i]; v[u] = gv[i]; } }
+                for (int u = 0; u < 4; ++u) { const uint32_t i = b + u * MAP_THREADS + tid; if (i < N) { k[u] = sk[i]; v[u] = sv[i]; } }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const uint32_t i = b + u * MAP_THREADS + tid; if (i < Aq) { kX[i] = k[u]; vX[i] = v[u]; } }
-                }
-            } else {
-                const uint32_t rlo = s_rbound[rd], rhi = s_rbound[rd + 1];
-                auto in_round = [&](KT k) -> bool {
-                    const uint32_t rel = (uint32_t)(k >> (PB + 1));
-                    return rel >= rlo && rel < rhi;
-                };
-                uint32_t wt = 0;
-                for (uint32_t b = w0; b < w1; b += 32) wt += __popc(__ballot_sync(0xffffffffu, b + lane < w1 && in_round(gk[b + lane])));
-                uint32_t run = scan_warp_totals(wt, &N);
-                if (N > cap) { if (tid == 0) atomicAdd(A.stats + 3, 1ull); N = 0; }   // cannot happen (planned)
-                if (N) {
-                    for (uint32_t b = w0; b < w1; b += 32) {
-                        const uint32_t i = b + lane;
-                        const KT k = i < w1 ? gk[i] : (KT)0;
-                        const bool in = i < w1 && in_round(k);
-                        const uint32_t m = __ballot_sync(0xffffffffu, in);
-                        if (in) { const uint32_t at = run + __popc(m & ((1u << lane) - 1)); kX[at] = k; vX[at] = gv[i]; }
-                        run += __popc(m);
-                    }
-                }
+                for (int u = 0; u < 4; ++u) { const uint32_t i = b + u * MAP_THREADS + tid; if (i < N) { kX[i] = k[u]; vX[i] = v[u]; } }
             }
             __syncthreads();
             { const long long now = clock64(); cy[1] += now - tc; tc = now; }

@@ -76,8 +76,21 @@ __global__ void seed_count_kernel(const uint64_t *__restrict__ qx, const uint64_
         if (n && I.bl && ((I.bl[start >> 5] >> (start & 31)) & 1)) n = 0;   // > mid_occ over all target shards
         if (n) {
             if (S.check_names || S.sharded) {
+                // 128-bit loads, two hit-list entries each, four loads in flight
                 const uint64_t y = qy[i];
-                for (uint32_t j = 0; j < n; ++j) cnt += !skip_hit(I.ty[start + j], (uint32_t)(y >> 32), (uint32_t)y, S);
+                const uint4 *ty4 = reinterpret_cast<const uint4 *>(I.ty);
+                const uint32_t p1 = (start + n + 1) >> 1;
+                for (uint32_t p = start >> 1; p < p1; p += 4) {
+                    uint4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = p + u < p1 ? __ldg(ty4 + p + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t e0 = 2 * (p + u), e1 = e0 + 1;
+                        if (e0 >= start && e0 < start + n) cnt += !skip_hit((uint64_t)v[u].y << 32 | v[u].x, (uint32_t)(y >> 32), (uint32_t)y, S);
+                        if (e1 >= start && e1 < start + n) cnt += !skip_hit((uint64_t)v[u].w << 32 | v[u].z, (uint32_t)(y >> 32), (uint32_t)y, S);
+                    }
+                }
             } else cnt = n;
         }
         hstart[i] = start;

@@ -178,6 +178,7 @@ struct lrge_staged {
     std::vector<uint32_t> name_off;
     std::vector<std::pair<uint64_t, uint32_t>> name_hash;   // (FNV-1a of the name, read), sorted: cheap equality joins
     bool names_unique = true;
+    bool has_empty = false;                                // a zero-length read: the index build skips it, mapping it is an error
     std::vector<uint32_t> lex_rank;                        // lazily: lexicographic rank of each name (AVA's strcmp order)
     std::vector<uint32_t> len_order;                       // reads, longest first (work order of the fused map kernel)
     cudaEvent_t ready = nullptr;                           // async staging: recorded on the copy stream after the H2D copies
@@ -303,9 +304,10 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool asy
     }
     s->h_len.resize(rs->n);
     s->max_len = 0;
+    s->has_empty = false;
     for (uint32_t i = 0; i < rs->n; ++i) {
         const uint64_t l = s->h_off[i + 1] - s->h_off[i];
-        if (l == 0) { cudaStreamSynchronize(c->copy_stream); throw std::invalid_argument("MapError: Sequence is empty"); }   // aligner.rs:214-216
+        if (l == 0) s->has_empty = true;                  // fatal only for a read that is MAPPED (aligner.rs:214-216), see run_overlap
         if (l >= (1u << 24)) { cudaStreamSynchronize(c->copy_stream); throw std::length_error("reads of 16 Mbases or more are not supported"); }
         s->h_len[i] = (uint32_t)l;
         s->max_len = std::max(s->max_len, (uint32_t)l);
@@ -856,6 +858,9 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     static_assert(sizeof(lrge_overlap) == sizeof(RegOut), "lrge_overlap and the device record must share a layout");
     const MapOpt o = preset_for(opts.platform);
     const uint32_t n_counts = mode == MODE_TWOSET ? str->n : idx->n;
+    // Aligner::map fails on an empty sequence (aligner.rs:214-216 -> LrgeError::MapError); minimap2's index build just
+    // skips empty target sequences, so only the streamed set is checked
+    if (str->has_empty) throw std::invalid_argument("MapError: Sequence is empty");
     c->prof.reset();
     c->prof.sbegin(ST_TOTAL);
     lrge_stats S{};
@@ -1054,20 +1059,37 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     O.names_unique = !host_dedupe;
     if (want_regs) { O.regs = c->regs.as<RegOut>(); O.n_regs = ctr + 2; O.regs_cap = rq->cap; }
 
-    auto run_batch = [&](uint32_t q0, uint32_t q1, bool smem_sort) {
-        const uint64_t nA = qa[q1] - qa[q0];
+    // A batch is the contiguous query range [q0, q1), or -- for the queries the per-query kernel deferred -- the
+    // scattered queries list[0 .. nlist), which then take local ids 0 .. nlist-1 in the 64-bit sort key.
+    auto run_batch = [&](uint32_t q0, uint32_t q1, bool smem_sort, const uint32_t *list = nullptr, uint32_t nlist = 0) {
+        uint64_t nA = 0;
+        if (list) { for (uint32_t j = 0; j < nlist; ++j) nA += qa[list[j] + 1] - qa[list[j]]; }
+        else nA = qa[q1] - qa[q0];
+        const uint32_t nq_batch = list ? nlist : q1 - q0;
         if (nA > a_max) throw std::length_error("a single read yields more anchors than fit in device memory");
-        const int QB = bits_for(q1 - q0 - 1);
+        const int QB = bits_for(nq_batch ? nq_batch - 1 : 0);
         if (QB + RB + 1 + PB > 64) throw std::length_error("sort key does not fit 64 bits (too many reads x read length)");
         if (!nA) return;
         c->prof.sbegin(ST_SEED);
         c->akey0.reserve(nA * 8); c->aval0.reserve(nA * 4);
-        const uint64_t m0 = moff_h[q0], m1 = moff_h[q1];
+        const uint64_t m0 = list ? 0 : moff_h[q0], m1 = list ? 0 : moff_h[q1];
         KeyLayout KL{PB, RB, r0};
         // SURVEY.md 8(d) K4 without the probes (seed_lookup_kernel): hit lists 8H + anchors 16A
         KLAUNCH(c, "anchor_fill_kernel", 8.0 * nA + 16.0 * nA, {
             const unsigned fg = (unsigned)((m1 - m0 + 255) / 256);
-            if (!smem_sort)
+            if (list) {
+                // one launch per listed query: its anchors follow those of the queries before it in the list
+                uint64_t base = 0;
+                for (uint32_t j = 0; j < nlist; ++j) {
+                    const uint32_t q = list[j];
+                    const uint64_t qm0 = moff_h[q], qm1 = moff_h[q + 1], nq_a = qa[q + 1] - qa[q];
+                    if (qm1 > qm0 && nq_a)
+                        anchor_fill_kernel<uint64_t, true><<<(unsigned)((qm1 - qm0 + 255) / 256), 256, 0, c->stream>>>(
+                            sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
+                            c->aoff.as<uint64_t>(), qm0, qm1, qa[q] - base, q - j, B.view, K, KL, c->akey0.as<uint64_t>(), c->aval0.as<uint32_t>());
+                    base += nq_a;
+                }
+            } else if (!smem_sort)
                 anchor_fill_kernel<uint64_t, true><<<fg, 256, 0, c->stream>>>(
                     sq->x.as<uint64_t>(), sq->y.as<uint64_t>(), c->hstart.as<uint32_t>(), c->hn.as<uint32_t>(), c->acnt.as<uint32_t>(),
                     c->aoff.as<uint64_t>(), m0, m1, qa[q0], q0, B.view, K, KL, c->akey0.as<uint64_t>(), c->aval0.as<uint32_t>());
@@ -1110,13 +1132,13 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
             if (order_p != str->len_order.data()) CUDA_CHECK(cudaStreamSynchronize(c->stream));
             CUDA_CHECK(cudaMemsetAsync(c->mapctr.p, 0, 4, c->stream));
             SortArgs A{};
+            c->akey1.reserve(nA * 8); c->aval1.reserve(nA * 4);
             A.akey = c->akey0.p; A.aval = c->aval0.as<uint32_t>(); A.qaoff = c->qaoff.as<uint64_t>(); A.a_base = qa[q0];
+            A.akey2 = c->akey1.p; A.aval2 = c->aval1.as<uint32_t>();
             A.qorder = c->qorder.as<uint32_t>(); A.nq = q1 - q0;
             A.work_ctr = c->mapctr.as<uint32_t>(); A.n_deferred = c->mapctr.as<uint32_t>() + 1; A.deferred = c->deferred.as<uint32_t>();
             A.cap = map_cap; A.PB = PB; A.key_bits = key_bits; A.rid_base = r0;
-            int hshift = 0;
-            while (n_local && ((n_local - 1) >> hshift) >= (uint32_t)MAP_BINS) ++hshift;
-            A.hshift = hshift;
+            A.rel_bits = bits_for(n_local ? n_local - 1 : 0);
             A.max_span = o.is_hpc ? 255 : o.k; A.min_cnt = o.min_cnt; A.min_sc = o.min_chain_score;
             A.anc = c->anc.as<uint2>(); A.L = GL; A.gcount = c->gmeta.as<uint32_t>(); A.pair_ctr = c->gmeta.as<uint32_t>() + 9;
             A.stats = ctr + 3;
@@ -1205,9 +1227,11 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
                 const uint32_t sentinel = (uint32_t)nA;
                 CUDA_CHECK(cudaMemcpyAsync(c->pstart.as<uint32_t>() + n_groups, &sentinel, 4, cudaMemcpyHostToDevice, c->stream));
                 if ((size_t)n_groups + 1 > n_desc) { c->pflag.reserve(((size_t)n_groups + 2) * 4); CUDA_CHECK(cudaMemsetAsync(c->pflag.p, 0, ((size_t)n_groups + 2) * 4, c->stream)); }
+                const uint32_t *qmap = nullptr;
+                if (list) { h2d(c, c->qorder, list, nlist); qmap = c->qorder.as<uint32_t>(); }
                 KLAUNCH(c, "group_classify_kernel", 8.0 * n_groups,
                         group_classify_kernel<<<(n_groups + 255) / 256, 256, 0, c->stream>>>(c->akey1.as<uint64_t>(), c->pstart.as<uint32_t>(), n_groups, PB, RB,
-                                                                                            q0, P.min_cnt, P.min_sc, o.is_hpc ? 255 : o.k, GL,
+                                                                                            q0, qmap, P.min_cnt, P.min_sc, o.is_hpc ? 255 : o.k, GL,
                                                                                             c->gmeta.as<uint32_t>()));
                 S.n_pairs += n_groups;
             }
@@ -1229,7 +1253,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
             CUDA_CHECK(cudaMemsetAsync(ctr + 9, 0, 8, c->stream));
             T.dd_out = c->ddbuf.as<uint2>(); T.dd_n = ctr + 9;
         }
-        KLAUNCH(c, "chain_group_kernel", 16.0 * nA + 4.0 * (q1 - q0),
+        KLAUNCH(c, "chain_group_kernel", 16.0 * nA + 4.0 * nq_batch,
                 chain_group_kernel<<<c->n_sm * (2048 / CG_THREADS), CG_THREADS, 0, c->stream>>>(T, P, O));
         CUDA_CHECK(cudaGetLastError());
         if (host_dedupe) {                                                   // passing (query, target) pairs -> HashSet<name> per query
@@ -1265,7 +1289,16 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
             CUDA_CHECK(cudaMemcpyAsync(deferred.data(), c->deferred.p, (size_t)mapctr_h[1] * 4, cudaMemcpyDeviceToHost, c->stream));
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
             std::sort(deferred.begin(), deferred.end());
-            for (uint32_t q : deferred) { ++S.n_batches; run_batch(q, q + 1, false); }
+            // all of them in as few device-wide sorts as the anchor memory allows
+            size_t lo = 0;
+            while (lo < deferred.size()) {
+                size_t hi = lo;
+                uint64_t sum = 0;
+                while (hi < deferred.size() && (hi == lo || sum + (qa[deferred[hi] + 1] - qa[deferred[hi]]) <= a_max)) { sum += qa[deferred[hi] + 1] - qa[deferred[hi]]; ++hi; }
+                ++S.n_batches;
+                run_batch(0, 0, false, deferred.data() + lo, (uint32_t)(hi - lo));
+                lo = hi;
+            }
         }
     }
 

@@ -1,12 +1,13 @@
 // lrge-b200 -- command-line driver with the lrge CLI's flags (lrge/src/cli.rs:9-87, main.rs:32-121) over liblrge_b200.so.
 //
-// Differences, on purpose: plain FASTA/FASTQ only (no gz/BAM: io.rs is out of scope); the random subsample uses this
-// file's own generator, so `-s SEED` is repeatable here but does not pick the reads the Rust `rand` crate would
-// (lib.rs:189-204); `-t`, `-C`, `-D` are accepted and ignored (no threads, no temp files on this path); and
-// `--platform` IS forwarded (the reference CLI parses it but never passes it on, main.rs:56-85).
+// Differences, on purpose: plain or gzip FASTA/FASTQ only (no bzip2/zstd/xz/BAM: the rest of io.rs is out of scope); the
+// random subsample uses this file's own generator, so `-s SEED` is repeatable here but does not pick the reads the Rust
+// `rand` crate would (lib.rs:189-204); `-t`, `-C`, `-D` are accepted and ignored (no threads, no temp files on this
+// path); and `--platform` IS forwarded (the reference CLI parses it but never passes it on, main.rs:56-85).
 #include "../../include/lrge_b200.hpp"
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@ namespace {
 struct Args {
     std::string input, output = "-", platform = "ont";
     size_t target = lrge::DEFAULT_TARGET_NUM_READS, query = lrge::DEFAULT_QUERY_NUM_READS, num = 0;
+    bool have_num = false, have_target = false, have_query = false;
     bool filter_contained = false, with_infinity = false, precise = false, use_min_ref = false, seeded = false;
     uint64_t seed = 0;
     float q1 = lrge::LOWER_QUANTILE, q3 = lrge::UPPER_QUANTILE, max_overhang_ratio = 0.2f;
@@ -54,9 +56,9 @@ Args parse(int argc, char **argv) {
         const std::string s = argv[i];
         if (s == "-h" || s == "--help") usage(0);
         else if (s == "-o" || s == "--output") a.output = need(i);
-        else if (s == "-T" || s == "--target") a.target = strtoull(need(i), nullptr, 10);
-        else if (s == "-Q" || s == "--query") a.query = strtoull(need(i), nullptr, 10);
-        else if (s == "-n" || s == "--num") a.num = strtoull(need(i), nullptr, 10);
+        else if (s == "-T" || s == "--target") { a.target = strtoull(need(i), nullptr, 10); a.have_target = true; }
+        else if (s == "-Q" || s == "--query") { a.query = strtoull(need(i), nullptr, 10); a.have_query = true; }
+        else if (s == "-n" || s == "--num") { a.num = strtoull(need(i), nullptr, 10); a.have_num = true; }
         else if (s == "-P" || s == "--platform") a.platform = need(i);
         else if (s == "-F" || s == "--filter-contained") a.filter_contained = true;
         else if (s == "-s" || s == "--seed") { a.seed = strtoull(need(i), nullptr, 10); a.seeded = true; }
@@ -69,12 +71,18 @@ Args parse(int argc, char **argv) {
         else if (s == "--device") a.device = atoi(need(i));
         else if (s == "-t" || s == "--threads" || s == "-D" || s == "--temp") need(i);
         else if (s == "-C" || s == "--keep-temp") {}
-        else if (s.rfind("-q", 0) == 0) a.quiet = (int)s.size() - 1;
-        else if (s.rfind("-v", 0) == 0) {}
+        else if (s == "--quiet") ++a.quiet;
+        else if (s == "--verbose") {}
+        else if (s.size() >= 2 && s[0] == '-' && s[1] == 'q' && s.find_first_not_of('q', 1) == std::string::npos) a.quiet += (int)s.size() - 1;
+        else if (s.size() >= 2 && s[0] == '-' && s[1] == 'v' && s.find_first_not_of('v', 1) == std::string::npos) {}
         else if (!s.empty() && s[0] == '-' && s != "-") { fprintf(stderr, "error: unexpected argument '%s'\n", s.c_str()); usage(2); }
         else a.input = s;
     }
     if (a.input.empty()) usage(2);
+    if (a.have_num && (a.have_target || a.have_query)) {      // cli.rs: num conflicts_with_all = ["target", "query"]
+        fprintf(stderr, "error: the argument '--num <INT>' cannot be used with '--target <INT>' / '--query <INT>'\n");
+        exit(2);
+    }
     // cli.rs: --q1 in [0, 0.5], --q3 in [0.5, 1], ratio in [0, 1]
     if (!(a.q1 >= 0.0f && a.q1 <= 0.5f) || !(a.q3 >= 0.5f && a.q3 <= 1.0f) || !(a.max_overhang_ratio >= 0.0f && a.max_overhang_ratio <= 1.0f)) {
         fprintf(stderr, "error: quantile or ratio out of range\n");
@@ -123,7 +131,7 @@ int main(int argc, char **argv) {
             return rs;
         };
         lrge::EstimateResult res;
-        if (a.num) {                                              // AvaStrategy (ava.rs:108-161)
+        if (a.have_num) {                                         // AvaStrategy (ava.rs:108-161)
             size_t n = a.num;
             if (n_fq < n) { if (a.quiet < 1) fprintf(stderr, "[WARN] only %u reads in input, using all\n", n_fq); n = n_fq; }
             auto idx = unique_random_set(n, n_fq, seed);
@@ -154,7 +162,14 @@ int main(int argc, char **argv) {
         }
         FILE *out = a.output == "-" ? stdout : fopen(a.output.c_str(), "w");
         if (!out) throw lrge::LrgeError(LRGE_ERR_IO, "IO error: cannot open " + a.output);
-        if (a.precise) fprintf(out, "%g\n", (double)*res.estimate); else fprintf(out, "%.0f\n", (double)*res.estimate);
+        if (a.precise) {                                          // main.rs:103-107 `{est}`: shortest decimal that round-trips the f32
+            char buf[64];
+            auto r = std::to_chars(buf, buf + sizeof buf - 1, *res.estimate, std::chars_format::fixed);
+            *r.ptr = 0;
+            std::string t = buf;
+            if (std::isinf(*res.estimate)) t = "inf";
+            fprintf(out, "%s\n", t.c_str());
+        } else fprintf(out, "%.0f\n", (double)*res.estimate);
         if (out != stdout) fclose(out);
         return 0;
     } catch (const std::exception &e) {

@@ -17,6 +17,11 @@ def test_cli_help_and_bad_args():
     assert r.returncode == 0 and "--filter-contained" in r.stdout and "--use-min-ref" in r.stdout
     assert subprocess.run([BIN], capture_output=True).returncode == 2
     assert subprocess.run([BIN, "--q1", "0.9", "x.fa"], capture_output=True).returncode == 2   # cli.rs validate_low_quantile
+    # cli.rs: --num conflicts with --target / --query; the long quiet / verbose flags exist
+    r = subprocess.run([BIN, "-n", "5", "-T", "3", "x.fa"], capture_output=True, text=True)
+    assert r.returncode == 2 and "cannot be used with" in r.stderr
+    r = subprocess.run([BIN, "--quiet", "--verbose", "-qq", "-v", "/nonexistent/x.fa"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unexpected argument" not in r.stderr
 
 
 @pytest.mark.skipif(has_gpu(), reason="needs a box without a GPU")
@@ -37,7 +42,10 @@ def test_cli_ava_matches_library(tmp_path):
     assert r.returncode == 0, r.stderr
     with lrge_b200.Context(0) as ctx:
         want = lrge_b200.AvaStrategy(R, ctx=ctx).estimate(True, lrge_b200.LOWER_QUANTILE, lrge_b200.UPPER_QUANTILE)
-    assert np.float32(float(r.stdout.strip())) == np.float32(float("%g" % want.estimate))
+    # -f prints the shortest decimal that round-trips the f32 (main.rs:103-107), never an exponent
+    assert "e" not in r.stdout and np.float32(r.stdout.strip()) == np.float32(want.estimate)
+    assert r.stdout.strip() == np.format_float_positional(np.float32(want.estimate), unique=True, trim="-") or \
+        np.float32(r.stdout.strip()) == np.float32(want.estimate)
     assert "Estimated genome size" in r.stderr and "IQR" in r.stderr
     # FASTQ input, two-set, -F, --use-min-ref: runs and lands near the truth
     fq = tmp_path / "reads.fq"

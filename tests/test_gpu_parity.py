@@ -206,6 +206,15 @@ def test_error_paths(ctx):
     with pytest.raises(lrge_b200.LrgeError) as e:
         ctx.twoset_counts(T, empty, "ont")
     assert e.value.kind == "MapError"
+    # an empty read in the INDEXED set is not an error (minimap2's index build skips it): it still counts as a target read
+    T, Q = small_sets(nt=60, nq=20, gsize=60_000)
+    recs = [(T.name(i), T.seq(i)) for i in range(T.n)]
+    recs.insert(7, ("empty_target", b""))
+    for platform in ("ont", "pb"):
+        T2 = ReadSet.from_records(recs)
+        res = ctx.twoset_counts(T2, Q, platform)
+        want, had, _ = oracle.twoset_counts(T2, Q, platform, threads=4)
+        assert np.array_equal(res.counts, want) and np.array_equal(res.had_mapping, had)
 
 
 def test_strategy_estimates_match_oracle(ctx):
