@@ -236,4 +236,178 @@ __global__ void owner_overflow_kernel(const uint32_t *__restrict__ gcnt, uint32_
     if (slot < cap) out[slot] = gcnt[g];
 }
 
+
+// ---- sharded index, fast path: packed (key << 24 | count) entries, sizes kept on the device --------------------------
+// A rank's count saturates at 2^20 - 1 (> max_mid_occ = 10^6, so "count > mid_occ" and the occurrence histogram, whose
+// bins saturate at OCC_BINS - 1, are unaffected); the sum over <= 16 ranks stays inside the 24-bit field.
+constexpr int PK_SHIFT = 24;
+constexpr uint64_t PK_CMAX = (1ull << 20) - 1;
+constexpr uint64_t PK_FIELD = (1ull << PK_SHIFT) - 1;
+constexpr uint64_t PK_SENTINEL = ~0ull;
+
+// one thread per run: packed entry; U and the run starts come from DeviceSelect (device side), the last run ends at M
+__global__ void rle_pack_kernel(const uint64_t *__restrict__ tx, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ U_dev,
+                                uint64_t M, uint64_t *__restrict__ out) {
+    const uint32_t U = *U_dev;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= U) return;
+    const uint64_t s0 = starts[i], s1 = i + 1 < U ? (uint64_t)starts[i + 1] : M;
+    const uint64_t n = s1 - s0;
+    out[i] = (tx[s0] >> 8) << PK_SHIFT | (n < PK_CMAX ? n : PK_CMAX);
+}
+
+// bounds[d] = first packed entry whose key belongs to owner >= d (d in [0, W]); sendc[d] = entries for owner d
+__global__ void owner_bounds_dev_kernel(const uint64_t *__restrict__ pk, const uint32_t *__restrict__ U_dev, int W, int kbits,
+                                        unsigned long long *bounds, unsigned long long *sendc) {
+    __shared__ unsigned long long sb[64];
+    const uint32_t U = *U_dev;
+    const int d = threadIdx.x;
+    if (d <= W) {
+        const uint64_t first = d == W ? ~0ull : (((uint64_t)d << kbits) + W - 1) / (uint64_t)W;
+        uint32_t lo = 0, hi = U;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((pk[mid] >> PK_SHIFT) < first) lo = mid + 1; else hi = mid; }
+        sb[d] = d == W ? U : lo;
+        bounds[d] = sb[d];
+    }
+    __syncthreads();
+    if (d < W) sendc[d] = sb[d + 1] - sb[d];
+}
+
+// owner side: the received packed entries are W runs, each sorted by key, holding every rank's distinct keys of this
+// owner's key range (<= W entries per key).  The range is cut into slices of equal key width; a CTA binary-searches its
+// slice in every run, pulls the W sub-runs (contiguous, coalesced) into a SHARED-MEMORY open-addressing table of packed
+// words (claim an empty slot with one 64-bit CAS; a slot already holding the key takes the count with one atomicAdd on
+// the same word) and reads the summed counts back: streaming HBM reads, no sort, no global atomics per entry.
+// A slice that does not fit the table is halved until it does (a single key never exceeds W entries).
+// MODE 0: occurrence histogram of the global counts (hist[OCC_BINS] counts the keys).
+// MODE 1: keys whose global count exceeds mid_occ (meta[0]) -> blacklist (unordered); meta[2] set if it does not fit cap.
+constexpr int OM_THREADS = 256;
+constexpr int OM_SLOTS = 4096;             // 32 KB of shared memory: several CTAs per SM hide the load latency
+constexpr int OM_HBINS = 64;               // counts below this go through a shared-memory histogram, the rest straight to global
+constexpr int OM_CAP = OM_SLOTS / 2;
+constexpr int OM_MAXW = 16;
+
+struct OwnerMergeArgs {
+    const uint64_t *rk;                    // received runs, run w = rk[roff[w] .. roff[w + 1])
+    uint64_t roff[OM_MAXW + 1];
+    int W;
+    uint64_t klo, khi;                     // this owner's key range
+    uint64_t slice_w;                      // keys per CTA slice
+    const uint32_t *cuts;                  // [run][slice + 1]: first entry of run w (relative to roff[w]) with key >= slice start
+    uint32_t n_slices;
+    unsigned long long *hist;              // MODE 0
+    const unsigned long long *meta;        // MODE 1: meta[0] = mid_occ
+    uint64_t *bl; unsigned long long *bl_n; uint64_t bl_cap; unsigned long long *bl_ovf;
+};
+
+// cuts[w][p] for every run and slice boundary: one thread per binary search
+__global__ void owner_cuts_kernel(OwnerMergeArgs A, uint32_t *__restrict__ cuts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t per = (uint64_t)A.n_slices + 1;
+    if (i >= per * A.W) return;
+    const int w = (int)(i / per);
+    const uint64_t p = i % per;
+    const uint64_t key = min(A.klo + p * A.slice_w, A.khi);
+    uint64_t lo = A.roff[w], hi = A.roff[w + 1];
+    while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((A.rk[mid] >> PK_SHIFT) < key) lo = mid + 1; else hi = mid; }
+    cuts[i] = (uint32_t)(lo - A.roff[w]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(OM_THREADS) owner_merge_kernel(OwnerMergeArgs A) {
+    __shared__ __align__(16) unsigned long long om_table[OM_SLOTS];
+    __shared__ unsigned int sh[OM_HBINS];
+    __shared__ uint64_t s_lo[OM_MAXW], s_hi[OM_MAXW];
+    __shared__ uint32_t s_pre[OM_MAXW + 1];
+    const uint32_t tid = threadIdx.x;
+    if (MODE == 0) for (int i = tid; i < OM_HBINS; i += OM_THREADS) sh[i] = 0;
+    unsigned int my_keys = 0;
+    const uint64_t slice_lo = A.klo + (uint64_t)blockIdx.x * A.slice_w;
+    const uint64_t slice_hi = min(slice_lo + A.slice_w, A.khi);
+    auto lower = [&](int w, uint64_t key) -> uint64_t {                // first entry of run w with key >= `key`
+        uint64_t lo = A.roff[w], hi = A.roff[w + 1];
+        while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if ((A.rk[mid] >> PK_SHIFT) < key) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    uint64_t a = slice_lo;
+    while (a < slice_hi) {
+        uint64_t b = slice_hi;
+        uint32_t n = 0;
+        for (;;) {
+            __syncthreads();
+            if (tid < (uint32_t)A.W) {
+                const uint32_t *cw = A.cuts + (uint64_t)tid * (A.n_slices + 1) + blockIdx.x;
+                s_lo[tid] = a == slice_lo ? A.roff[tid] + cw[0] : lower((int)tid, a);        // slice boundaries are precomputed
+                s_hi[tid] = b == slice_hi ? A.roff[tid] + cw[1] : lower((int)tid, b);
+            }
+            __syncthreads();
+            if (tid == 0) { uint32_t run = 0; for (int w = 0; w < A.W; ++w) { s_pre[w] = run; run += (uint32_t)min(s_hi[w] - s_lo[w], (uint64_t)0x7fffffff); } s_pre[A.W] = run; }
+            __syncthreads();
+            n = s_pre[A.W];
+            if (n <= (uint32_t)OM_CAP || b - a <= 1) break;
+            b = a + (b - a) / 2;
+        }
+        for (int i = tid; i < OM_SLOTS; i += OM_THREADS) om_table[i] = 0ull;
+        __syncthreads();
+        for (uint32_t j = tid; j < n; j += OM_THREADS) {
+            int w = 0;
+            while (w + 1 < A.W && j >= s_pre[w + 1]) ++w;
+            const unsigned long long e = A.rk[s_lo[w] + (j - s_pre[w])];
+            const uint64_t key = e >> PK_SHIFT;
+            uint32_t s = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40) & (OM_SLOTS - 1);
+            for (;;) {
+                unsigned long long cur = om_table[s];
+                if (cur == 0ull) { cur = atomicCAS(&om_table[s], 0ull, e); if (cur == 0ull) break; }
+                if ((cur >> PK_SHIFT) == key) { atomicAdd(&om_table[s], e & PK_FIELD); break; }
+                s = (s + 1) & (OM_SLOTS - 1);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < OM_SLOTS; i += OM_THREADS) {
+            const unsigned long long e = om_table[i];
+            if (e == 0ull) continue;
+            const uint64_t g = e & PK_FIELD;
+            if (MODE == 0) {
+                if (g < OM_HBINS) atomicAdd(&sh[g], 1u);
+                else atomicAdd(&A.hist[g < OCC_BINS - 1 ? g : OCC_BINS - 1], 1ull);
+                ++my_keys;
+            }
+            else if (g > A.meta[0]) {
+                const unsigned long long slot = atomicAdd(A.bl_n, 1ull);
+                if (slot < A.bl_cap) A.bl[slot] = e >> PK_SHIFT; else *A.bl_ovf = 1;
+            }
+        }
+        a = b;
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        for (int i = tid; i < OM_HBINS; i += OM_THREADS)
+            if (sh[i]) atomicAdd(&A.hist[i], (unsigned long long)sh[i]);
+        for (int o = 16; o > 0; o >>= 1) my_keys += __shfl_down_sync(0xffffffffu, my_keys, o);
+        if ((tid & 31) == 0 && my_keys) atomicAdd(&A.hist[OCC_BINS], (unsigned long long)my_keys);
+    }
+}
+
+// mm_idx_cal_max_occ + mm_mapopt_update on the (all-reduced) histogram, on the device: meta[0] = mid_occ,
+// meta[1] = 1 if the rank lies in the overflow bin (the exact host path must run), meta[2] is the blacklist overflow flag.
+__global__ void mid_occ_kernel(const unsigned long long *__restrict__ hist, float mid_occ_frac, int min_mid_occ, int max_mid_occ,
+                               unsigned long long *meta) {
+    if (threadIdx.x || blockIdx.x) return;
+    const unsigned long long n_keys = hist[OCC_BINS];
+    long long mid = 0x7fffffff;
+    unsigned long long need_exact = 0;
+    if (n_keys) {
+        const unsigned long long rank = (unsigned int)((1. - (double)mid_occ_frac) * (double)n_keys);
+        unsigned long long cum = 0;
+        long long val = -1;
+        for (int b = 0; b < OCC_BINS - 1; ++b) { cum += hist[b]; if (cum > rank) { val = b; break; } }
+        if (val < 0) need_exact = 1;
+        mid = val + 1;
+        if (mid < min_mid_occ) mid = min_mid_occ;
+        if (max_mid_occ > min_mid_occ && mid > max_mid_occ) mid = max_mid_occ;
+    }
+    meta[0] = (unsigned long long)mid;
+    meta[1] = need_exact;
+}
+
 }  // namespace lrge

@@ -179,6 +179,7 @@ struct lrge_staged {
     std::vector<std::pair<uint64_t, uint32_t>> name_hash;   // (FNV-1a of the name, read), sorted: cheap equality joins
     bool names_unique = true;
     bool has_empty = false;                                // a zero-length read: the index build skips it, mapping it is an error
+    const lrge_readset *names_src = nullptr;               // host-buffer calls: names are analysed later, while the GPU sketches
     std::vector<uint32_t> lex_rank;                        // lazily: lexicographic rank of each name (AVA's strcmp order)
     std::vector<uint32_t> len_order;                       // reads, longest first (work order of the fused map kernel)
     cudaEvent_t ready = nullptr;                           // async staging: recorded on the copy stream after the H2D copies
@@ -226,6 +227,13 @@ struct lrge_ctx {
     bool sketch_two_pass = false;          // LRGE_SKETCH_TWO_PASS=1: count + emit instead of stage + compact
     bool sketch_legacy = false;            // LRGE_SKETCH_LEGACY=1: pack + warp-shuffle sketch + compact instead of the lane-serial kernel
     DevBuf tile_read;                      // lane-serial sketch: tile -> entry
+    // small device -> host results land in PINNED memory: a cudaMemcpyAsync into pageable memory blocks the host until
+    // the stream gets there, which would turn every "queue the copy, sync later" below into a sync on the spot
+    uint8_t *pin2 = nullptr;               // sharded index: bounds + send-count matrix, then mid_occ / flags / totals (32 x 33 + 8 u64)
+    uint8_t *pin = nullptr;                // [0] sketch total [4] sketch overflow [64..] occurrence histogram, (OCC_BINS + 2) x u64
+    uint32_t &sk_total() { return *reinterpret_cast<uint32_t *>(pin); }
+    uint32_t &sk_ovf() { return *reinterpret_cast<uint32_t *>(pin + 4); }
+    unsigned long long *hist_h() { return reinterpret_cast<unsigned long long *>(pin + 64); }
     size_t free_at_create = 0, held_at_create = 0;
     DevBuf stg_x, stg_y, xflag;
     lrge_staged tmp_a, tmp_b;              // device staging of the host-buffer entry points (reused across calls)
@@ -262,8 +270,38 @@ inline void shard_range(uint32_t n, int rank, int world, uint32_t *lo, uint32_t 
 // names and lengths of ALL reads are kept on the host side either way.  async: return without waiting -- the first
 // kernel that touches the set waits for `ready` on the compute stream, so the copy of the second set overlaps the
 // sketch of the first.
+// Host-side analysis of a staged set that no kernel launch depends on: work order by length, name copies, name hashes
+// (duplicate detection, shared names).  The host-buffer entry points defer it until the first sketch is in flight.
+void finish_staging(lrge_staged *s) {
+    const lrge_readset *rs = s->names_src;
+    if (!rs) return;
+    s->names_src = nullptr;
+    s->len_order.resize(rs->n);
+    std::iota(s->len_order.begin(), s->len_order.end(), 0u);
+    std::stable_sort(s->len_order.begin(), s->len_order.end(), [&](uint32_t a, uint32_t b) { return s->h_len[a] > s->h_len[b]; });
+    s->name_off.assign(rs->name_off, rs->name_off + rs->n + 1);
+    s->names.assign(rs->names + rs->name_off[0], rs->names + rs->name_off[rs->n]);
+    if (rs->n && rs->name_off[0] != 0) { const uint32_t b = rs->name_off[0]; for (auto &o : s->name_off) o -= b; }
+    // name hashes: equal names <=> equal hashes (verified); the usual case "all names distinct" needs no string sort
+    s->name_hash.resize(rs->n);
+    for (uint32_t i = 0; i < rs->n; ++i) {
+        uint64_t h = 1469598103934665603ull;
+        for (uint32_t j = s->name_off[i]; j < s->name_off[i + 1]; ++j) h = (h ^ (uint8_t)s->names[j]) * 1099511628211ull;
+        s->name_hash[i] = {h, i};
+    }
+    std::sort(s->name_hash.begin(), s->name_hash.end());
+    s->names_unique = true;
+    s->lex_rank.clear();
+    for (uint32_t i = 1; i < rs->n && s->names_unique; ++i)
+        if (s->name_hash[i].first == s->name_hash[i - 1].first) {
+            const uint32_t a = s->name_hash[i - 1].second, b = s->name_hash[i].second;
+            const uint32_t la = s->name_off[a + 1] - s->name_off[a], lb = s->name_off[b + 1] - s->name_off[b];
+            if (la == lb && memcmp(s->names.data() + s->name_off[a], s->names.data() + s->name_off[b], la) == 0) s->names_unique = false;
+        }
+}
+
 void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool async = false, uint32_t blk_first = 0,
-                   uint32_t blk_count = 0xffffffffu) {
+                   uint32_t blk_count = 0xffffffffu, bool defer_names = false) {
     s->n = rs->n;
     s->total_bases = rs->n ? rs->off[rs->n] - rs->off[0] : 0;
     s->pending = false;
@@ -312,28 +350,8 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool asy
         s->h_len[i] = (uint32_t)l;
         s->max_len = std::max(s->max_len, (uint32_t)l);
     }
-    s->len_order.resize(rs->n);
-    std::iota(s->len_order.begin(), s->len_order.end(), 0u);
-    std::stable_sort(s->len_order.begin(), s->len_order.end(), [&](uint32_t a, uint32_t b) { return s->h_len[a] > s->h_len[b]; });
-    s->name_off.assign(rs->name_off, rs->name_off + rs->n + 1);
-    s->names.assign(rs->names + rs->name_off[0], rs->names + rs->name_off[rs->n]);
-    if (rs->n && rs->name_off[0] != 0) { const uint32_t b = rs->name_off[0]; for (auto &o : s->name_off) o -= b; }
-    // name hashes: equal names <=> equal hashes (verified); the usual case "all names distinct" needs no string sort
-    s->name_hash.resize(rs->n);
-    for (uint32_t i = 0; i < rs->n; ++i) {
-        uint64_t h = 1469598103934665603ull;
-        for (uint32_t j = s->name_off[i]; j < s->name_off[i + 1]; ++j) h = (h ^ (uint8_t)s->names[j]) * 1099511628211ull;
-        s->name_hash[i] = {h, i};
-    }
-    std::sort(s->name_hash.begin(), s->name_hash.end());
-    s->names_unique = true;
-    s->lex_rank.clear();
-    for (uint32_t i = 1; i < rs->n && s->names_unique; ++i)
-        if (s->name_hash[i].first == s->name_hash[i - 1].first) {
-            const uint32_t a = s->name_hash[i - 1].second, b = s->name_hash[i].second;
-            const uint32_t la = s->name_off[a + 1] - s->name_off[a], lb = s->name_off[b + 1] - s->name_off[b];
-            if (la == lb && memcmp(s->names.data() + s->name_off[a], s->names.data() + s->name_off[b], la) == 0) s->names_unique = false;
-        }
+    s->names_src = rs;
+    if (!defer_names) finish_staging(s);
     if (async) {
         if (!s->ready) CUDA_CHECK(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventRecord(s->ready, c->copy_stream));
@@ -354,8 +372,18 @@ __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32
 
 // K1, lane-serial form (kernels_sketch.cuh: sketch2_kernel): ava-ont only (no HPC, k = 15).  One launch per staged
 // chunk straight from the ASCII bases (no pack kernel), staging slots + compact_kernel as in the single-pass path.
-// Returns false if a sub-tile overflowed its slot (very dense reads): the caller falls back to the exact two-pass path.
-bool sketch_readset2(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first, uint32_t count) {
+// sketch2_begin launches and returns without waiting (false: not applicable / no room, nothing launched); sketch2_end
+// waits for the minimizer total, then packs.  It returns false if a sub-tile overflowed its slot (very dense reads):
+// the caller falls back to the exact two-pass path.
+struct Sketch2Job { bool active = false; uint32_t n = 0, nw = 0; Sketch *out = nullptr; };
+
+bool sketch2_begin(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first, uint32_t count, Sketch2Job *job) {
+    job->active = false;
+    if (o.is_hpc || o.k != 15 || c->sketch_legacy) return false;
+    if (first > s->n) first = s->n;
+    if (count > s->n - first) count = s->n - first;
+    if (count && (first < s->blk_first || first + count > s->blk_first + s->blk_count))
+        throw std::runtime_error("internal: sketch of reads that were not staged");
     const uint32_t n = count;
     std::vector<uint64_t> soff(n);
     std::vector<uint32_t> tile_off((size_t)n + 1), slen(n), rid_map(n);
@@ -387,7 +415,8 @@ bool sketch_readset2(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch 
     out->M = 0;
     c->wcnt.reserve(((size_t)nw + 1) * 4);
     c->woff.reserve(((size_t)nw + 1) * 4);
-    if (tiles == 0) { CUDA_CHECK(cudaMemsetAsync(out->moff.p, 0, ((size_t)n + 1) * 4, c->stream)); c->prof.send(ST_SKETCH); return true; }
+    job->n = n; job->nw = nw; job->out = out; job->active = true;
+    if (tiles == 0) { CUDA_CHECK(cudaMemsetAsync(out->moff.p, 0, ((size_t)n + 1) * 4, c->stream)); c->sk_total() = 0; c->sk_ovf() = 0; c->prof.send(ST_SKETCH); return true; }
     c->stg_x.reserve(stage_bytes / 2 + 64); c->stg_y.reserve(stage_bytes / 2 + 64);
     c->xflag.reserve(16);
     CUDA_CHECK(cudaMemsetAsync(c->xflag.p, 0, 16, c->stream));
@@ -421,11 +450,20 @@ bool sketch_readset2(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch 
     cub::DeviceScan::ExclusiveSum(nullptr, tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream);
     KLAUNCH(c, "cub::DeviceScan(u32)", 8.0 * nw,
             cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>(), c->woff.as<uint32_t>(), nw + 1, c->stream));
-    uint32_t total = 0, ovf = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&total, c->woff.as<uint32_t>() + nw, 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(&ovf, c->xflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&c->sk_total(), c->woff.as<uint32_t>() + nw, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&c->sk_ovf(), c->xflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->prof.send(ST_SKETCH);
+    return true;
+}
+
+bool sketch2_end(lrge_ctx *c, const Sketch2Job &job) {
+    Sketch *out = job.out;
+    const uint32_t n = job.n, nw = job.nw;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (ovf) { c->prof.send(ST_SKETCH); return false; }
+    if (nw == 0) return true;
+    if (c->sk_ovf()) return false;
+    const uint32_t total = c->sk_total();
+    c->prof.sbegin(ST_SKETCH);
     out->M = total;
     out->x.reserve(((size_t)total + 1) * 8);
     out->y.reserve(((size_t)total + 1) * 8);
@@ -442,12 +480,14 @@ bool sketch_readset2(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch 
 }
 
 // K0 + K1: sketch a staged read set, or only its reads [first, first + count), into `out`
-void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first = 0, uint32_t count = 0xffffffffu) {
+void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first = 0, uint32_t count = 0xffffffffu,
+                    bool skip_fast = false) {
     if (first > s->n) first = s->n;
     if (count > s->n - first) count = s->n - first;
     if (count && (first < s->blk_first || first + count > s->blk_first + s->blk_count))
         throw std::runtime_error("internal: sketch of reads that were not staged");
-    if (!o.is_hpc && o.k == 15 && !c->sketch_legacy && sketch_readset2(c, s, o, out, first, count)) return;
+    if (skip_fast) { /* the caller already tried the lane-serial kernel */ }
+    else { Sketch2Job job; if (sketch2_begin(c, s, o, out, first, count, &job) && sketch2_end(c, job)) return; }
     const bool subset = first != 0 || count != s->n;
     const uint32_t n = count;
     std::vector<uint64_t> poff(n), soff(n);
@@ -585,8 +625,10 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
 
 struct BuiltIndex { IndexView view; int mid_occ; uint64_t n_keys; };
 
-// K2 + K3
-BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
+// K2 + K3.  build_index_launch queues the sort, the bucket table and the occurrence histogram (+ its copy to pinned
+// host memory) and returns; build_index_finish -- after any later synchronisation of the stream -- turns the histogram
+// into mid_occ on the host.  Nothing in between may depend on mid_occ (the sketch of the streamed set does not).
+BuiltIndex build_index_launch(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     BuiltIndex B{};
     const uint64_t M = sk.M;
     if (M >= (1ull << 32) - 2) throw std::length_error("more than 2^32 target minimizers per GPU are not supported");
@@ -616,10 +658,19 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     c->tk32.reserve((M + 64) * 4);
     KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
             index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(), hist));
-    std::vector<unsigned long long> h(OCC_BINS + 2);
-    CUDA_CHECK(cudaMemcpyAsync(h.data(), hist, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->hist_h(), hist, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaGetLastError());
+    B.view.tx = c->tx.as<uint64_t>(); B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
+    B.mid_occ = -1; B.n_keys = 0;
+    return B;
+}
+
+void build_index_finish(lrge_ctx *c, const MapOpt &o, BuiltIndex *Bp) {       // the stream has been synchronised since the launch
+    BuiltIndex &B = *Bp;
+    const uint64_t M = B.view.M;
+    const unsigned long long *h = c->hist_h();
+    unsigned long long *hist = c->hist.as<unsigned long long>();
     const uint64_t n_keys = h[OCC_BINS];
     int mid_occ;
     if (n_keys == 0) mid_occ = INT32_MAX;
@@ -643,9 +694,13 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     }
     if (mid_occ < o.min_mid_occ) mid_occ = o.min_mid_occ;
     if (o.max_mid_occ > o.min_mid_occ && mid_occ > o.max_mid_occ) mid_occ = o.max_mid_occ;
-    B.view.tx = c->tx.as<uint64_t>(); B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
-    B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
     B.mid_occ = mid_occ; B.n_keys = n_keys;
+}
+
+BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
+    BuiltIndex B = build_index_launch(c, sk, o);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    build_index_finish(c, o, &B);
     return B;
 }
 
@@ -655,7 +710,7 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
 // Exact global occurrence counts: distinct local keys (key, count) go to the rank owning their key range,
 // are summed there, the occurrence histogram is all-reduced (=> the same mid_occ on every rank), and the keys
 // above mid_occ come back as a blacklist marked in a bitmap over the local runs.
-BuiltIndex build_index_sharded(lrge_ctx *c, const Sketch &sk, const MapOpt &o, lrge_stats *S) {
+BuiltIndex build_index_sharded_exact(lrge_ctx *c, const Sketch &sk, const MapOpt &o, lrge_stats *S) {
     BuiltIndex B{};
     const int W = c->world, me = c->rank;
     const uint64_t M = sk.M;
@@ -816,6 +871,155 @@ BuiltIndex build_index_sharded(lrge_ctx *c, const Sketch &sk, const MapOpt &o, l
     return B;
 }
 
+// The same, fast path: ONE host synchronisation (the W x W matrix of send counts, which ncclSend/ncclRecv need on the
+// host), hidden behind `while_waiting` (the caller launches the sketch of the streamed set there).  Packed
+// (key << 24 | count) entries, one array per exchange; the owner sorts keys only; mid_occ is computed on the device from
+// the all-reduced histogram; results (mid_occ, key / minimizer totals, fallback flags, all-reduced so that every rank
+// decides alike) land in pinned memory and are read by build_index_sharded_finish after the caller's next
+// synchronisation.  Flags set = rank in the overflow bin or blacklist above its buffer: the exact path above runs.
+struct ShardedJob { BuiltIndex B; bool active = false; };
+
+// bl_cap: blacklist entries per rank in the all-gather -- MUST be the same number on every rank (derive it from a
+// quantity all ranks share, not from the local minimizer count).
+template <typename F>
+ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOpt &o, uint64_t bl_cap, F while_waiting) {
+    ShardedJob J;
+    BuiltIndex &B = J.B;
+    const int W = c->world, me = c->rank;
+    const uint64_t M = sk.M;
+    if (M >= (1ull << 32) - 2) throw std::length_error("more than 2^32 target minimizers per GPU are not supported");
+    if (W > 16) throw std::length_error("more than 16 ranks are not supported");
+    c->tx.reserve((M + 1) * 8);
+    c->ty.reserve((M + 1) * 8);
+    size_t tb = 0;
+    if (M) {
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
+        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", 32.0 * M,
+                cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                                c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
+        c->launches += (2 * o.k + 7) / 8;
+        c->prof.set_passes("cub::DeviceRadixSort(index: u64 key, u64 value)", (2 * o.k + 7) / 8);
+    }
+    int bits = 8;
+    while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
+    if (bits < 2 * o.k - 32) bits = 2 * o.k - 32;
+    const uint32_t nb = 1u << bits;
+    const int shift = 8 + 2 * o.k - bits;
+    c->boff.reserve(((size_t)nb + 2) * 4);
+    c->hist.reserve((OCC_BINS + 2) * 8);
+    CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));      // local histogram: unused here
+    c->tk32.reserve((M + 64) * 4);
+    KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
+            index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(),
+                                                              c->hist.as<unsigned long long>()));
+    // distinct local keys, packed with their counts, in key order
+    c->flags.reserve(M + 1);
+    c->pstart.reserve((M + 2) * 4);
+    c->npairs.reserve(16);
+    c->ukey.reserve((M + 1) * 8);
+    CUDA_CHECK(cudaMemsetAsync(c->npairs.p, 0, 16, c->stream));
+    if (M) {
+        KLAUNCH(c, "run_flag_kernel", 9.0 * M, run_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, 8, c->flags.as<uint8_t>()));
+        cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
+                                   c->npairs.as<uint32_t>(), (int64_t)M, c->stream);
+        KLAUNCH(c, "cub::DeviceSelect(run starts)", 5.0 * M,
+                cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
+                                           c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)M, c->stream));
+        KLAUNCH(c, "rle_pack_kernel", 20.0 * M,
+                rle_pack_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), M,
+                                                                                    c->ukey.as<uint64_t>()));
+    }
+    // xmeta: bounds[W+1] | sendc[W] | mat[W*W] | hist[OCC_BINS+2] | meta[8]
+    c->xmeta.reserve(((size_t)(2 * W + 1) + (size_t)W * W + OCC_BINS + 2 + 8) * 8 + 64);
+    unsigned long long *bounds_d = c->xmeta.as<unsigned long long>();
+    unsigned long long *sendc_d = bounds_d + (W + 1);
+    unsigned long long *mat_d = sendc_d + W;
+    unsigned long long *hist_d = mat_d + (size_t)W * W;
+    unsigned long long *meta_d = hist_d + OCC_BINS + 2;          // [0] mid_occ [1] need exact [2] blacklist overflow [3] blacklist length
+    owner_bounds_dev_kernel<<<1, 64, 0, c->stream>>>(c->ukey.as<uint64_t>(), c->npairs.as<uint32_t>(), W, 2 * o.k, bounds_d, sendc_d);
+    ++c->launches;
+    NCCL_CHECK(ncclAllGather(sendc_d, mat_d, W, ncclUint64, c->comm, c->stream));
+    unsigned long long *pin64 = reinterpret_cast<unsigned long long *>(c->pin2);   // bounds[W+1] then mat[W*W]
+    CUDA_CHECK(cudaMemcpyAsync(pin64, bounds_d, (size_t)(W + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(pin64 + W + 1, mat_d, (size_t)W * W * 8, cudaMemcpyDeviceToHost, c->stream));
+    while_waiting();                                               // e.g. launch the sketch of the streamed set
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    std::vector<uint64_t> bounds(pin64, pin64 + W + 1), roff(W + 1, 0);
+    const unsigned long long *mat = pin64 + W + 1;
+    for (int s2 = 0; s2 < W; ++s2) roff[s2 + 1] = roff[s2] + mat[(size_t)s2 * W + me];
+    const uint64_t R = roff[W];
+    if (R >= (1ull << 32) - 2) throw std::length_error("too many distinct keys per owner rank");
+    c->rkey.reserve((R + 1) * 8);
+    c->prof.kbegin("ncclSend/Recv(key ranges)", 8.0 * R);
+    NCCL_CHECK(ncclGroupStart());
+    for (int d = 0; d < W; ++d) {
+        const uint64_t sc = bounds[d + 1] - bounds[d];
+        if (sc) NCCL_CHECK(ncclSend(c->ukey.as<uint64_t>() + bounds[d], sc, ncclUint64, d, c->comm, c->stream));
+    }
+    for (int s2 = 0; s2 < W; ++s2)
+        if (roff[s2 + 1] > roff[s2]) NCCL_CHECK(ncclRecv(c->rkey.as<uint64_t>() + roff[s2], roff[s2 + 1] - roff[s2], ncclUint64, s2, c->comm, c->stream));
+    NCCL_CHECK(ncclGroupEnd());
+    c->prof.kend();
+    // owner: sum the <= W partial counts of every key (owner_merge_kernel: slices of the key range through a
+    // shared-memory table), histogram of the sums
+    CUDA_CHECK(cudaMemsetAsync(hist_d, 0, (OCC_BINS + 2 + 8) * 8, c->stream));
+    OwnerMergeArgs OA{};
+    OA.rk = c->rkey.as<uint64_t>(); OA.W = W;
+    for (int s2 = 0; s2 <= W; ++s2) OA.roff[s2] = roff[s2];
+    const int kbits = 2 * o.k;
+    OA.klo = (((uint64_t)me << kbits) + W - 1) / (uint64_t)W;
+    OA.khi = me + 1 == W ? (1ull << kbits) : (((uint64_t)(me + 1) << kbits) + W - 1) / (uint64_t)W;
+    const uint64_t n_slices = std::max<uint64_t>(1, std::min<uint64_t>(R / (OM_CAP * 3 / 4) + 1, OA.khi - OA.klo));   // ~6k entries per slice (table: OM_CAP)
+    OA.slice_w = (OA.khi - OA.klo + n_slices - 1) / n_slices;
+    OA.hist = hist_d; OA.meta = meta_d;
+    const size_t om_smem = 0;
+    const unsigned om_grid = (unsigned)((OA.khi - OA.klo + OA.slice_w - 1) / OA.slice_w);
+    OA.n_slices = om_grid;
+    c->ucnt.reserve(((size_t)om_grid + 1) * W * 4);
+    OA.cuts = c->ucnt.as<uint32_t>();
+    if (R) KLAUNCH(c, "owner_cuts_kernel", 4.0 * (om_grid + 1) * W,
+                   owner_cuts_kernel<<<(unsigned)(((uint64_t)(om_grid + 1) * W + 255) / 256), 256, 0, c->stream>>>(OA, c->ucnt.as<uint32_t>()));
+    if (R) KLAUNCH(c, "owner_merge_kernel<hist>", 8.0 * R, owner_merge_kernel<0><<<om_grid, OM_THREADS, om_smem, c->stream>>>(OA));
+    const unsigned long long extra = M;
+    CUDA_CHECK(cudaMemcpyAsync(hist_d + OCC_BINS + 1, &extra, 8, cudaMemcpyHostToDevice, c->stream));
+    NCCL_CHECK(ncclAllReduce(hist_d, hist_d, OCC_BINS + 2, ncclUint64, ncclSum, c->comm, c->stream));
+    mid_occ_kernel<<<1, 32, 0, c->stream>>>(hist_d, o.mid_occ_frac, o.min_mid_occ, o.max_mid_occ, meta_d);
+    ++c->launches;
+    // blacklist: owned keys above mid_occ -> everyone -> bitmap over the local runs
+    const uint64_t cap_bl = bl_cap;
+    c->blist.reserve(cap_bl * 8); c->blall.reserve(cap_bl * 8 * W);
+    CUDA_CHECK(cudaMemsetAsync(c->blist.p, 0xff, cap_bl * 8, c->stream));
+    OA.bl = c->blist.as<uint64_t>(); OA.bl_n = meta_d + 3; OA.bl_cap = cap_bl; OA.bl_ovf = meta_d + 2;
+    if (R) KLAUNCH(c, "owner_merge_kernel<select>", 8.0 * R, owner_merge_kernel<1><<<om_grid, OM_THREADS, om_smem, c->stream>>>(OA));
+    NCCL_CHECK(ncclAllGather(c->blist.p, c->blall.p, cap_bl, ncclUint64, c->comm, c->stream));
+    NCCL_CHECK(ncclAllReduce(meta_d + 1, meta_d + 1, 2, ncclUint64, ncclMax, c->comm, c->stream));     // fallback flags: every rank alike
+    c->blmap.reserve((M / 32 + 2) * 4);
+    CUDA_CHECK(cudaMemsetAsync(c->blmap.p, 0, (M / 32 + 2) * 4, c->stream));
+    B.view.tx = c->tx.as<uint64_t>(); B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
+    KLAUNCH(c, "bl_mark_kernel", 8.0 * cap_bl * W,
+            bl_mark_kernel<<<(unsigned)((cap_bl * W + 255) / 256), 256, 0, c->stream>>>(c->blall.as<uint64_t>(), cap_bl * W, B.view, c->blmap.as<uint32_t>()));
+    CUDA_CHECK(cudaGetLastError());
+    B.view.bl = c->blmap.as<uint32_t>();
+    // results for build_index_sharded_finish: meta[0..2], then n_keys and the minimizer total of all shards
+    CUDA_CHECK(cudaMemcpyAsync(pin64, meta_d, 24, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(pin64 + 3, hist_d + OCC_BINS, 16, cudaMemcpyDeviceToHost, c->stream));
+    B.mid_occ = -1; B.n_keys = 0;
+    J.active = true;
+    return J;
+}
+
+// after a synchronisation of the stream: false = one of the fallback conditions held on some rank (run the exact path)
+bool build_index_sharded_finish(lrge_ctx *c, ShardedJob *J, lrge_stats *S) {
+    const unsigned long long *r = reinterpret_cast<const unsigned long long *>(c->pin2);
+    if (r[1] || r[2]) return false;
+    J->B.mid_occ = (int)r[0];
+    J->B.n_keys = r[3];
+    if (S) S->n_target_minimizers = r[4];
+    return true;
+}
+
 // lexicographic name ranks over the union of two sets (equal names share a rank)
 struct NameRanks { std::vector<uint32_t> a, b; bool a_unique = true, b_unique = true, shared = false; };
 NameRanks rank_names(const lrge_staged *A, const lrge_staged *B) {
@@ -867,7 +1071,22 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     S.n_target_bases = idx->total_bases; S.n_query_bases = str->total_bases;
     const uint32_t launches0 = c->launches;
 
+    // K0/K1 on the indexed set first: its kernels run while the host analyses the read names below.  With a
+    // communicator the index itself is sharded: this rank sketches only its block of targets (shard_range) and the
+    // occurrence filter is made exact by build_index_sharded.
+    const int world = std::max(opts.shard_count, 1);
+    const bool sharded_index = c->comm != nullptr && world > 1;
+    if (sharded_index && (world != c->world || opts.shard_index != c->rank))
+        throw std::runtime_error("shard_index/shard_count do not match the communicator");
+    uint32_t i0 = 0, i1 = idx->n;
+    if (sharded_index) shard_range(idx->n, c->rank, world, &i0, &i1);
+    Sketch2Job job_idx;
+    const bool fast_idx = sketch2_begin(c, idx, o, &c->sk_idx, i0, i1 - i0, &job_idx);
+
     // names -> ranks.  Only equality (two-set: NO_DIAG, HashSet<name>) or strcmp order (AVA: NO_DUAL) is ever used.
+    finish_staging(idx);
+    finish_staging(str);
+    struct Drain { lrge_ctx *c; bool armed; ~Drain() { if (armed) cudaStreamSynchronize(c->stream); } } drain{c, true};   // D2H targets live in ctx
     if ((mode == MODE_AVA || mode == MODE_INVERSE) && !idx->names_unique) throw std::domain_error("DuplicateReadIdentifier");
     NameRanks R;
     if (mode == MODE_AVA) {
@@ -898,33 +1117,42 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         } else R = rank_names(idx, str);
     }
     const std::vector<uint32_t> &rank_idx = R.a, &rank_str = mode == MODE_AVA ? R.a : R.b;
+    drain.armed = false;
 
-    // K0/K1 on the indexed set, K2/K3.  With a communicator the index itself is sharded: this rank sketches only
-    // its block of targets (shard_range) and the occurrence filter is made exact by build_index_sharded.
-    const int world = std::max(opts.shard_count, 1);
-    const bool sharded_index = c->comm != nullptr && world > 1;
-    if (sharded_index && (world != c->world || opts.shard_index != c->rank))
-        throw std::runtime_error("shard_index/shard_count do not match the communicator");
+    if (!fast_idx || !sketch2_end(c, job_idx)) sketch_readset(c, idx, o, &c->sk_idx, i0, i1 - i0, true);
+    // K2/K3, then K1 on the streamed set.  Single GPU: the sketch's synchronisation also delivers the occurrence histogram
+    // of the index (build_index_finish).  Sharded index: the sketch is launched while the host waits for the send counts
+    // of the key exchange, and its synchronisation delivers mid_occ and the fallback flags.
     BuiltIndex B;
+    Sketch *sq = &c->sk_idx;
+    const bool need_str = mode != MODE_AVA || sharded_index;
     if (sharded_index) {
-        uint32_t r0, r1;
-        shard_range(idx->n, c->rank, world, &r0, &r1);
-        sketch_readset(c, idx, o, &c->sk_idx, r0, r1 - r0);
+        Sketch2Job job_str;
+        bool fast_str = false, tried = false;
         c->prof.sbegin(ST_INDEX);
-        B = build_index_sharded(c, c->sk_idx, o, &S);
+        // the blacklist holds ~2e-4 of the distinct keys; room for 1/512 of a rank's nominal share of the bases
+        const uint64_t bl_cap = std::max<uint64_t>(4096, idx->total_bases / (uint64_t)world / 512);
+        ShardedJob J = build_index_sharded_launch(c, c->sk_idx, o, bl_cap, [&]() {
+            tried = true;
+            fast_str = sketch2_begin(c, str, o, &c->sk_str, 0, str->n, &job_str);
+        });
         c->prof.send(ST_INDEX);
+        (void)tried;
+        if (!fast_str || !sketch2_end(c, job_str)) sketch_readset(c, str, o, &c->sk_str, 0, 0xffffffffu, true);
+        sq = &c->sk_str;
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (build_index_sharded_finish(c, &J, &S)) B = J.B;
+        else { c->prof.sbegin(ST_INDEX); B = build_index_sharded_exact(c, c->sk_idx, o, &S); c->prof.send(ST_INDEX); }
     } else {
-        sketch_readset(c, idx, o, &c->sk_idx);
         c->prof.sbegin(ST_INDEX);
-        B = build_index(c, c->sk_idx, o);
-        c->prof.send(ST_INDEX);
+        B = build_index_launch(c, c->sk_idx, o);
         S.n_target_minimizers = c->sk_idx.M;
+        c->prof.send(ST_INDEX);
+        if (need_str) { sketch_readset(c, str, o, &c->sk_str); sq = &c->sk_str; }
+        else CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        build_index_finish(c, o, &B);
     }
     S.n_keys = B.n_keys; S.mid_occ = B.mid_occ;
-
-    // K1 on the streamed set
-    Sketch *sq = &c->sk_idx;
-    if (mode != MODE_AVA || sharded_index) { sketch_readset(c, str, o, &c->sk_str); sq = &c->sk_str; }
     const uint64_t MQ = sq->M;
     S.n_query_minimizers = MQ;
 
@@ -1278,28 +1506,32 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
             q0 = q1;
         }
     }
-    // queries the per-query kernel could not plan (one target bin above the smem capacity): device-wide sort, one per batch
+    // queries the per-query kernel could not plan (one target bin above the smem capacity): device-wide sort, in as few
+    // batches as the anchor memory allows.  Single GPU: the check rides on the final copy of the results (no extra
+    // synchronisation in the usual case); sharded: before the count reduction.
     std::vector<uint32_t> deferred;
-    if (use_smem_sort && str->n && MQ) {
-        uint32_t mapctr_h[2] = {0, 0};
+    uint32_t mapctr_h[2] = {0, 0};
+    auto run_deferred = [&]() {
+        deferred.resize(mapctr_h[1]);
+        if (!mapctr_h[1]) return;
+        CUDA_CHECK(cudaMemcpyAsync(deferred.data(), c->deferred.p, (size_t)mapctr_h[1] * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        std::sort(deferred.begin(), deferred.end());
+        size_t lo = 0;
+        while (lo < deferred.size()) {
+            size_t hi = lo;
+            uint64_t sum = 0;
+            while (hi < deferred.size() && (hi == lo || sum + (qa[deferred[hi] + 1] - qa[deferred[hi]]) <= a_max)) { sum += qa[deferred[hi] + 1] - qa[deferred[hi]]; ++hi; }
+            ++S.n_batches;
+            run_batch(0, 0, false, deferred.data() + lo, (uint32_t)(hi - lo));
+            lo = hi;
+        }
+    };
+    const bool have_map = use_smem_sort && str->n && MQ;
+    if (have_map && sharded_index) {
         CUDA_CHECK(cudaMemcpyAsync(mapctr_h, c->mapctr.p, 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        deferred.resize(mapctr_h[1]);
-        if (mapctr_h[1]) {
-            CUDA_CHECK(cudaMemcpyAsync(deferred.data(), c->deferred.p, (size_t)mapctr_h[1] * 4, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            std::sort(deferred.begin(), deferred.end());
-            // all of them in as few device-wide sorts as the anchor memory allows
-            size_t lo = 0;
-            while (lo < deferred.size()) {
-                size_t hi = lo;
-                uint64_t sum = 0;
-                while (hi < deferred.size() && (hi == lo || sum + (qa[deferred[hi] + 1] - qa[deferred[hi]]) <= a_max)) { sum += qa[deferred[hi] + 1] - qa[deferred[hi]]; ++hi; }
-                ++S.n_batches;
-                run_batch(0, 0, false, deferred.data() + lo, (uint32_t)(hi - lo));
-                lo = hi;
-            }
-        }
+        run_deferred();
     }
 
     // one exchange on the query path: sum the per-read counts of all target shards over NVLink
@@ -1323,7 +1555,13 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         c->prof.send(ST_D2H);
     };
     fetch_results();
+    if (have_map && !sharded_index) CUDA_CHECK(cudaMemcpyAsync(mapctr_h, c->mapctr.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (have_map && !sharded_index && mapctr_h[1]) {
+        run_deferred();
+        fetch_results();
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
     if (want_regs) {
 #ifdef LRGE_TEST_KERNELS
         if (c->chain_v1) throw std::runtime_error("overlap records need the warp-per-group kernel (unset LRGE_CHAIN_V1)");
@@ -1436,6 +1674,8 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         c->prof.reset();
         { size_t f = 0, t = 0; CUDA_CHECK(cudaMemGetInfo(&f, &t)); c->free_at_create = f; c->held_at_create = dev_bytes_in_use().load(); }
         CUDA_CHECK(cudaMemcpyToSymbol(c_nt4, kNt4, 256));
+        CUDA_CHECK(cudaHostAlloc((void **)&c->pin, 64 + (OCC_BINS + 2) * 8 + 64, cudaHostAllocDefault));
+        CUDA_CHECK(cudaHostAlloc((void **)&c->pin2, (33 + 32 * 32 + 16) * 8, cudaHostAllocDefault));
         *out = c.release();
         return LRGE_OK;
     } catch (const std::exception &ex) { g_create_error = ex.what(); cudaGetLastError(); return LRGE_ERR_CUDA; }
@@ -1445,6 +1685,8 @@ void lrge_gpu_destroy(lrge_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
+    if (ctx->pin) { cudaFreeHost(ctx->pin); ctx->pin = nullptr; }
+    if (ctx->pin2) { cudaFreeHost(ctx->pin2); ctx->pin2 = nullptr; }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     delete ctx;
@@ -1497,8 +1739,8 @@ int lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_read
             shard_range(inverse ? Q->n : T->n, opts->shard_index, opts->shard_count, &lo, &hi);
             b0 = lo; b1 = hi - lo;
         }
-        stage_readset(ctx, inverse ? Q : T, inverse ? &sQ : &sT, true, b0, b1);
-        stage_readset(ctx, inverse ? T : Q, inverse ? &sT : &sQ, true);
+        stage_readset(ctx, inverse ? Q : T, inverse ? &sQ : &sT, true, b0, b1, true);
+        stage_readset(ctx, inverse ? T : Q, inverse ? &sT : &sQ, true, 0, 0xffffffffu, true);
         if (inverse) run_overlap(ctx, &sQ, &sT, MODE_INVERSE, *opts, counts, nullptr, stats);
         else run_overlap(ctx, &sT, &sQ, MODE_TWOSET, *opts, counts, had_mapping, stats);
         if (stats) {   // host buffers in, counts out: wall time of the whole call
@@ -1547,7 +1789,7 @@ int lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *o
         const auto t0 = std::chrono::steady_clock::now();
         lrge_staged &sR = ctx->tmp_a;
         struct Drain { lrge_ctx *c; ~Drain() { cudaStreamSynchronize(c->copy_stream); } } drain{ctx};
-        stage_readset(ctx, R, &sR, true);
+        stage_readset(ctx, R, &sR, true, 0, 0xffffffffu, true);
         run_overlap(ctx, &sR, &sR, MODE_AVA, *opts, counts, nullptr, stats);
         if (stats) {
             stats->ms_h2d = 0.0f;
