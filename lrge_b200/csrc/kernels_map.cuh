@@ -390,7 +390,9 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
                 if (tid == 0) s_nrounds = any_bad ? 0 : R;
             } else if (tid == 0) s_nrounds = 0;
             __syncthreads();
-            if (s_nrounds == 0) {                                         // exact greedy partition (serial, rare)
+            const bool greedy = s_nrounds == 0;                           // read by everyone BEFORE thread 0 rewrites it below
+            __syncthreads();
+            if (greedy) {                                                 // exact greedy partition (serial, rare)
                 if (tid == 0) {
                     uint32_t r = 0, acc = 0;
                     bool ok = true;
@@ -494,6 +496,9 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
             { const long long now = clock64(); cy[2] += now - tc; tc = now; }
 
             // ---- 3. groups: warps claim 32-anchor windows; the (query, target) pairs starting there are theirs ---
+            // NB (racecheck): a warp looking for the end of ITS pair reads keys of later pairs while their owners sort
+            // them in place.  Only the (target, strand) bits are read, and a group sort never changes those bits of any
+            // slot of its group (all its records share them; keys are single 32/64-bit words), so the race is benign.
             uint2 *out = A.anc + a0 + round_base;
             for (;;) {
                 uint32_t u = 0;

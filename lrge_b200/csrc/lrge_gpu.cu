@@ -312,6 +312,7 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool asy
     s->blk_base = rs->n ? b0 - rs->off[0] : 0;
     // start the copies first; the host-side bookkeeping below overlaps with them
     s->asc.reserve((b1 - b0) + 64);
+    CUDA_CHECK(cudaMemsetAsync(s->asc.as<uint8_t>() + (b1 - b0), 0, 64, c->copy_stream));   // slack read by the word-wise packers
     s->chunk_hi.clear();
     if (b1 > b0) {
         const uint64_t min_chunk = 8ull << 20;
@@ -656,6 +657,7 @@ BuiltIndex build_index_launch(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));
     unsigned long long *hist = c->hist.as<unsigned long long>();
     c->tk32.reserve((M + 64) * 4);
+    CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));          // slack read by the 8-wide bucket fetch
     KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
             index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(), hist));
     CUDA_CHECK(cudaMemcpyAsync(c->hist_h(), hist, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -736,6 +738,7 @@ BuiltIndex build_index_sharded_exact(lrge_ctx *c, const Sketch &sk, const MapOpt
             bucket_bounds_kernel<<<(unsigned)((M + 1 + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>()));
 
     c->tk32.reserve((M + 64) * 4);
+    CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));
     if (M) KLAUNCH(c, "tk32_kernel", 12.0 * M, tk32_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, c->tk32.as<uint32_t>()));
     // local run-length encoding: (key, count) per distinct local key
     c->flags.reserve(M + 1);
@@ -910,6 +913,7 @@ ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOp
     c->hist.reserve((OCC_BINS + 2) * 8);
     CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));      // local histogram: unused here
     c->tk32.reserve((M + 64) * 4);
+    CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));
     KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
             index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(),
                                                               c->hist.as<unsigned long long>()));
