@@ -118,8 +118,9 @@ int  lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *
                          uint32_t *counts, lrge_stats *stats);
 
 /* Every overlap minimap2 would report for the pair of sets (one record per kept chain = one PAF row / mm_reg1_t as
- * liblrge copies it out, aligner.rs:244-290; with MM_F_ALL_CHAINS every chain is reported, tp:A:S, mapq 0), in no
- * particular order.  query/target are read indices into Q / T.  Not restated yet: dv (mm_est_err) and rl (rep_len).
+ * liblrge copies it out, aligner.rs:244-290; with MM_F_ALL_CHAINS every chain is reported, tp:A:S, mapq 0), sorted by
+ * query and, within a query, in the order mm_map returns its regions (mm_gen_regs: score descending, hash tie-break).
+ * query/target are read indices into Q / T.  dv and rl need the whole index on one GPU (no target sharding).
  * Up to cap records are written; *n_out receives the number found (call again with a larger buffer if > cap).
  * counts / had_mapping (optional) are filled as by lrge_gpu_twoset_counts. */
 typedef struct lrge_overlap {
@@ -128,6 +129,8 @@ typedef struct lrge_overlap {
     int32_t  qs, qe, ts, te;      /* PafRecord query_start/query_end/target_start/target_end */
     int32_t  score, cnt;          /* s1:i, cm:i */
     int32_t  mlen, blen;          /* match_len, block_len */
+    float    dv;                  /* dv:f, mm_est_err (aligner.rs:264-268); < 0: not estimated */
+    int32_t  rl;                  /* rl:i, length of the query's repetitive seeds (aligner.rs:269) */
 } lrge_overlap;
 int  lrge_gpu_twoset_overlaps(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,
                               lrge_overlap *out, uint64_t cap, uint64_t *n_out,

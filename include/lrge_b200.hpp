@@ -101,6 +101,23 @@ class Context {
     lrge_ctx *h_ = nullptr;
 };
 
+// overlaps.paf as liblrge leaves it in the temp directory with -C (twoset.rs:244-250,290-293; ava.rs:219-226): one row per
+// kept chain, serialised like PafRecord (mapping.rs:81-177).  Rows come sorted by query, in mm_map's order within a query
+// (liblrge's own file interleaves queries in thread-completion order).
+inline void write_paf(const std::string &path, const std::vector<lrge_overlap> &ov, const ReadSet &Q, const ReadSet &T) {
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) throw LrgeError(LRGE_ERR_PAF_WRITE, "PAF write error: cannot open " + path);
+    char buf[2048];
+    for (const lrge_overlap &o : ov) {
+        const uint32_t q = o.query, t = o.target;
+        const int n = lrge_paf_format(&o, Q.names.data() + Q.name_off[q], (int)(Q.name_off[q + 1] - Q.name_off[q]), (int32_t)(Q.off[q + 1] - Q.off[q]),
+                                      T.names.data() + T.name_off[t], (int)(T.name_off[t + 1] - T.name_off[t]), (int32_t)(T.off[t + 1] - T.off[t]),
+                                      o.dv, o.rl, buf, sizeof buf);
+        if (n < 0 || fwrite(buf, 1, (size_t)n, f) != (size_t)n || fputc('\n', f) == EOF) { fclose(f); throw LrgeError(LRGE_ERR_PAF_WRITE, "PAF write error: " + path); }
+    }
+    fclose(f);
+}
+
 // trait Estimate (estimate.rs:21-78)
 class Estimate {
   public:
@@ -130,12 +147,18 @@ class TwoSetStrategy : public Estimate {
         Builder &use_min_ref(bool b) { o_.use_min_ref = b; return *this; }
         Builder &platform(Platform p) { o_.platform = p == Platform::PacBio ? LRGE_PLATFORM_PACBIO : LRGE_PLATFORM_NANOPORE; return *this; }
         Builder &device(int d) { device_ = d; return *this; }
-        TwoSetStrategy build(ReadSet target, ReadSet query) const { return TwoSetStrategy(std::move(target), std::move(query), o_, device_); }
+        Builder &paf(std::string path) { paf_ = std::move(path); return *this; }     // also write overlaps.paf (the -C artefact)
+        TwoSetStrategy build(ReadSet target, ReadSet query) const {
+            TwoSetStrategy s(std::move(target), std::move(query), o_, device_);
+            s.paf_path_ = paf_;
+            return s;
+        }
         Builder() { lrge_opts_default(&o_); }
 
       private:
         lrge_opts o_;
         int device_ = 0;
+        std::string paf_;
     };
     TwoSetStrategy(ReadSet target, ReadSet query) : TwoSetStrategy(Builder().build(std::move(target), std::move(query))) {}
     size_t target_num_reads() const { return target_.size(); }
@@ -147,6 +170,19 @@ class TwoSetStrategy : public Estimate {
         std::vector<float> est(query_.size());
         uint32_t no_mapping = 0;
         const lrge_readset t = target_.view(), q = query_.view();
+        if (!paf_path_.empty()) {
+            std::vector<lrge_overlap> ov(std::max<size_t>(1024, 64 * query_.size()));
+            uint64_t n = 0;
+            for (;;) {
+                ctx.check(lrge_gpu_twoset_overlaps(ctx.get(), &t, &q, &opts_, ov.data(), ov.size(), &n, nullptr, nullptr, nullptr));
+                if (n <= ov.size()) break;
+                ov.resize(n);
+            }
+            ov.resize(n);
+            // with use_min_ref and more target than query bases the records name streamed target reads as queries
+            const bool inverse = opts_.use_min_ref && target_.bases.size() > query_.bases.size();
+            write_paf(paf_path_, ov, inverse ? target_ : query_, inverse ? query_ : target_);
+        }
         ctx.check(lrge_twoset_generate_estimates(ctx.get(), &t, &q, &opts_, est.data(), &no_mapping, &stats_));
         return {std::move(est), no_mapping};
     }
@@ -156,6 +192,7 @@ class TwoSetStrategy : public Estimate {
     ReadSet target_, query_;
     lrge_opts opts_;
     int device_;
+    std::string paf_path_;
     lrge_stats stats_{};
 };
 
@@ -167,12 +204,18 @@ class AvaStrategy : public Estimate {
         Builder &max_overhang_ratio(float r) { o_.max_overhang_ratio = r; return *this; }
         Builder &platform(Platform p) { o_.platform = p == Platform::PacBio ? LRGE_PLATFORM_PACBIO : LRGE_PLATFORM_NANOPORE; return *this; }
         Builder &device(int d) { device_ = d; return *this; }
-        AvaStrategy build(ReadSet reads) const { return AvaStrategy(std::move(reads), o_, device_); }
+        Builder &paf(std::string path) { paf_ = std::move(path); return *this; }     // also write overlaps.paf (the -C artefact)
+        AvaStrategy build(ReadSet reads) const {
+            AvaStrategy s(std::move(reads), o_, device_);
+            s.paf_path_ = paf_;
+            return s;
+        }
         Builder() { lrge_opts_default(&o_); }
 
       private:
         lrge_opts o_;
         int device_ = 0;
+        std::string paf_;
     };
     explicit AvaStrategy(ReadSet reads) : AvaStrategy(Builder().build(std::move(reads))) {}
     size_t num_reads() const { return reads_.size(); }
@@ -183,6 +226,17 @@ class AvaStrategy : public Estimate {
         std::vector<float> est(reads_.size());
         uint32_t no_mapping = 0;
         const lrge_readset r = reads_.view();
+        if (!paf_path_.empty()) {
+            std::vector<lrge_overlap> ov(std::max<size_t>(1024, 64 * reads_.size()));
+            uint64_t n = 0;
+            for (;;) {
+                ctx.check(lrge_gpu_ava_overlaps(ctx.get(), &r, &opts_, ov.data(), ov.size(), &n, nullptr, nullptr));
+                if (n <= ov.size()) break;
+                ov.resize(n);
+            }
+            ov.resize(n);
+            write_paf(paf_path_, ov, reads_, reads_);
+        }
         ctx.check(lrge_ava_generate_estimates(ctx.get(), &r, &opts_, est.data(), &no_mapping, &stats_));
         return {std::move(est), no_mapping};
     }
@@ -192,6 +246,7 @@ class AvaStrategy : public Estimate {
     ReadSet reads_;
     lrge_opts opts_;
     int device_;
+    std::string paf_path_;
     lrge_stats stats_{};
 };
 

@@ -56,7 +56,7 @@ class Opts(ctypes.Structure):
 
 
 OVERLAP_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("rev", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("ts", "<i4"),
-                          ("te", "<i4"), ("score", "<i4"), ("cnt", "<i4"), ("mlen", "<i4"), ("blen", "<i4")])
+                          ("te", "<i4"), ("score", "<i4"), ("cnt", "<i4"), ("mlen", "<i4"), ("blen", "<i4"), ("dv", "<f4"), ("rl", "<i4")])
 
 
 class KernelTime(ctypes.Structure):
@@ -362,10 +362,12 @@ def read_fastx(path: str) -> ReadSet:
     return ReadSet(bases[:nb.value], off, names[:nn.value], noff)
 
 
-def paf_line(ov, Q: ReadSet, T: ReadSet, dv: float = -1.0, rl: int = 0) -> bytes:
-    """One PAF row as PafRecord serialises it (mapping.rs:81-177)."""
+def paf_line(ov, Q: ReadSet, T: ReadSet, dv=None, rl=None) -> bytes:
+    """One PAF row as PafRecord serialises it (mapping.rs:81-177); dv / rl default to the record's own."""
     rec = np.zeros(1, OVERLAP_DTYPE)
     rec[0] = ov
+    dv = float(ov["dv"]) if dv is None else dv
+    rl = int(ov["rl"]) if rl is None else rl
     qn, tn = Q.name(int(ov["query"])), T.name(int(ov["target"]))
     buf = ctypes.create_string_buffer(1024)
     n = lib().lrge_paf_format(rec.ctypes.data, qn, len(qn), int(Q.off[int(ov["query"]) + 1] - Q.off[int(ov["query"])]), tn, len(tn),

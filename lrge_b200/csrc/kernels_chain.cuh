@@ -40,8 +40,9 @@ struct PairTask {
     int32_t *f, *p, *t;          // per-anchor scratch (batch sized); t zeroed before launch
 };
 
-// one kept chain = one mm_reg1_t as liblrge reads it (aligner.rs:244-290); same layout as lrge_overlap
-struct RegOut { uint32_t qid, rid; int32_t rev, qs, qe, rs, re, score, cnt, mlen, blen; };
+// one kept chain = one mm_reg1_t as liblrge reads it (aligner.rs:244-290), plus the chain's end anchors: the host
+// derives the PAF tags dv (mm_est_err) and rl, and the row order of mm_gen_regs, from them and the query's sketch
+struct RegOut { uint32_t qid, rid; int32_t rev, qs, qe, rs, re, score, cnt, mlen, blen; uint32_t a0x, a0y, a1y; };
 
 struct CountOut {
     RegOut *regs;                // optional: every kept chain (full DP + full backtrack, no counting shortcut)
@@ -423,6 +424,7 @@ __device__ void chain_one_group(const A anc, int32_t n, int2 *fp, int32_t *t, co
                 if (slot < O.regs_cap) {
                     RegOut r; r.qid = qid; r.rid = rid; r.rev = strand; r.qs = qs; r.qe = qe; r.rs = rs; r.re = re;
                     r.score = c.sc; r.cnt = c.cnt; r.mlen = mlen; r.blen = blen;
+                    r.a0x = af.x; r.a0y = af.y; r.a1y = al.y;
                     O.regs[slot] = r;
                 }
             }

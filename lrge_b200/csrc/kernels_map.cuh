@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(SL_THREADS) seed_lookup_kernel(const uint64_t 
             } else {
                 n = index_lookup(I, key[u], (uint32_t)mid_occ, &start);       // large bucket: bisect
             }
-            if (n > (uint32_t)mid_occ) n = 0;                                   // m[i].flt = 1
-            if (n && I.bl && ((I.bl[start >> 5] >> (start & 31)) & 1)) n = 0;   // > mid_occ over all target shards
+            bool rep = n > (uint32_t)mid_occ;                                   // m[i].flt = 1
+            if (n && I.bl && ((I.bl[start >> 5] >> (start & 31)) & 1)) rep = true;   // > mid_occ over all target shards
+            if (rep) { n = 0; start = SEED_REPETITIVE; }                        // present in the index, dropped: counts for rl
         }
         hstart[i] = start;
         hn[i] = n;

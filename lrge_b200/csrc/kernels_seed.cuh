@@ -15,6 +15,7 @@
 namespace lrge {
 
 constexpr int MZ_TABLE = 8192;
+constexpr uint32_t SEED_REPETITIVE = 0xffffffffu;   // hstart of a seed that is in the index but occurs > mid_occ times
 
 // mm_seed_mz_flt: flag query minimizers whose x occurs > mid_occ times AND > q_occ_frac * n times in
 // the query.  A counting table over-estimates occurrences; candidates are then counted exactly.
@@ -72,8 +73,9 @@ __global__ void seed_count_kernel(const uint64_t *__restrict__ qx, const uint64_
     if (i < MQ && !flt[i]) {
         const uint64_t x = qx[i];
         n = index_lookup(I, x >> 8, (uint32_t)mid_occ, &start);
-        if (n > (uint32_t)mid_occ) n = 0;                     // m[i].flt = 1 (seed.c mm_collect_matches)
-        if (n && I.bl && ((I.bl[start >> 5] >> (start & 31)) & 1)) n = 0;   // > mid_occ over all target shards
+        bool rep = n > (uint32_t)mid_occ;                     // m[i].flt = 1 (seed.c mm_collect_matches)
+        if (n && I.bl && ((I.bl[start >> 5] >> (start & 31)) & 1)) rep = true;   // > mid_occ over all target shards
+        if (rep) { n = 0; start = SEED_REPETITIVE; }
         if (n) {
             if (S.check_names || S.sharded) {
                 // 128-bit loads, two hit-list entries each, four loads in flight

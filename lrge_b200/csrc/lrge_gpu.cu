@@ -1053,6 +1053,67 @@ NameRanks rank_names(const lrge_staged *A, const lrge_staged *B) {
     return R;
 }
 
+// ---- PAF annotations of the overlap records (host side; records mode only) -------------------------------------------
+// mm_est_err (esterr.c) -> dv, tbuf->rep_len (seed.c mm_collect_matches) -> rl, and the row order of mm_gen_regs (hit.c:
+// regions sorted by (score << 32 | cnt) ^ hash, descending).  All three are functions of the query's sketch and of the
+// end anchors of each chain, which the chaining kernel returns with the record.
+namespace paf {
+
+inline uint64_t hash64(uint64_t key) {
+    key = (~key + (key << 21)); key = key ^ key >> 24; key = ((key + (key << 3)) + (key << 8)); key = key ^ key >> 14;
+    key = ((key + (key << 2)) + (key << 4)); key = key ^ key >> 28; key = (key + (key << 31));
+    return key;
+}
+inline uint32_t wang_hash(uint32_t key) {
+    key += ~(key << 15); key ^= (key >> 10); key += (key << 3); key ^= (key >> 6); key += ~(key << 11); key ^= (key >> 16);
+    return key;
+}
+inline uint32_t x31_hash(const char *s, uint32_t len) {
+    if (len == 0) return 0;
+    uint32_t h = (uint32_t)(unsigned char)s[0];
+    for (uint32_t i = 1; i < len; ++i) h = (h << 5) - h + (uint32_t)(unsigned char)s[i];
+    return h;
+}
+
+struct QuerySeeds {                       // the seeds of one query as mm_collect_matches leaves them
+    std::vector<int32_t> pos;             // mini_pos: q_pos >> 1 of every kept seed (has hits, not repetitive), ascending
+    std::vector<uint8_t> tandem;          // is_tandem of those seeds
+    int32_t rep_len = 0;
+    float avg_k = 0.0f;
+};
+
+QuerySeeds query_seeds(const uint64_t *x, const uint64_t *y, const uint8_t *flt, const uint32_t *hstart, const uint32_t *hn,
+                       uint32_t m0, uint32_t m1) {
+    QuerySeeds S;
+    std::vector<uint32_t> mv;             // minimizers that survive mm_seed_mz_flt
+    for (uint32_t i = m0; i < m1; ++i) if (!flt[i]) mv.push_back(i);
+    int rep_st = 0, rep_en = 0;
+    uint64_t sum_k = 0;
+    for (size_t j = 0; j < mv.size(); ++j) {
+        const uint32_t i = mv[j];
+        const bool repetitive = hstart[i] == SEED_REPETITIVE;
+        if (hn[i] == 0 && !repetitive) continue;                          // not in the index
+        const uint32_t q_pos = (uint32_t)y[i], q_span = (uint32_t)(x[i] & 0xff);
+        if (repetitive) {
+            const int en = (int)(q_pos >> 1) + 1, st = en - (int)q_span;
+            if (st > rep_en) { S.rep_len += rep_en - rep_st; rep_st = st; rep_en = en; }
+            else rep_en = en;
+        } else {
+            bool t = false;
+            if (j > 0 && (x[i] >> 8) == (x[mv[j - 1]] >> 8)) t = true;
+            if (j + 1 < mv.size() && (x[i] >> 8) == (x[mv[j + 1]] >> 8)) t = true;
+            S.pos.push_back((int32_t)(q_pos >> 1));
+            S.tandem.push_back(t);
+            sum_k += q_span;
+        }
+    }
+    S.rep_len += rep_en - rep_st;
+    if (!S.pos.empty()) S.avg_k = (float)sum_k / (int)S.pos.size();
+    return S;
+}
+
+}  // namespace paf
+
 enum Mode { MODE_TWOSET = 0, MODE_AVA = 1, MODE_INVERSE = 2 };
 
 struct WidenU32 { __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; } };
@@ -1063,7 +1124,6 @@ struct RegsRequest { lrge_overlap *out = nullptr; uint64_t cap = 0; uint64_t *n_
 
 void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, const lrge_opts &opts,
                  uint32_t *counts_out, uint8_t *had_out, lrge_stats *st, const RegsRequest *rq = nullptr) {
-    static_assert(sizeof(lrge_overlap) == sizeof(RegOut), "lrge_overlap and the device record must share a layout");
     const MapOpt o = preset_for(opts.platform);
     const uint32_t n_counts = mode == MODE_TWOSET ? str->n : idx->n;
     // Aligner::map fails on an empty sequence (aligner.rs:214-216 -> LrgeError::MapError); minimap2's index build just
@@ -1572,7 +1632,78 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
 #endif
         *rq->n_out = ctr_h[2];
         const uint64_t m = std::min<uint64_t>(ctr_h[2], rq->cap);
-        if (m && rq->out) CUDA_CHECK(cudaMemcpyAsync(rq->out, c->regs.p, m * sizeof(RegOut), cudaMemcpyDeviceToHost, c->stream));
+        if (m && rq->out) {
+            // records + the query sketch to the host, then the PAF annotations (namespace paf above)
+            std::vector<RegOut> raw(m);
+            std::vector<uint64_t> hx(MQ), hy(MQ);
+            std::vector<uint8_t> hflt(MQ);
+            std::vector<uint32_t> hhs(MQ), hhn(MQ);
+            CUDA_CHECK(cudaMemcpyAsync(raw.data(), c->regs.p, m * sizeof(RegOut), cudaMemcpyDeviceToHost, c->stream));
+            if (MQ) {
+                CUDA_CHECK(cudaMemcpyAsync(hx.data(), sq->x.p, MQ * 8, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaMemcpyAsync(hy.data(), sq->y.p, MQ * 8, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaMemcpyAsync(hflt.data(), c->flt.p, MQ, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaMemcpyAsync(hhs.data(), c->hstart.p, MQ * 4, cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaMemcpyAsync(hhn.data(), c->hn.p, MQ * 4, cudaMemcpyDeviceToHost, c->stream));
+            }
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            std::vector<uint32_t> order(m);
+            std::iota(order.begin(), order.end(), 0u);
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return raw[a].qid < raw[b].qid; });
+            std::vector<uint64_t> zx(m);
+            std::vector<float> dv(m, -1.0f);
+            std::vector<int32_t> rl(m, 0);
+            size_t lo = 0;
+            while (lo < m) {
+                size_t hi = lo;
+                const uint32_t q = raw[order[lo]].qid;
+                while (hi < m && raw[order[hi]].qid == q) ++hi;
+                const paf::QuerySeeds QS = paf::query_seeds(hx.data(), hy.data(), hflt.data(), hhs.data(), hhn.data(), moff_h[q], moff_h[q + 1]);
+                const int32_t qlen = (int32_t)str->h_len[q];
+                uint32_t qhash = paf::x31_hash(str->names.data() + str->name_off[q], str->name_off[q + 1] - str->name_off[q]);
+                qhash ^= paf::wang_hash((uint32_t)qlen) + paf::wang_hash(11u);      // mm_mapopt_t.seed = 11
+                qhash = paf::wang_hash(qhash);
+                const int32_t n_mp = (int32_t)QS.pos.size();
+                auto mini_idx = [&](int32_t p) -> int32_t {
+                    auto it = std::lower_bound(QS.pos.begin(), QS.pos.end(), p);
+                    return it != QS.pos.end() && *it == p ? (int32_t)(it - QS.pos.begin()) : -1;
+                };
+                for (size_t e = lo; e < hi; ++e) {
+                    const RegOut &r = raw[order[e]];
+                    const int32_t span0 = (int32_t)(r.a0y >> 24), y0 = (int32_t)(r.a0y & 0xffffff);
+                    const int32_t span1 = (int32_t)(r.a1y >> 24), y1 = (int32_t)(r.a1y & 0xffffff);
+                    auto for_qpos = [&](int32_t y, int32_t span) { return r.rev ? qlen - 1 - (y + 1 - span) : y; };   // get_for_qpos
+                    const int32_t i0 = mini_idx(for_qpos(y0, span0)), i1 = mini_idx(for_qpos(y1, span1));
+                    rl[order[e]] = QS.rep_len;
+                    // mm_est_err: every anchor of a chain is a kept seed of the query, visited in query order, so
+                    // n_match = cnt and [st, en] are the seeds between the chain's two ends
+                    const int32_t st = r.rev ? i1 : i0, en = r.rev ? i0 : i1;
+                    if (n_mp && r.cnt > 0 && st >= 0 && en >= 0) {
+                        const int32_t l_ref = (int32_t)idx->h_len[r.rid];
+                        const int32_t n_match = r.cnt;
+                        int32_t n_tot = en - st + 1;
+                        if (r.qs > QS.avg_k && r.rs > QS.avg_k) ++n_tot;
+                        if (qlen - r.qs > QS.avg_k && l_ref - r.re > QS.avg_k) ++n_tot;
+                        dv[order[e]] = n_match >= n_tot ? 0.0f : (float)(1.0 - pow((double)n_match / n_tot, 1.0 / QS.avg_k));
+                    }
+                    // mm_gen_regs: h = hash64((hash64(a[k].x) + hash64(a[k].y)) ^ hash) of the chain's first anchor
+                    const bool tandem = i0 >= 0 && QS.tandem[i0];
+                    const bool self = rank_str[q] == rank_idx[r.rid] && idx->h_len[r.rid] == str->h_len[q] && !r.rev;
+                    const uint64_t ax = (uint64_t)(r.rev ? 1 : 0) << 63 | (uint64_t)r.rid << 32 | r.a0x;
+                    const uint64_t ay = (uint64_t)span0 << 32 | (uint64_t)y0 | (tandem ? 1ULL << 42 : 0) | (self ? 1ULL << 43 : 0);
+                    const uint32_t h = (uint32_t)paf::hash64((paf::hash64(ax) + paf::hash64(ay)) ^ qhash);
+                    zx[order[e]] = ((uint64_t)(uint32_t)r.score << 32 | (uint32_t)r.cnt) ^ h;
+                }
+                std::sort(order.begin() + lo, order.begin() + hi, [&](uint32_t a, uint32_t b) { return zx[a] > zx[b]; });
+                lo = hi;
+            }
+            for (uint64_t e = 0; e < m; ++e) {
+                const RegOut &r = raw[order[e]];
+                lrge_overlap &o2 = rq->out[e];
+                o2.query = r.qid; o2.target = r.rid; o2.rev = r.rev; o2.qs = r.qs; o2.qe = r.qe; o2.ts = r.rs; o2.te = r.re;
+                o2.score = r.score; o2.cnt = r.cnt; o2.mlen = r.mlen; o2.blen = r.blen; o2.dv = dv[order[e]]; o2.rl = rl[order[e]];
+            }
+        }
     }
     c->prof.send(ST_TOTAL);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));

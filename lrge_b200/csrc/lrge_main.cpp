@@ -2,8 +2,9 @@
 //
 // Differences, on purpose: plain or gzip FASTA/FASTQ only (no bzip2/zstd/xz/BAM: the rest of io.rs is out of scope); the
 // random subsample uses this file's own generator, so `-s SEED` is repeatable here but does not pick the reads the Rust
-// `rand` crate would (lib.rs:189-204); `-t`, `-C`, `-D` are accepted and ignored (no threads, no temp files on this
-// path); and `--platform` IS forwarded (the reference CLI parses it but never passes it on, main.rs:56-85).
+// `rand` crate would (lib.rs:189-204); `-t` is accepted and ignored; `-C -D <dir>` writes <dir>/overlaps.paf (the one
+// intermediate of liblrge that is worth keeping; there are no temp FASTA files on this path); and `--platform` IS
+// forwarded (the reference CLI parses it but never passes it on, main.rs:56-85).
 #include "../../include/lrge_b200.hpp"
 
 #include <algorithm>
@@ -20,7 +21,8 @@
 namespace {
 
 struct Args {
-    std::string input, output = "-", platform = "ont";
+    std::string input, output = "-", platform = "ont", temp_dir;
+    bool keep_temp = false;
     size_t target = lrge::DEFAULT_TARGET_NUM_READS, query = lrge::DEFAULT_QUERY_NUM_READS, num = 0;
     bool have_num = false, have_target = false, have_query = false;
     bool filter_contained = false, with_infinity = false, precise = false, use_min_ref = false, seeded = false;
@@ -45,7 +47,9 @@ struct Args {
             "      --max-overhang-ratio <FLOAT> [default: 0.2]\n"
             "      --use-min-ref            index the smaller of the two sets\n"
             "      --device <INT>           CUDA device [default: 0]\n"
-            "  -t/-C/-D                     accepted for compatibility, ignored\n");
+            "  -C, --keep-temp              keep overlaps.paf (written to the -D directory, default: current directory)\n"
+            "  -D, --temp <DIR>             directory for overlaps.paf\n"
+            "  -t, --threads <INT>          accepted for compatibility, ignored\n");
     exit(rc);
 }
 
@@ -69,8 +73,9 @@ Args parse(int argc, char **argv) {
         else if (s == "--max-overhang-ratio") a.max_overhang_ratio = strtof(need(i), nullptr);
         else if (s == "--use-min-ref") a.use_min_ref = true;
         else if (s == "--device") a.device = atoi(need(i));
-        else if (s == "-t" || s == "--threads" || s == "-D" || s == "--temp") need(i);
-        else if (s == "-C" || s == "--keep-temp") {}
+        else if (s == "-t" || s == "--threads") need(i);
+        else if (s == "-D" || s == "--temp") a.temp_dir = need(i);
+        else if (s == "-C" || s == "--keep-temp") a.keep_temp = true;
         else if (s == "--quiet") ++a.quiet;
         else if (s == "--verbose") {}
         else if (s.size() >= 2 && s[0] == '-' && s[1] == 'q' && s.find_first_not_of('q', 1) == std::string::npos) a.quiet += (int)s.size() - 1;
@@ -131,13 +136,14 @@ int main(int argc, char **argv) {
             return rs;
         };
         lrge::EstimateResult res;
+        const std::string paf_path = a.keep_temp ? (a.temp_dir.empty() ? std::string("overlaps.paf") : a.temp_dir + "/overlaps.paf") : std::string();
         if (a.have_num) {                                         // AvaStrategy (ava.rs:108-161)
             size_t n = a.num;
             if (n_fq < n) { if (a.quiet < 1) fprintf(stderr, "[WARN] only %u reads in input, using all\n", n_fq); n = n_fq; }
             auto idx = unique_random_set(n, n_fq, seed);
             std::sort(idx.begin(), idx.end());
             auto strat = lrge::AvaStrategy::Builder().platform(platform).remove_internal(a.filter_contained)
-                             .max_overhang_ratio(a.max_overhang_ratio).device(a.device).build(take(idx));
+                             .max_overhang_ratio(a.max_overhang_ratio).device(a.device).paf(paf_path).build(take(idx));
             res = strat.estimate(!a.with_infinity, a.q1, a.q3);
         } else {                                                  // TwoSetStrategy (twoset.rs:122-201)
             size_t T = a.target, Q = a.query;
@@ -148,7 +154,8 @@ int main(int argc, char **argv) {
             std::vector<uint32_t> t(idx.end() - T, idx.end()), q(idx.begin(), idx.end() - T);
             std::sort(t.begin(), t.end()); std::sort(q.begin(), q.end());
             auto strat = lrge::TwoSetStrategy::Builder().platform(platform).remove_internal(a.filter_contained)
-                             .max_overhang_ratio(a.max_overhang_ratio).use_min_ref(a.use_min_ref).device(a.device).build(take(t), take(q));
+                             .max_overhang_ratio(a.max_overhang_ratio).use_min_ref(a.use_min_ref).device(a.device).paf(paf_path)
+                             .build(take(t), take(q));
             res = strat.estimate(!a.with_infinity, a.q1, a.q3);
         }
         if (!res.estimate) {

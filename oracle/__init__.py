@@ -41,12 +41,13 @@ class Reg(ctypes.Structure):
         ("rid", ctypes.c_int32), ("rev", ctypes.c_int32),
         ("qs", ctypes.c_int32), ("qe", ctypes.c_int32), ("rs", ctypes.c_int32), ("re", ctypes.c_int32),
         ("score", ctypes.c_int32), ("cnt", ctypes.c_int32), ("mlen", ctypes.c_int32), ("blen", ctypes.c_int32),
-        ("div", ctypes.c_float), ("hash", ctypes.c_uint32),
+        ("div", ctypes.c_float), ("hash", ctypes.c_uint32), ("rl", ctypes.c_int32), ("order", ctypes.c_int32),
     ]
 
 
 REG_DTYPE = np.dtype([("rid", "<i4"), ("rev", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("rs", "<i4"), ("re", "<i4"),
-                      ("score", "<i4"), ("cnt", "<i4"), ("mlen", "<i4"), ("blen", "<i4"), ("div", "<f4"), ("hash", "<u4")])
+                      ("score", "<i4"), ("cnt", "<i4"), ("mlen", "<i4"), ("blen", "<i4"), ("div", "<f4"), ("hash", "<u4"),
+                      ("rl", "<i4"), ("order", "<i4")])
 M128_DTYPE = np.dtype([("x", "<u8"), ("y", "<u8")])
 
 

@@ -600,12 +600,15 @@ static seed_t *seed_collect_all(const orc_index_t *mi, const v128_t *mv, int32_t
 }
 
 /* occ_dist == 0 for both presets -> the plain "n > max_occ => filtered" branch */
-static seed_t *collect_matches(int *_n_m, int max_occ, const orc_index_t *mi, const v128_t *mv, int64_t *n_a, int *rep_len, uint64_t *n_flt) {
+static seed_t *collect_matches(int *_n_m, int max_occ, const orc_index_t *mi, const v128_t *mv, int64_t *n_a, int *rep_len, uint64_t *n_flt,
+                               int *n_mini_pos, uint64_t **mini_pos) {
     int rep_st = 0, rep_en = 0, n_m, n_m0;
     int i;
     seed_t *m = seed_collect_all(mi, mv, &n_m0);
     for (i = 0; i < n_m0; ++i)
         if (m[i].n > (uint32_t)max_occ) { m[i].flt = 1; if (n_flt) ++*n_flt; }
+    *mini_pos = (uint64_t*)malloc((mv->n ? mv->n : 1) * sizeof(uint64_t));
+    *n_mini_pos = 0;
     for (i = 0, n_m = 0, *rep_len = 0, *n_a = 0; i < n_m0; ++i) {
         seed_t *q = &m[i];
         if (q->flt) {
@@ -614,6 +617,7 @@ static seed_t *collect_matches(int *_n_m, int max_occ, const orc_index_t *mi, co
             else rep_en = en;
         } else {
             *n_a += q->n;
+            (*mini_pos)[(*n_mini_pos)++] = (uint64_t)q->q_span << 32 | q->q_pos >> 1;
             m[n_m++] = *q;
         }
     }
@@ -642,9 +646,10 @@ static int skip_seed(int64_t flag, uint64_t r, const seed_t *q, const char *qnam
 }
 
 static orc128_t *collect_seed_hits(const orc_opt_t *opt, int max_occ, const orc_index_t *mi, const char *qname,
-                                   const v128_t *mv, int qlen, int64_t *n_a, int *rep_len, orc_stats_t *st) {
+                                   const v128_t *mv, int qlen, int64_t *n_a, int *rep_len, orc_stats_t *st,
+                                   int *n_mini_pos, uint64_t **mini_pos) {
     int i, n_m;
-    seed_t *m = collect_matches(&n_m, max_occ, mi, mv, n_a, rep_len, st ? &st->n_occ_filtered : 0);
+    seed_t *m = collect_matches(&n_m, max_occ, mi, mv, n_a, rep_len, st ? &st->n_occ_filtered : 0, n_mini_pos, mini_pos);
     orc128_t *a = (orc128_t*)malloc((*n_a ? *n_a : 1) * sizeof(orc128_t));
     if (st) { st->n_seeds += n_m; st->n_hits += *n_a; }
     for (i = 0, *n_a = 0; i < n_m; ++i) {
@@ -912,7 +917,7 @@ static void reg_set_coor(orc_reg_t *r, int32_t qlen, const orc128_t *a, int32_t 
     }
     cal_fuzzy_len(r, a, as);
 }
-static orc_reg_t *gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, orc128_t *a, int tie_mode) {
+static orc_reg_t *gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, orc128_t *a, int tie_mode, int32_t *as_out) {
     orc128_t *z, tmp;
     orc_reg_t *r;
     int i, k;
@@ -934,9 +939,59 @@ static orc_reg_t *gen_regs(uint32_t hash, int qlen, int n_u, uint64_t *u, orc128
         ri->cnt = (int32_t)z[i].y;
         ri->div = -1.0f;
         reg_set_coor(ri, qlen, a, (int32_t)(z[i].y >> 32));
+        if (as_out) as_out[i] = (int32_t)(z[i].y >> 32);
     }
     free(z);
     return r;
+}
+
+/* ------------------------------------------------------------------ esterr.c: mm_est_err (PAF dv tag) */
+
+static inline int32_t get_for_qpos(int32_t qlen, const orc128_t *a) {
+    int32_t x = (int32_t)a->y;
+    int32_t q_span = a->y >> 32 & 0xff;
+    if (a->x >> 63) x = qlen - 1 - (x + 1 - q_span);   /* back to the forward strand of the query */
+    return x;
+}
+
+static int get_mini_idx(int qlen, const orc128_t *a, int32_t n, const uint64_t *mini_pos) {
+    int32_t x, L = 0, R = n - 1;
+    x = get_for_qpos(qlen, a);
+    while (L <= R) {
+        int32_t m = ((uint64_t)L + R) >> 1;
+        int32_t y = (int32_t)mini_pos[m];
+        if (y < x) L = m + 1;
+        else if (y > x) R = m - 1;
+        else return m;
+    }
+    return -1;
+}
+
+static void est_err(const orc_index_t *mi, int qlen, int n_regs, orc_reg_t *regs, const int32_t *as, const orc128_t *a,
+                    int32_t n, const uint64_t *mini_pos) {
+    int i;
+    uint64_t sum_k = 0;
+    float avg_k;
+    if (n == 0) return;
+    for (i = 0; i < n; ++i) sum_k += mini_pos[i] >> 32 & 0xff;
+    avg_k = (float)sum_k / n;
+    for (i = 0; i < n_regs; ++i) {
+        orc_reg_t *r = &regs[i];
+        int32_t st, en, j, k, n_match, n_tot, l_ref;
+        r->div = -1.0f;
+        if (r->cnt == 0) continue;
+        st = en = get_mini_idx(qlen, r->rev ? &a[as[i] + r->cnt - 1] : &a[as[i]], n, mini_pos);
+        if (st < 0) continue;
+        l_ref = mi->len[r->rid];
+        for (k = 1, j = st + 1, n_match = 1; j < n && k < r->cnt; ++j) {
+            int32_t q = get_for_qpos(qlen, r->rev ? &a[as[i] + r->cnt - 1 - k] : &a[as[i] + k]);
+            if (q == (int32_t)mini_pos[j]) ++n_match, en = j, ++k;
+        }
+        n_tot = en - st + 1;
+        if (r->qs > avg_k && r->rs > avg_k) ++n_tot;
+        if (qlen - r->qs > avg_k && l_ref - r->re > avg_k) ++n_tot;
+        r->div = n_match >= n_tot ? 0.0f : (float)(1.0 - pow((double)n_match / n_tot, 1.0 / avg_k));
+    }
 }
 
 /* ------------------------------------------------------------------ mm_map_frag (single segment, no CIGAR) */
@@ -967,7 +1022,9 @@ int orc_map(const orc_index_t *mi, const orc_opt_t *opt, const uint8_t *seq, int
     mm_sketch(seq, qlen, mi->w, mi->k, 0, mi->is_hpc, &mv);     /* collect_minimizers; sdust_thres == 0 */
     if (st) st->n_q_minimizers += mv.n;
     if (opt->q_occ_frac > 0.0f) seed_mz_flt(&mv, opt->mid_occ, opt->q_occ_frac, st);
-    a = collect_seed_hits(opt, opt->mid_occ, mi, qname, &mv, qlen, &n_a, &rep_len, st);
+    int n_mini_pos = 0;
+    uint64_t *mini_pos = 0;
+    a = collect_seed_hits(opt, opt->mid_occ, mi, qname, &mv, qlen, &n_a, &rep_len, st, &n_mini_pos, &mini_pos);
     free(mv.a);
     if (st) {
         st->n_anchors += n_a;
@@ -992,13 +1049,17 @@ int orc_map(const orc_index_t *mi, const orc_opt_t *opt, const uint8_t *seq, int
     if (rep_len_) *rep_len_ = rep_len;
     if (st) st->n_chains += n_regs0;
     if (n_regs0 > 0) {
-        orc_reg_t *r = gen_regs(hash, qlen, n_regs0, u, a, opt->tie_mode);
-        /* chain_post: no-op under ALL_CHAINS; mm_est_err -> div (PAF only, not restated: stays -1);
-         * mm_filter_strand_retained keeps all; align_regs returns early without CIGAR; mapq stays 0 */
+        int32_t *as = (int32_t*)malloc(n_regs0 * sizeof(int32_t));
+        orc_reg_t *r = gen_regs(hash, qlen, n_regs0, u, a, opt->tie_mode, as);
+        /* chain_post: no-op under ALL_CHAINS; mm_filter_strand_retained keeps all; align_regs returns early without
+         * CIGAR; mapq stays 0; then mm_est_err (dv) */
+        est_err(mi, qlen, n_regs0, r, as, a, n_mini_pos, mini_pos);
+        for (int i = 0; i < n_regs0; ++i) { r[i].rl = rep_len; r[i].order = i; }   /* tbuf->rep_len of this query (aligner.rs:269) */
+        free(as);
         if (regs) *regs = r; else free(r);
         if (n_regs) *n_regs = n_regs0;
     }
-    free(a); free(u);
+    free(a); free(u); free(mini_pos);
     return 0;
 }
 

@@ -72,8 +72,10 @@ typedef struct {
     int32_t rid, rev;
     int32_t qs, qe, rs, re;
     int32_t score, cnt, mlen, blen;
-    float   div;
+    float   div;                 /* mm_est_err (PAF dv) */
     uint32_t hash;
+    int32_t rl;                  /* rep_len of the query (PAF rl) */
+    int32_t order;               /* position of the row in mm_map's output for its query (score desc, hash tie-break) */
 } orc_reg_t;
 
 typedef struct {

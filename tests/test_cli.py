@@ -56,3 +56,13 @@ def test_cli_ava_matches_library(tmp_path):
     r = subprocess.run([BIN, "-T", "100", "-Q", "50", "-s", "7", "-F", "--use-min-ref", str(fq)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert 40_000 < float(r.stdout.strip()) < 400_000
+    # -C -D dir keeps overlaps.paf (twoset.rs:244-250): 17 columns, PafRecord's tags, one row per overlap record
+    r = subprocess.run([BIN, "-n", "150", "-s", "1", "-C", "-D", str(tmp_path), str(fa)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = open(tmp_path / "overlaps.paf").read().splitlines()
+    with lrge_b200.Context(0) as ctx:
+        ov, _ = ctx.ava_overlaps(R, "ont")
+    assert len(rows) == ov.shape[0] > 100
+    assert rows == [lrge_b200.paf_line(o, R, R).decode() for o in ov]
+    f = rows[0].split("\t")
+    assert len(f) == 17 and f[12] == "tp:A:S" and f[13].startswith("cm:i:") and f[15].startswith("dv:f:") and f[16].startswith("rl:i:")

@@ -304,14 +304,30 @@ def test_query_batching(ctx, monkeypatch):
     assert np.array_equal(av.counts, want)
 
 
-def _reg_set(regs, qidx=None):
+def _reg_rows(regs, qidx=None):
+    """Rows as tuples incl. the PAF tags dv (bit pattern of the f32) and rl; product records or oracle regs."""
     if qidx is None:
-        return sorted(zip(regs["query"].tolist(), regs["target"].tolist(), regs["rev"].tolist(), regs["qs"].tolist(), regs["qe"].tolist(),
-                          regs["ts"].tolist(), regs["te"].tolist(), regs["score"].tolist(), regs["cnt"].tolist(), regs["mlen"].tolist(),
-                          regs["blen"].tolist()))
-    return sorted(zip(qidx.tolist(), regs["rid"].tolist(), regs["rev"].tolist(), regs["qs"].tolist(), regs["qe"].tolist(),
-                      regs["rs"].tolist(), regs["re"].tolist(), regs["score"].tolist(), regs["cnt"].tolist(), regs["mlen"].tolist(),
-                      regs["blen"].tolist()))
+        return list(zip(regs["query"].tolist(), regs["target"].tolist(), regs["rev"].tolist(), regs["qs"].tolist(), regs["qe"].tolist(),
+                        regs["ts"].tolist(), regs["te"].tolist(), regs["score"].tolist(), regs["cnt"].tolist(), regs["mlen"].tolist(),
+                        regs["blen"].tolist(), regs["dv"].view(np.uint32).tolist(), regs["rl"].tolist()))
+    return list(zip(qidx.tolist(), regs["rid"].tolist(), regs["rev"].tolist(), regs["qs"].tolist(), regs["qe"].tolist(),
+                    regs["rs"].tolist(), regs["re"].tolist(), regs["score"].tolist(), regs["cnt"].tolist(), regs["mlen"].tolist(),
+                    regs["blen"].tolist(), regs["div"].view(np.uint32).tolist(), regs["rl"].tolist()))
+
+
+def _reg_set(regs, qidx=None):
+    return sorted(_reg_rows(regs, qidx))
+
+
+def _assert_row_order(ov, regs, qidx):
+    """Product rows come sorted by query and, within a query, in mm_map's order (mm_gen_regs: score descending, hash
+    tie-break): compare the whole sequence with the oracle's, query by query (the oracle's flattened list is in
+    thread-completion order of the queries, its `order` field is the row's position inside its query)."""
+    key = np.lexsort((regs["order"], qidx))
+    want = [_reg_rows(regs, qidx)[i] for i in key.tolist()]
+    got = _reg_rows(ov)
+    assert [r[0] for r in got] == sorted(r[0] for r in got)
+    assert got == want
 
 
 @pytest.mark.parametrize("platform", ["ont", "pb"])
@@ -321,7 +337,9 @@ def test_overlap_records_parity(ctx, platform):
     ov, cnt = ctx.twoset_overlaps(T, Q, platform)
     regs, qidx, _ = oracle.twoset_regs(T, Q, platform, threads=8, tie_mode=oracle.TIE_STABLE)
     assert ov.shape[0] == regs.shape[0] > 0
-    assert _reg_set(ov) == _reg_set(regs, qidx)
+    assert _reg_set(ov) == _reg_set(regs, qidx)          # every field incl. dv (mm_est_err) and rl (rep_len)
+    _assert_row_order(ov, regs, qidx)
+    assert (ov["dv"] >= 0).all() and ov["dv"].max() > 0.001
     plain = ctx.twoset_counts(T, Q, platform)
     assert np.array_equal(cnt.counts, plain.counts) and np.array_equal(cnt.had_mapping, plain.had_mapping)
     # the literal (unstable ksort) tie order gives the same rows here
@@ -331,7 +349,7 @@ def test_overlap_records_parity(ctx, platform):
     small, _ = ctx.twoset_overlaps(T, Q, platform, cap=8)
     assert small.shape[0] == ov.shape[0]
     line = lrge_b200.paf_line(ov[0], Q, T)
-    assert line.count(b"\t") == 16 and b"tp:A:S" in line
+    assert line.count(b"\t") == 16 and b"tp:A:S" in line and b"dv:f:0." in line
 
 
 def test_ava_overlap_records_parity(ctx):
@@ -340,6 +358,7 @@ def test_ava_overlap_records_parity(ctx):
     ov, cnt = ctx.ava_overlaps(R, "ont")
     regs, qidx, _ = oracle.twoset_regs(R, R, "ont", threads=8, tie_mode=oracle.TIE_STABLE, dual=False)
     assert _reg_set(ov) == _reg_set(regs, qidx)
+    _assert_row_order(ov, regs, qidx)                    # incl. the self-overlap rows (SEED_SELF enters the row hash)
     want, _ = oracle.ava_counts(R, "ont", threads=8)
     assert np.array_equal(cnt.counts, want)
 

@@ -101,7 +101,7 @@ def test_host_estimator_equals_oracle_bitwise():
 
 def test_paf_format_golden():   # mapping.rs:197-420: the serialised record of the reference's own test
     ov = np.zeros(1, lrge_b200.OVERLAP_DTYPE)
-    ov[0] = (0, 0, 1, 40, 237, 41, 238, 190, 59, 190, 197)
+    ov[0] = (0, 0, 1, 40, 237, 41, 238, 190, 59, 190, 197, 0.0022, 56)
     buf = ctypes.create_string_buffer(512)
     q, t = b"SRR28370649.1", b"SRR28370649.7311"
     n = lrge_b200.lib().lrge_paf_format(ov.ctypes.data, q, len(q), 4402, t, len(t), 5094, 0.0022, 56, buf, 512)
