@@ -195,6 +195,17 @@ int  lrge_fastx_count(const char *path, uint64_t *n_records, uint64_t *n_bases, 
 int  lrge_fastx_load(const char *path, uint8_t *bases, uint64_t cap_bases, uint64_t *off, uint64_t cap_records,
                      char *names, uint64_t cap_name_bytes, uint32_t *name_off);
 
+/* Two-pass subsampled ingestion (TwoSetStrategy::split_fastq, twoset.rs:122-201; AvaStrategy::subsample_reads,
+ * ava.rs:108-161): after lrge_fastx_count the caller draws its record indices (ascending, unique); this second pass keeps
+ * only those records and writes them straight into pinned (pinned != 0) host buffers, up to two disjoint selections in
+ * the same pass (target and query set; idx_b / out_b may be NULL).  A set keeps the file order of its records.
+ * hint_bases_per_record sizes the first allocation (0: 10 000); buffers grow on demand. */
+typedef struct lrge_hostset lrge_hostset;
+int  lrge_fastx_load_subsets(const char *path, const uint64_t *idx_a, uint64_t n_a, const uint64_t *idx_b, uint64_t n_b,
+                             uint64_t hint_bases_per_record, int pinned, lrge_hostset **out_a, lrge_hostset **out_b);
+const lrge_readset *lrge_hostset_view(lrge_hostset *h);   /* valid until lrge_hostset_free */
+void lrge_hostset_free(lrge_hostset *h);
+
 /* host-side estimator arithmetic (f32, evaluation order of estimate.rs) */
 float lrge_per_read_estimate(uint64_t read_len, float avg_target_len, uint64_t n_target_reads,
                              uint64_t n_ovlaps, uint32_t ovlap_thresh);

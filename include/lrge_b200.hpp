@@ -16,6 +16,7 @@
 #include <cctype>
 #include <cstdint>
 #include <limits>
+#include <memory>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -44,15 +45,17 @@ inline Platform platform_from_str(std::string s) {      // Platform::from_str (l
     throw LrgeError(LRGE_ERR_INVALID_PLATFORM, "Invalid platform: " + s);
 }
 
-// Reads in the layout the C ABI takes; owns its storage.
+// Reads in the layout the C ABI takes.  Either owns its storage (vectors below) or wraps a pinned lrge_hostset filled by
+// the two-pass subsampled loader (from_fastx_subsets).
 struct ReadSet {
     std::vector<uint8_t> bases;
     std::vector<uint64_t> off{0};
     std::string names;
     std::vector<uint32_t> name_off{0};
+    std::shared_ptr<lrge_hostset> host;      // set: the buffers live in (pinned) library memory, the vectors are unused
 
-    uint32_t size() const { return (uint32_t)(off.size() - 1); }
-    uint64_t total_bases() const { return off.back(); }
+    uint32_t size() const { return host ? lrge_hostset_view(host.get())->n : (uint32_t)(off.size() - 1); }
+    uint64_t total_bases() const { const lrge_readset v = view(); return v.n ? v.off[v.n] - v.off[0] : 0; }
     void push(const std::string &name, const std::string &seq) {
         bases.insert(bases.end(), seq.begin(), seq.end());
         off.push_back(bases.size());
@@ -60,9 +63,24 @@ struct ReadSet {
         name_off.push_back((uint32_t)names.size());
     }
     lrge_readset view() const {
+        if (host) return *lrge_hostset_view(host.get());
         lrge_readset v;
         v.bases = bases.data(); v.off = off.data(); v.names = names.data(); v.name_off = name_off.data(); v.n = size();
         return v;
+    }
+    // pass 2 of split_fastq / subsample_reads (twoset.rs:157-186, ava.rs:128-155): only the records idx_a / idx_b
+    // (ascending record numbers) are kept, straight into pinned buffers; idx_b may be empty
+    static std::pair<ReadSet, ReadSet> from_fastx_subsets(const std::string &path, const std::vector<uint64_t> &idx_a,
+                                                          const std::vector<uint64_t> &idx_b, uint64_t hint_bases_per_record = 0) {
+        lrge_hostset *a = nullptr, *b = nullptr;
+        const int rc = lrge_fastx_load_subsets(path.c_str(), idx_a.data(), idx_a.size(), idx_b.empty() ? nullptr : idx_b.data(), idx_b.size(),
+                                               hint_bases_per_record, 1, &a, idx_b.empty() ? nullptr : &b);
+        if (rc == LRGE_ERR_IO) throw LrgeError(LRGE_ERR_IO, "IO error: cannot read " + path);
+        if (rc != LRGE_OK) throw LrgeError((lrge_status)rc, "FASTQ parse error: " + path);
+        ReadSet A, B;
+        A.host.reset(a, lrge_hostset_free);
+        if (b) B.host.reset(b, lrge_hostset_free);
+        return {std::move(A), std::move(B)};
     }
     // plain or gzip FASTA / FASTQ; the read id is the header up to the first whitespace (io.rs:192-205)
     static ReadSet from_fastx(const std::string &path) {
@@ -108,10 +126,11 @@ inline void write_paf(const std::string &path, const std::vector<lrge_overlap> &
     FILE *f = fopen(path.c_str(), "w");
     if (!f) throw LrgeError(LRGE_ERR_PAF_WRITE, "PAF write error: cannot open " + path);
     char buf[2048];
+    const lrge_readset vq = Q.view(), vt = T.view();
     for (const lrge_overlap &o : ov) {
         const uint32_t q = o.query, t = o.target;
-        const int n = lrge_paf_format(&o, Q.names.data() + Q.name_off[q], (int)(Q.name_off[q + 1] - Q.name_off[q]), (int32_t)(Q.off[q + 1] - Q.off[q]),
-                                      T.names.data() + T.name_off[t], (int)(T.name_off[t + 1] - T.name_off[t]), (int32_t)(T.off[t + 1] - T.off[t]),
+        const int n = lrge_paf_format(&o, vq.names + vq.name_off[q], (int)(vq.name_off[q + 1] - vq.name_off[q]), (int32_t)(vq.off[q + 1] - vq.off[q]),
+                                      vt.names + vt.name_off[t], (int)(vt.name_off[t + 1] - vt.name_off[t]), (int32_t)(vt.off[t + 1] - vt.off[t]),
                                       o.dv, o.rl, buf, sizeof buf);
         if (n < 0 || fwrite(buf, 1, (size_t)n, f) != (size_t)n || fputc('\n', f) == EOF) { fclose(f); throw LrgeError(LRGE_ERR_PAF_WRITE, "PAF write error: " + path); }
     }
@@ -180,7 +199,7 @@ class TwoSetStrategy : public Estimate {
             }
             ov.resize(n);
             // with use_min_ref and more target than query bases the records name streamed target reads as queries
-            const bool inverse = opts_.use_min_ref && target_.bases.size() > query_.bases.size();
+            const bool inverse = opts_.use_min_ref && target_.total_bases() > query_.total_bases();
             write_paf(paf_path_, ov, inverse ? target_ : query_, inverse ? query_ : target_);
         }
         ctx.check(lrge_twoset_generate_estimates(ctx.get(), &t, &q, &opts_, est.data(), &no_mapping, &stats_));

@@ -37,6 +37,7 @@ C_API = [
     "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates", "lrge_gpu_comm_unique_id", "lrge_gpu_comm_init",
     "lrge_gpu_set_profiling", "lrge_gpu_kernel_times", "lrge_gpu_twoset_overlaps", "lrge_gpu_ava_overlaps", "lrge_paf_format",
     "lrge_gpu_dump_minimizers_block", "lrge_fastx_count", "lrge_fastx_load",
+    "lrge_fastx_load_subsets", "lrge_hostset_view", "lrge_hostset_free",
 ]
 
 
@@ -125,6 +126,11 @@ def lib():
                                       ctypes.c_float, ctypes.c_int32, ctypes.c_char_p, ctypes.c_size_t]
         L.lrge_fastx_count.argtypes = [ctypes.c_char_p, P(ctypes.c_uint64), P(ctypes.c_uint64), P(ctypes.c_uint64)]
         L.lrge_fastx_load.argtypes = [ctypes.c_char_p, vp, ctypes.c_uint64, vp, ctypes.c_uint64, vp, ctypes.c_uint64, vp]
+        L.lrge_fastx_load_subsets.argtypes = [ctypes.c_char_p, vp, ctypes.c_uint64, vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, P(vp), P(vp)]
+        L.lrge_hostset_view.argtypes = [vp]
+        L.lrge_hostset_view.restype = P(CReadSet)
+        L.lrge_hostset_free.argtypes = [vp]
+        L.lrge_hostset_free.restype = None
         L.lrge_gpu_host_alloc.argtypes = [ctypes.c_size_t, P(vp)]
         L.lrge_gpu_host_free.argtypes = [vp]
         L.lrge_gpu_host_free.restype = None
@@ -360,6 +366,31 @@ def read_fastx(path: str) -> ReadSet:
     if rc != 0:
         raise LrgeError(rc, path)
     return ReadSet(bases[:nb.value], off, names[:nn.value], noff)
+
+
+def read_fastx_subsets(path: str, idx_a, idx_b=None, pinned: bool = False):
+    """Pass 2 of the two-pass subsampled ingestion (lrge_fastx_load_subsets): the records idx_a (and idx_b) of the file, in
+    file order, as ReadSets (copied out of the library's buffers)."""
+    a = np.ascontiguousarray(idx_a, dtype=np.uint64)
+    b = np.ascontiguousarray(idx_b if idx_b is not None else [], dtype=np.uint64)
+    ha, hb = ctypes.c_void_p(), ctypes.c_void_p()
+    rc = lib().lrge_fastx_load_subsets(path.encode(), a.ctypes.data, a.shape[0], b.ctypes.data if b.shape[0] else None, b.shape[0], 0,
+                                       int(pinned), ctypes.byref(ha), ctypes.byref(hb) if idx_b is not None else None)
+    if rc != 0:
+        raise LrgeError(rc, path)
+
+    def take(h):
+        v = lib().lrge_hostset_view(h).contents
+        n = v.n
+        off = np.ctypeslib.as_array(ctypes.cast(v.off, ctypes.POINTER(ctypes.c_uint64)), shape=(n + 1,)).copy()
+        noff = np.ctypeslib.as_array(ctypes.cast(v.name_off, ctypes.POINTER(ctypes.c_uint32)), shape=(n + 1,)).copy()
+        bases = np.ctypeslib.as_array(ctypes.cast(v.bases, ctypes.POINTER(ctypes.c_uint8)), shape=(max(int(off[-1]), 1),))[:int(off[-1])].copy()
+        names = np.ctypeslib.as_array(ctypes.cast(v.names, ctypes.POINTER(ctypes.c_uint8)), shape=(max(int(noff[-1]), 1),))[:int(noff[-1])].copy()
+        lib().lrge_hostset_free(h)
+        return ReadSet(bases, off, names, noff)
+
+    A = take(ha)
+    return (A, take(hb)) if idx_b is not None else A
 
 
 def paf_line(ov, Q: ReadSet, T: ReadSet, dv=None, rl=None) -> bytes:

@@ -126,6 +126,115 @@ int lrge_fastx_load(const char *path, uint8_t *bases, uint64_t cap_bases, uint64
     return fits ? LRGE_OK : LRGE_ERR_INVALID_ARG;
 }
 
+// ---- two-pass subsampled ingestion (TwoSetStrategy::split_fastq, twoset.rs:122-201; AvaStrategy::subsample_reads,
+// ava.rs:108-161): pass 1 = lrge_fastx_count, the caller draws its record indices, pass 2 = this function, which keeps
+// only the selected records and writes them straight into PINNED host buffers (what the H2D copies of the *_counts calls
+// want), without ever holding the whole file in memory.  Up to two disjoint selections are filled in the same pass
+// (target and query set).  Indices must be ascending and unique (liblrge sorts nothing, it tests HashSet membership;
+// here the order of a set is the file order, as in the temp FASTA liblrge writes).
+struct lrge_hostset {
+    uint8_t *bases = nullptr; uint64_t *off = nullptr; char *names = nullptr; uint32_t *name_off = nullptr;
+    uint64_t cap_bases = 0, cap_names = 0, n = 0, cap_n = 0;
+    bool pinned = false;
+    lrge_readset view{};
+};
+
+namespace {
+
+void *hs_alloc(size_t bytes, bool pinned) {
+    void *p = nullptr;
+    if (pinned) { if (lrge_gpu_host_alloc(bytes ? bytes : 1, &p) != LRGE_OK) p = nullptr; }
+    else p = malloc(bytes ? bytes : 1);
+    return p;
+}
+void hs_free(void *p, bool pinned) { if (!p) return; if (pinned) lrge_gpu_host_free(p); else free(p); }
+
+bool hs_grow(lrge_hostset *h, uint64_t need_bases, uint64_t need_names) {
+    if (need_bases > h->cap_bases) {
+        const uint64_t cap = std::max<uint64_t>(need_bases + need_bases / 4, 1 << 20);
+        uint8_t *nb = (uint8_t *)hs_alloc(cap, h->pinned);
+        if (!nb) return false;
+        if (h->bases) { memcpy(nb, h->bases, h->off[h->n]); hs_free(h->bases, h->pinned); }
+        h->bases = nb; h->cap_bases = cap;
+    }
+    if (need_names > h->cap_names) {
+        const uint64_t cap = std::max<uint64_t>(need_names + need_names / 4, 1 << 16);
+        char *nn = (char *)hs_alloc(cap, h->pinned);
+        if (!nn) return false;
+        if (h->names) { memcpy(nn, h->names, h->name_off[h->n]); hs_free(h->names, h->pinned); }
+        h->names = nn; h->cap_names = cap;
+    }
+    return true;
+}
+
+lrge_hostset *hs_new(uint64_t n, uint64_t hint_bases, bool pinned) {
+    lrge_hostset *h = new lrge_hostset();
+    h->pinned = pinned; h->cap_n = n;
+    h->off = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+    h->name_off = (uint32_t *)malloc((n + 1) * sizeof(uint32_t));
+    if (!h->off || !h->name_off) { free(h->off); free(h->name_off); delete h; return nullptr; }
+    h->off[0] = 0; h->name_off[0] = 0;
+    if (!hs_grow(h, std::max<uint64_t>(hint_bases, 1), std::max<uint64_t>(n * 40, 1))) { free(h->off); free(h->name_off); delete h; return nullptr; }
+    return h;
+}
+
+}  // namespace
+
+void lrge_hostset_free(lrge_hostset *h) {
+    if (!h) return;
+    hs_free(h->bases, h->pinned); hs_free(h->names, h->pinned);
+    free(h->off); free(h->name_off);
+    delete h;
+}
+
+const lrge_readset *lrge_hostset_view(lrge_hostset *h) {
+    if (!h) return nullptr;
+    h->view.bases = h->bases; h->view.off = h->off; h->view.names = h->names; h->view.name_off = h->name_off; h->view.n = (uint32_t)h->n;
+    return &h->view;
+}
+
+int lrge_fastx_load_subsets(const char *path, const uint64_t *idx_a, uint64_t n_a, const uint64_t *idx_b, uint64_t n_b,
+                            uint64_t hint_bases_per_record, int pinned, lrge_hostset **out_a, lrge_hostset **out_b) {
+    if (!path || !out_a || (n_a && !idx_a) || (n_b && (!idx_b || !out_b))) return LRGE_ERR_INVALID_ARG;
+    for (uint64_t i = 1; i < n_a; ++i) if (idx_a[i] <= idx_a[i - 1]) return LRGE_ERR_INVALID_ARG;
+    for (uint64_t i = 1; i < n_b; ++i) if (idx_b[i] <= idx_b[i - 1]) return LRGE_ERR_INVALID_ARG;
+    if (n_a >= (1ull << 32) || n_b >= (1ull << 32)) return LRGE_ERR_TOO_MANY_READS;
+    const uint64_t hint = hint_bases_per_record ? hint_bases_per_record : 10000;
+    bool pin = pinned != 0;
+    if (pin) {                                   // no usable CUDA runtime: plain memory (the GPU call will fail loudly later)
+        void *probe = nullptr;
+        if (lrge_gpu_host_alloc(16, &probe) == LRGE_OK) lrge_gpu_host_free(probe); else pin = false;
+    }
+    lrge_hostset *A = hs_new(n_a, n_a * hint + n_a * hint / 8, pin);
+    lrge_hostset *B = out_b ? hs_new(n_b, n_b * hint + n_b * hint / 8, pin) : nullptr;
+    if (!A || (out_b && !B)) { lrge_hostset_free(A); lrge_hostset_free(B); return LRGE_ERR_OUT_OF_MEMORY; }
+    uint64_t rec = 0, ia = 0, ib = 0;
+    bool oom = false, big_names = false;
+    auto push = [&](lrge_hostset *h, const char *id, size_t il, const char *seq, size_t sl) {
+        const uint64_t b = h->off[h->n], nb = h->name_off[h->n];
+        if (nb + il > 0xffffffffull) { big_names = true; return; }
+        if (!hs_grow(h, b + sl, nb + il)) { oom = true; return; }
+        memcpy(h->bases + b, seq, sl);
+        memcpy(h->names + nb, id, il);
+        ++h->n; h->off[h->n] = b + sl; h->name_off[h->n] = (uint32_t)(nb + il);
+    };
+    const int rc = for_each_record(path, [&](const char *id, size_t il, const char *seq, size_t sl) {
+        if (!oom && !big_names) {
+            if (ia < n_a && idx_a[ia] == rec) { push(A, id, il, seq, sl); ++ia; }
+            else if (ib < n_b && idx_b[ib] == rec) { push(B, id, il, seq, sl); ++ib; }
+        }
+        ++rec;
+    });
+    int err = rc;
+    if (err == LRGE_OK && oom) err = LRGE_ERR_OUT_OF_MEMORY;
+    if (err == LRGE_OK && big_names) err = LRGE_ERR_INVALID_ARG;
+    if (err == LRGE_OK && (ia != n_a || ib != n_b)) err = LRGE_ERR_INVALID_ARG;     // an index beyond the last record
+    if (err != LRGE_OK) { lrge_hostset_free(A); lrge_hostset_free(B); return err; }
+    *out_a = A;
+    if (out_b) *out_b = B;
+    return LRGE_OK;
+}
+
 float lrge_per_read_estimate(uint64_t read_len, float avg_target_len, uint64_t n_target_reads, uint64_t n_ovlaps,
                              uint32_t ovlap_thresh) {
     if (n_ovlaps == 0) return std::numeric_limits<float>::infinity();

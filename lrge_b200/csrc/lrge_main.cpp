@@ -125,15 +125,22 @@ int main(int argc, char **argv) {
     const Args a = parse(argc, argv);
     try {
         const lrge::Platform platform = lrge::platform_from_str(a.platform);
-        lrge::ReadSet all = lrge::ReadSet::from_fastx(a.input);
-        const uint32_t n_fq = all.size();
+        // pass 1 of split_fastq / subsample_reads: count the records (io::count_records, twoset.rs:124, ava.rs:110)
+        uint64_t n_rec = 0, n_bases = 0, n_name_bytes = 0;
+        {
+            const int rc = lrge_fastx_count(a.input.c_str(), &n_rec, &n_bases, &n_name_bytes);
+            if (rc == LRGE_ERR_IO) throw lrge::LrgeError(LRGE_ERR_IO, "IO error: cannot read " + a.input + " (is the file empty?)");
+            if (rc == LRGE_ERR_UNSUPPORTED) throw lrge::LrgeError(LRGE_ERR_UNSUPPORTED, "unsupported compression: " + a.input);
+            if (rc != LRGE_OK) throw lrge::LrgeError(LRGE_ERR_FASTQ_PARSE, "FASTQ parse error: " + a.input);
+            if (n_rec > 0xffffffffull) throw lrge::LrgeError(LRGE_ERR_TOO_MANY_READS, "Too many reads");   // twoset.rs:126-130
+        }
+        const uint32_t n_fq = (uint32_t)n_rec;
+        const uint64_t hint = n_rec ? n_bases / n_rec + 1 : 0;
         const uint64_t seed = a.seeded ? a.seed : (uint64_t)time(nullptr);
-        auto take = [&](const std::vector<uint32_t> &sorted_idx) {
-            lrge::ReadSet rs;
-            for (uint32_t i : sorted_idx)
-                rs.push(all.names.substr(all.name_off[i], all.name_off[i + 1] - all.name_off[i]),
-                        std::string(all.bases.begin() + all.off[i], all.bases.begin() + all.off[i + 1]));
-            return rs;
+        // pass 2: only the selected records are kept, straight into pinned buffers
+        auto take = [&](const std::vector<uint32_t> &sa, const std::vector<uint32_t> &sb) {
+            return lrge::ReadSet::from_fastx_subsets(a.input, std::vector<uint64_t>(sa.begin(), sa.end()),
+                                                     std::vector<uint64_t>(sb.begin(), sb.end()), hint);
         };
         lrge::EstimateResult res;
         const std::string paf_path = a.keep_temp ? (a.temp_dir.empty() ? std::string("overlaps.paf") : a.temp_dir + "/overlaps.paf") : std::string();
@@ -143,7 +150,7 @@ int main(int argc, char **argv) {
             auto idx = unique_random_set(n, n_fq, seed);
             std::sort(idx.begin(), idx.end());
             auto strat = lrge::AvaStrategy::Builder().platform(platform).remove_internal(a.filter_contained)
-                             .max_overhang_ratio(a.max_overhang_ratio).device(a.device).paf(paf_path).build(take(idx));
+                             .max_overhang_ratio(a.max_overhang_ratio).device(a.device).paf(paf_path).build(take(idx, {}).first);
             res = strat.estimate(!a.with_infinity, a.q1, a.q3);
         } else {                                                  // TwoSetStrategy (twoset.rs:122-201)
             size_t T = a.target, Q = a.query;
@@ -153,9 +160,10 @@ int main(int argc, char **argv) {
             // split_into_hashsets pops from the END: the last T indices are the targets (twoset.rs:632-652)
             std::vector<uint32_t> t(idx.end() - T, idx.end()), q(idx.begin(), idx.end() - T);
             std::sort(t.begin(), t.end()); std::sort(q.begin(), q.end());
+            auto sets = take(t, q);
             auto strat = lrge::TwoSetStrategy::Builder().platform(platform).remove_internal(a.filter_contained)
                              .max_overhang_ratio(a.max_overhang_ratio).use_min_ref(a.use_min_ref).device(a.device).paf(paf_path)
-                             .build(take(t), take(q));
+                             .build(std::move(sets.first), std::move(sets.second));
             res = strat.estimate(!a.with_infinity, a.q1, a.q3);
         }
         if (!res.estimate) {

@@ -660,7 +660,10 @@ static orc128_t *collect_seed_hits(const orc_opt_t *opt, int max_occ, const orc_
             int32_t is_self, rpos = (uint32_t)r[k] >> 1;
             orc128_t *p;
             if (skip_seed(opt->flag, r[k], q, qname, qlen, mi, &is_self)) continue;
-            if (opt->shard_count > 1 && (int32_t)((r[k] >> 32) % (uint32_t)opt->shard_count) != opt->shard_index) continue;
+            if (opt->shard_count > 1) {     /* contiguous target blocks, as the CUDA path shards: [n*i/W, n*(i+1)/W) */
+                const uint64_t rid = r[k] >> 32, n = mi->n_seq, W = (uint64_t)opt->shard_count, i = (uint64_t)opt->shard_index;
+                if (rid < n * i / W || rid >= n * (i + 1) / W) continue;
+            }
             p = &a[(*n_a)++];
             if ((r[k] & 1) == (q->q_pos & 1)) {
                 p->x = (r[k] & 0xffffffff00000000ULL) | rpos;

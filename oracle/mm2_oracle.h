@@ -62,8 +62,9 @@ typedef struct {
     int32_t max_occ, occ_dist, max_max_occ;
     int32_t seed;
     int32_t tie_mode;
-    /* target sharding as the CUDA path does it (not minimap2): keep only hits with rid % shard_count == shard_index;
-     * occurrence filtering still sees the whole index. shard_count <= 1 disables it. */
+    /* target sharding as the CUDA path does it (not minimap2): keep only hits of the contiguous target block
+     * [n*shard_index/shard_count, n*(shard_index+1)/shard_count); occurrence filtering still sees the whole index.
+     * shard_count <= 1 disables it. */
     int32_t shard_index, shard_count;
 } orc_opt_t;
 

@@ -67,3 +67,26 @@ def test_errors(tmp_path):
     with pytest.raises(lrge_b200.LrgeError) as e:
         lrge_b200.read_fastx(str(bz))
     assert e.value.kind == "Unsupported"
+
+
+def test_two_pass_subsampled_ingestion(tmp_path, reads):
+    """split_fastq / subsample_reads (twoset.rs:122-201, ava.rs:108-161): pass 1 counts, pass 2 keeps only the drawn
+    records, two disjoint sets in one pass, file order inside a set; plain, gzip and FASTQ."""
+    fa = tmp_path / "r.fa"
+    reads.write_fasta(str(fa))
+    gz = tmp_path / "r.fq.gz"
+    with gzip.open(gz, "wb") as fh:
+        for i in range(reads.n):
+            s = reads.seq(i)
+            fh.write(b"@" + reads.name(i) + b" x\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    rng = np.random.default_rng(1)
+    pick = rng.permutation(reads.n)[:25]
+    ia, ib = np.sort(pick[:15]), np.sort(pick[15:])
+    for path in (fa, gz):
+        A, B = lrge_b200.read_fastx_subsets(str(path), ia, ib)
+        assert same(A, reads.subset(ia)) and same(B, reads.subset(ib))
+    only = lrge_b200.read_fastx_subsets(str(fa), ia)
+    assert same(only, reads.subset(ia))
+    for bad in ([3, 3], [5, 2], [reads.n]):             # duplicates, descending, beyond the last record
+        with pytest.raises(lrge_b200.LrgeError):
+            lrge_b200.read_fastx_subsets(str(fa), bad)

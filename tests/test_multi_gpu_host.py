@@ -1,6 +1,8 @@
-"""world_size-2 `gloo` test of the multi-GPU host logic on CPU: target shards (rid % world) are additive under
-GLOBAL occurrence filtering, and the reduction the library does with NCCL (sum of counts, max of had_mapping)
-reproduces the single-process result.  The oracle stands in for the per-shard compute (tests only)."""
+"""world_size-2 `gloo` test of the multi-GPU scheme on CPU: contiguous target blocks [n*r/W, n*(r+1)/W) -- the product's
+shard_range -- are additive under GLOBAL occurrence filtering, and the reduction the library does with NCCL (sum of
+counts, max of had_mapping) reproduces the single-process result.  There is no GPU here, so the oracle stands in for the
+per-shard compute (tests only); the product's own sharded path is checked on hardware by bench.py at every N > 1
+(cpu_baseline.parity) and by tests/test_gpu_parity.py::test_target_sharding_is_additive."""
 import os
 import sys
 
@@ -33,6 +35,9 @@ def _worker(rank, world, port, out):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max-over-ranks timing reduce used by bench.py
     if rank == 0:
         full, full_had, full_st = oracle.twoset_counts(T, Q, "ont", threads=2)
+        # the block boundaries of the product (lrge_gpu.cu shard_range): every target belongs to exactly one rank
+        blocks = [(T.n * r // world, T.n * (r + 1) // world) for r in range(world)]
+        out["ok_blocks"] = blocks[0][0] == 0 and blocks[-1][1] == T.n and all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
         out["ok_counts"] = bool(np.array_equal(c.numpy(), full.astype(np.int64)))
         out["ok_had"] = bool(np.array_equal(h.numpy(), full_had.astype(np.int64)))
         out["ok_mid"] = st["mid_occ"] == full_st["mid_occ"]
@@ -48,5 +53,5 @@ def test_two_rank_sharded_counts_reduce_to_full():
         out = m.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         res = dict(out)
-    assert res["ok_counts"] and res["ok_had"] and res["ok_mid"] and res["ok_max"]
+    assert res["ok_counts"] and res["ok_had"] and res["ok_mid"] and res["ok_max"] and res["ok_blocks"]
     assert res["overlaps"] > 0
