@@ -28,7 +28,10 @@ __global__ void bucket_bounds_kernel(const uint64_t *__restrict__ tx, uint64_t M
 // K2b + K3 fused: one coalesced pass over the sorted keys writes the bucket table and the occurrence histogram.
 // Run lengths come from the warp's run-start ballot; only the last run of each warp may continue into the next
 // warp's elements and is finished by galloping.  hist[OCC_BINS] bins + hist[OCC_BINS] = number of keys.
-__global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restrict__ tx, uint64_t M, int shift, uint32_t nb,
+// XT = uint64_t: tx holds hash << 8 | span (KSH = 8), the compact keys tk32 are written here.
+// XT = uint32_t: tx IS the compact key array (sorted 32-bit hashes, KSH = 0), nothing to write.
+template <typename XT, int KSH>
+__global__ void __launch_bounds__(256) index_post_kernel(const XT *__restrict__ tx, uint64_t M, int shift, uint32_t nb,
                                                          uint32_t *__restrict__ boff, uint32_t *__restrict__ tk32,
                                                          unsigned long long *hist) {
     __shared__ unsigned int sh[OCC_BINS];
@@ -41,12 +44,12 @@ __global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restr
     for (uint64_t r = 0; r < rounds; ++r) {
         const uint64_t i = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // warp-contiguous
         const bool in = i < M;
-        const uint64_t x = in ? tx[i] : 0;
+        const uint64_t x = in ? (uint64_t)tx[i] : 0;
         // the element after the warp's last one, fetched together with the main load (ends most boundary runs)
-        const uint64_t xnext = (lane == 31 && i + 1 < M) ? tx[i + 1] : 0;
+        const uint64_t xnext = (lane == 31 && i + 1 < M) ? (uint64_t)tx[i + 1] : 0;
         uint64_t xp = __shfl_up_sync(0xffffffffu, x, 1);
-        if (lane == 0 && i > 0 && i <= M) xp = tx[i - 1];
-        if (in) tk32[i] = (uint32_t)(x >> 8);                     // compact lookup keys (low 32 bits of the hash)
+        if (lane == 0 && i > 0 && i <= M) xp = (uint64_t)tx[i - 1];
+        if (KSH && in) tk32[i] = (uint32_t)(x >> KSH);            // compact lookup keys (low 32 bits of the hash)
         // bucket table: boff[b] = first i with bucket >= b
         if (i <= M) {
             const int32_t b_prev = i == 0 ? -1 : (int32_t)(xp >> shift);
@@ -54,10 +57,10 @@ __global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restr
             for (int32_t b = b_prev + 1; b <= b_cur; ++b) boff[b] = (uint32_t)i;
         }
         // occurrence of every key that STARTS in this warp
-        const bool start = in && (i == 0 || (xp >> 8) != (x >> 8));
+        const bool start = in && (i == 0 || (xp >> KSH) != (x >> KSH));
         const uint32_t S = __ballot_sync(0xffffffffu, start);
         const uint32_t valid = __ballot_sync(0xffffffffu, in);
-        const uint64_t key_next = __shfl_sync(0xffffffffu, xnext, 31) >> 8;
+        const uint64_t key_next = __shfl_sync(0xffffffffu, xnext, 31) >> KSH;
         const bool full_warp = valid == 0xffffffffu;
         uint64_t n = 0;
         if (start) {
@@ -66,16 +69,16 @@ __global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restr
             else {
                 const uint32_t nvalid = __popc(valid);
                 const uint64_t last = i + (nvalid - 1 - lane);         // last element of the warp, same key
-                const uint64_t key = x >> 8;
+                const uint64_t key = x >> KSH;
                 if (!full_warp || last + 1 >= M || key_next != key) n = last - i + 1;
                 else {
                     // the run continues past the prefetched element: finish it by galloping
                     uint64_t lo = last + 1, step = 1;
-                    while (lo + step < M && (tx[lo + step] >> 8) == key) { lo += step; step <<= 1; }
+                    while (lo + step < M && ((uint64_t)tx[lo + step] >> KSH) == key) { lo += step; step <<= 1; }
                     uint64_t hi = lo + step < M ? lo + step : M;
                     while (hi - lo > 1) {
                         const uint64_t mid = (lo + hi) >> 1;
-                        if ((tx[mid] >> 8) == key) lo = mid; else hi = mid;
+                        if (((uint64_t)tx[mid] >> KSH) == key) lo = mid; else hi = mid;
                     }
                     n = hi - i;
                 }
@@ -94,6 +97,12 @@ __global__ void __launch_bounds__(256) index_post_kernel(const uint64_t *__restr
     if (lane == 0 && my_keys) atomicAdd(&hist[OCC_BINS], (unsigned long long)my_keys);
 }
 
+// 32-bit hashes of the (read, position)-ordered minimizers: the sort keys of the single-GPU index for 2k <= 32
+__global__ void key32_kernel(const uint64_t *__restrict__ x, uint64_t M, uint32_t *__restrict__ k32) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) k32[i] = (uint32_t)(x[i] >> 8);
+}
+
 // sharded path: the compact lookup keys alone
 __global__ void tk32_kernel(const uint64_t *__restrict__ tx, uint64_t M, uint32_t *__restrict__ tk32) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,18 +111,19 @@ __global__ void tk32_kernel(const uint64_t *__restrict__ tx, uint64_t M, uint32_
 
 // Run lengths that fell into the overflow bin, collected for an exact order statistic on the host
 // (only reached when the mid_occ rank lands among keys occurring >= OCC_BINS-1 times).
-__global__ void occ_overflow_kernel(const uint64_t *__restrict__ tx, uint64_t M, uint32_t *out, unsigned long long *n_out,
+template <typename XT, int KSH>
+__global__ void occ_overflow_kernel(const XT *__restrict__ tx, uint64_t M, uint32_t *out, unsigned long long *n_out,
                                     uint64_t cap) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t key = tx[i] >> 8;
-        if (i > 0 && (tx[i - 1] >> 8) == key) continue;
-        if (i + OCC_BINS - 2 >= M || (tx[i + OCC_BINS - 2] >> 8) != key) continue;   // n < OCC_BINS-1
+        const uint64_t key = (uint64_t)tx[i] >> KSH;
+        if (i > 0 && ((uint64_t)tx[i - 1] >> KSH) == key) continue;
+        if (i + OCC_BINS - 2 >= M || ((uint64_t)tx[i + OCC_BINS - 2] >> KSH) != key) continue;   // n < OCC_BINS-1
         uint64_t lo = i + OCC_BINS - 2, step = 1;
-        while (lo + step < M && (tx[lo + step] >> 8) == key) { lo += step; step <<= 1; }
+        while (lo + step < M && ((uint64_t)tx[lo + step] >> KSH) == key) { lo += step; step <<= 1; }
         uint64_t hi = lo + step < M ? lo + step : M;
         while (hi - lo > 1) {
             const uint64_t mid = (lo + hi) >> 1;
-            if ((tx[mid] >> 8) == key) lo = mid; else hi = mid;
+            if (((uint64_t)tx[mid] >> KSH) == key) lo = mid; else hi = mid;
         }
         const unsigned long long slot = atomicAdd(n_out, 1ull);
         if (slot < cap) out[slot] = (uint32_t)(hi - i);

@@ -624,7 +624,7 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
     c->prof.send(ST_SKETCH);
 }
 
-struct BuiltIndex { IndexView view; int mid_occ; uint64_t n_keys; };
+struct BuiltIndex { IndexView view; int mid_occ; uint64_t n_keys; bool x32 = false; };
 
 // K2 + K3.  build_index_launch queues the sort, the bucket table and the occurrence histogram (+ its copy to pinned
 // host memory) and returns; build_index_finish -- after any later synchronisation of the stream -- turns the histogram
@@ -633,37 +633,60 @@ BuiltIndex build_index_launch(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     BuiltIndex B{};
     const uint64_t M = sk.M;
     if (M >= (1ull << 32) - 2) throw std::length_error("more than 2^32 target minimizers per GPU are not supported");
-    c->tx.reserve((M + 1) * 8);
-    c->ty.reserve((M + 1) * 8);
-    if (M) {
-        size_t tb = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
-                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
-        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", 32.0 * M,
-                cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
-                                                c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
-        c->launches += (2 * o.k + 7) / 8;
-        c->prof.set_passes("cub::DeviceRadixSort(index: u64 key, u64 value)", (2 * o.k + 7) / 8);
-    }
     // ~8 entries per bucket: the table (4 B x 2^bits) stays L2-resident, a lookup bisects <= 3 steps
     int bits = 8;
     while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
     if (bits < 2 * o.k - 32) bits = 2 * o.k - 32;              // tk32: the in-bucket part of a key must fit 32 bits
     const uint32_t nb = 1u << bits;
-    const int shift = 8 + 2 * o.k - bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
-    // bucket table + occurrence histogram -> mid_occ (mm_idx_cal_max_occ + mm_mapopt_update), one pass over the keys
     c->hist.reserve((OCC_BINS + 2) * 8);
     CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));
     unsigned long long *hist = c->hist.as<unsigned long long>();
+    c->ty.reserve((M + 1) * 8);
     c->tk32.reserve((M + 64) * 4);
-    CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));          // slack read by the 8-wide bucket fetch
-    KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
-            index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(), hist));
+    const bool k32 = !o.is_hpc && 2 * o.k <= 32;               // ava-ont: the key is the 30-bit hash alone (span = k)
+    B.x32 = k32;
+    size_t tb = 0;
+    if (k32) {
+        // sort (32-bit hash, y): 12-byte records instead of 16, and the sorted keys ARE the compact lookup keys
+        c->ukey.reserve((M + 1) * 4);
+        if (M) {
+            KLAUNCH(c, "key32_kernel", 12.0 * M,
+                    key32_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(sk.x.as<uint64_t>(), M, c->ukey.as<uint32_t>()));
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, c->ukey.as<uint32_t>(), c->tk32.as<uint32_t>(), sk.y.as<uint64_t>(), c->ty.as<uint64_t>(),
+                                            (int64_t)M, 0, 2 * o.k, c->stream);
+            KLAUNCH(c, "cub::DeviceRadixSort(index: u32 key, u64 value)", 32.0 * M,       // 2 x 16 x M_T
+                    cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->ukey.as<uint32_t>(), c->tk32.as<uint32_t>(), sk.y.as<uint64_t>(),
+                                                    c->ty.as<uint64_t>(), (int64_t)M, 0, 2 * o.k, c->stream));
+            c->launches += (2 * o.k + 7) / 8;
+            c->prof.set_passes("cub::DeviceRadixSort(index: u32 key, u64 value)", (2 * o.k + 7) / 8);
+        }
+        CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));          // slack read by the 8-wide bucket fetch
+        const int shift = 2 * o.k - bits;
+        KLAUNCH(c, "index_post_kernel", 4.0 * M + 4.0 * nb,
+                (index_post_kernel<uint32_t, 0><<<148 * 8, 256, 0, c->stream>>>(c->tk32.as<uint32_t>(), M, shift, nb, c->boff.as<uint32_t>(), nullptr, hist)));
+        B.view.tx = nullptr; B.view.shift = 8 + shift;          // index_lookup shifts hash << 8
+    } else {
+        c->tx.reserve((M + 1) * 8);
+        if (M) {
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                            c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
+            KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", 32.0 * M,
+                    cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                                    c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
+            c->launches += (2 * o.k + 7) / 8;
+            c->prof.set_passes("cub::DeviceRadixSort(index: u64 key, u64 value)", (2 * o.k + 7) / 8);
+        }
+        CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));          // slack read by the 8-wide bucket fetch
+        const int shift = 8 + 2 * o.k - bits;
+        KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
+                (index_post_kernel<uint64_t, 8><<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(), hist)));
+        B.view.tx = c->tx.as<uint64_t>(); B.view.shift = shift;
+    }
     CUDA_CHECK(cudaMemcpyAsync(c->hist_h(), hist, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaGetLastError());
-    B.view.tx = c->tx.as<uint64_t>(); B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
-    B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
+    B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.M = M; B.view.bl = nullptr;
     B.mid_occ = -1; B.n_keys = 0;
     return B;
 }
@@ -684,7 +707,8 @@ void build_index_finish(lrge_ctx *c, const MapOpt &o, BuiltIndex *Bp) {       //
             const uint64_t n_over = h[OCC_BINS - 1];
             DevBuf over; over.reserve((n_over + 1) * 4);
             CUDA_CHECK(cudaMemsetAsync(hist + OCC_BINS + 1, 0, 8, c->stream));
-            occ_overflow_kernel<<<148 * 4, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, over.as<uint32_t>(), hist + OCC_BINS + 1, n_over);
+            if (B.x32) occ_overflow_kernel<uint32_t, 0><<<148 * 4, 256, 0, c->stream>>>(c->tk32.as<uint32_t>(), M, over.as<uint32_t>(), hist + OCC_BINS + 1, n_over);
+            else occ_overflow_kernel<uint64_t, 8><<<148 * 4, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, over.as<uint32_t>(), hist + OCC_BINS + 1, n_over);
             ++c->launches;
             std::vector<uint32_t> ov(n_over);
             CUDA_CHECK(cudaMemcpyAsync(ov.data(), over.p, n_over * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -915,8 +939,8 @@ ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOp
     c->tk32.reserve((M + 64) * 4);
     CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));
     KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
-            index_post_kernel<<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(),
-                                                              c->hist.as<unsigned long long>()));
+            (index_post_kernel<uint64_t, 8><<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(),
+                                                                            c->hist.as<unsigned long long>())));
     // distinct local keys, packed with their counts, in key order
     c->flags.reserve(M + 1);
     c->pstart.reserve((M + 2) * 4);
