@@ -326,7 +326,7 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
     # ---- the other BASELINE.json configurations, verified over all reads (N = 1: C1, C3, C4; N = 4: C4) -------
-    names = [n for n in args.configs.split(",") if n] if args.configs != "auto" else \
+    names = [n for n in args.configs.split(",") if n and n != "none"] if args.configs != "auto" else \
         (["C1", "C3", "C4"] if world == 1 else ["C4"] if world == 4 else [])
     if args.no_cpu_baseline:
         names = []

@@ -113,6 +113,15 @@ const char *lrge_gpu_last_error(const lrge_ctx *ctx);   /* ctx may be NULL: last
  *   had_mapping[Q->n] 1 if mm_map returned any region for the read (twoset.rs:288); may be NULL */
 int  lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_readset *Q, const lrge_opts *opts,
                             uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats);
+/* The same for target sets that do not fit one host: every rank of the communicator (lrge_gpu_comm_init) passes ONLY ITS
+ * block of the target reads (any partition; blocks need not be equal) and ALL query reads; opts->shard_index / shard_count
+ * = rank / world; use_min_ref must be 0.  The minimizer occurrence counts and mid_occ are made global by the index
+ * exchange, so every rank returns the complete per-query counts -- identical to one lrge_gpu_twoset_counts call on the
+ * concatenated target set.  Name rules (twoset.rs:286-302 dedupe of equal target names, equal query/target names) see the
+ * names of the local block only: target names must be unique across blocks.  This is how README.md:173-175's
+ * 2 000 000-target human read set is meant to run (8 ranks x 250 000 targets). */
+int  lrge_gpu_twoset_counts_shard(lrge_ctx *ctx, const lrge_readset *T_block, const lrge_readset *Q, const lrge_opts *opts,
+                                  uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats);
 /* counts[R->n]: unique overlapping partners per read (ava.rs:265-306) */
 int  lrge_gpu_ava_counts(lrge_ctx *ctx, const lrge_readset *R, const lrge_opts *opts,
                          uint32_t *counts, lrge_stats *stats);

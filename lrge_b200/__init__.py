@@ -34,7 +34,7 @@ C_API = [
     "lrge_gpu_twoset_counts", "lrge_gpu_ava_counts", "lrge_gpu_stage", "lrge_gpu_unstage",
     "lrge_gpu_twoset_counts_staged", "lrge_gpu_ava_counts_staged", "lrge_gpu_host_alloc", "lrge_gpu_host_free",
     "lrge_gpu_dump_minimizers", "lrge_gpu_dump_mid_occ", "lrge_per_read_estimate", "lrge_estimate", "lrge_is_internal",
-    "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates", "lrge_gpu_comm_unique_id", "lrge_gpu_comm_init",
+    "lrge_twoset_generate_estimates", "lrge_ava_generate_estimates", "lrge_gpu_comm_unique_id", "lrge_gpu_comm_init", "lrge_gpu_twoset_counts_shard",
     "lrge_gpu_set_profiling", "lrge_gpu_kernel_times", "lrge_gpu_twoset_overlaps", "lrge_gpu_ava_overlaps", "lrge_paf_format",
     "lrge_gpu_dump_minimizers_block", "lrge_fastx_count", "lrge_fastx_load",
     "lrge_fastx_load_subsets", "lrge_hostset_view", "lrge_hostset_free",
@@ -110,6 +110,7 @@ def lib():
         L.lrge_gpu_last_error.argtypes = [vp]
         L.lrge_gpu_last_error.restype = ctypes.c_char_p
         L.lrge_gpu_twoset_counts.argtypes = [vp, P(CReadSet), P(CReadSet), P(Opts), vp, vp, P(Stats)]
+        L.lrge_gpu_twoset_counts_shard.argtypes = [vp, P(CReadSet), P(CReadSet), P(Opts), vp, vp, P(Stats)]
         L.lrge_gpu_ava_counts.argtypes = [vp, P(CReadSet), P(Opts), vp, P(Stats)]
         L.lrge_gpu_stage.argtypes = [vp, P(CReadSet), P(vp)]
         L.lrge_gpu_unstage.argtypes = [vp, vp]
@@ -282,6 +283,16 @@ class Context:
             ct, cq = as_c(T), as_c(Q)
             self._check(lib().lrge_gpu_twoset_counts(self.h, ctypes.byref(ct), ctypes.byref(cq), ctypes.byref(o),
                                                      counts.ctypes.data, had.ctypes.data, ctypes.byref(st)))
+        return Counts(counts, had, st.as_dict())
+
+    def twoset_counts_shard(self, T_block, Q, platform="ont", **kw) -> Counts:
+        """lrge_gpu_twoset_counts_shard: this rank's block of the targets + all queries (needs comm_init)."""
+        o = make_opts(platform, **kw)
+        st = Stats()
+        counts, had = np.zeros(Q.n, np.uint32), np.zeros(Q.n, np.uint8)
+        ct, cq = as_c(T_block), as_c(Q)
+        self._check(lib().lrge_gpu_twoset_counts_shard(self.h, ctypes.byref(ct), ctypes.byref(cq), ctypes.byref(o),
+                                                       counts.ctypes.data, had.ctypes.data, ctypes.byref(st)))
         return Counts(counts, had, st.as_dict())
 
     def ava_counts(self, R, platform="ont", **kw) -> Counts:

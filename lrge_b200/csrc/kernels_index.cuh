@@ -33,7 +33,7 @@ __global__ void bucket_bounds_kernel(const uint64_t *__restrict__ tx, uint64_t M
 template <typename XT, int KSH>
 __global__ void __launch_bounds__(256) index_post_kernel(const XT *__restrict__ tx, uint64_t M, int shift, uint32_t nb,
                                                          uint32_t *__restrict__ boff, uint32_t *__restrict__ tk32,
-                                                         unsigned long long *hist) {
+                                                         unsigned long long *hist, uint32_t *__restrict__ run_n = nullptr) {
     __shared__ unsigned int sh[OCC_BINS];
     for (int i = threadIdx.x; i < OCC_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(256) index_post_kernel(const XT *__restrict__ 
             }
             ++my_keys;
         }
+        // sharded index: run length at the first element of every run (saturated like the packed entries), 0 elsewhere
+        if (run_n && in) run_n[i] = (uint32_t)(n < ((1ull << 20) - 1) ? n : ((1ull << 20) - 1));
         // most keys occur once or twice: add those bins once per warp instead of 32 same-address atomics
         const uint32_t n1 = __ballot_sync(0xffffffffu, n == 1), n2 = __ballot_sync(0xffffffffu, n == 2);
         if (lane == 0) { if (n1) atomicAdd(&sh[1], (unsigned)__popc(n1)); if (n2) atomicAdd(&sh[2], (unsigned)__popc(n2)); }
@@ -255,6 +257,16 @@ constexpr uint64_t PK_CMAX = (1ull << 20) - 1;
 constexpr uint64_t PK_FIELD = (1ull << PK_SHIFT) - 1;
 constexpr uint64_t PK_SENTINEL = ~0ull;
 
+// element i of the sorted keys as a packed entry (key << 24 | run length): the input of the DeviceSelect that keeps the
+// run starts (run_n != 0) -- distinct keys and their counts in one pass, sizes stay on the device
+template <typename XT, int KSH>
+struct PackRunOp {
+    const XT *tx; const uint32_t *run_n;
+    __host__ __device__ __forceinline__ uint64_t operator()(uint32_t i) const {
+        return ((uint64_t)tx[i] >> KSH) << 24 | (uint64_t)run_n[i];
+    }
+};
+
 // one thread per run: packed entry; U and the run starts come from DeviceSelect (device side), the last run ends at M
 __global__ void rle_pack_kernel(const uint64_t *__restrict__ tx, const uint32_t *__restrict__ starts, const uint32_t *__restrict__ U_dev,
                                 uint64_t M, uint64_t *__restrict__ out) {
@@ -308,6 +320,9 @@ struct OwnerMergeArgs {
     unsigned long long *hist;              // MODE 0
     const unsigned long long *meta;        // MODE 1: meta[0] = mid_occ
     uint64_t *bl; unsigned long long *bl_n; uint64_t bl_cap; unsigned long long *bl_ovf;
+    // MODE 0 with candidates: summed entries above cand_thr (a lower bound of mid_occ) are kept, so that the blacklist
+    // is a filter over them instead of a second merge
+    uint64_t *cand; unsigned long long *cand_n; uint64_t cand_thr;
 };
 
 // cuts[w][p] for every run and slice boundary: one thread per binary search
@@ -329,6 +344,8 @@ __global__ void __launch_bounds__(OM_THREADS) owner_merge_kernel(OwnerMergeArgs 
     __shared__ unsigned int sh[OM_HBINS];
     __shared__ uint64_t s_lo[OM_MAXW], s_hi[OM_MAXW];
     __shared__ uint32_t s_pre[OM_MAXW + 1];
+    __shared__ uint32_t s_cw[OM_THREADS / 32];
+    __shared__ unsigned long long s_gbase;
     const uint32_t tid = threadIdx.x;
     if (MODE == 0) for (int i = tid; i < OM_HBINS; i += OM_THREADS) sh[i] = 0;
     unsigned int my_keys = 0;
@@ -373,6 +390,7 @@ __global__ void __launch_bounds__(OM_THREADS) owner_merge_kernel(OwnerMergeArgs 
             }
         }
         __syncthreads();
+        uint32_t my_cand = 0;
         for (int i = tid; i < OM_SLOTS; i += OM_THREADS) {
             const unsigned long long e = om_table[i];
             if (e == 0ull) continue;
@@ -381,10 +399,32 @@ __global__ void __launch_bounds__(OM_THREADS) owner_merge_kernel(OwnerMergeArgs 
                 if (g < OM_HBINS) atomicAdd(&sh[g], 1u);
                 else atomicAdd(&A.hist[g < OCC_BINS - 1 ? g : OCC_BINS - 1], 1ull);
                 ++my_keys;
+                if (g > A.cand_thr) ++my_cand;
             }
             else if (g > A.meta[0]) {
                 const unsigned long long slot = atomicAdd(A.bl_n, 1ull);
                 if (slot < A.bl_cap) A.bl[slot] = e >> PK_SHIFT; else *A.bl_ovf = 1;
+            }
+        }
+        if (MODE == 0 && A.cand) {
+            // candidates of this table: one global atomic per CTA step (<= one candidate per received entry: cand always fits)
+            uint32_t incl = my_cand;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)(tid & 31) >= o) incl += u; }
+            if ((tid & 31) == 31) s_cw[tid >> 5] = incl;
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t run = 0;
+                for (int w = 0; w < OM_THREADS / 32; ++w) { const uint32_t t = s_cw[w]; s_cw[w] = run; run += t; }
+                s_gbase = run ? atomicAdd(A.cand_n, (unsigned long long)run) : 0ull;
+            }
+            __syncthreads();
+            if (my_cand) {
+                unsigned long long pos = s_gbase + s_cw[tid >> 5] + incl - my_cand;
+                for (int i = tid; i < OM_SLOTS; i += OM_THREADS) {
+                    const unsigned long long e = om_table[i];
+                    if (e != 0ull && (e & PK_FIELD) > A.cand_thr) A.cand[pos++] = e;
+                }
             }
         }
         a = b;
@@ -395,6 +435,19 @@ __global__ void __launch_bounds__(OM_THREADS) owner_merge_kernel(OwnerMergeArgs 
             if (sh[i]) atomicAdd(&A.hist[i], (unsigned long long)sh[i]);
         for (int o = 16; o > 0; o >>= 1) my_keys += __shfl_down_sync(0xffffffffu, my_keys, o);
         if ((tid & 31) == 0 && my_keys) atomicAdd(&A.hist[OCC_BINS], (unsigned long long)my_keys);
+    }
+}
+
+// blacklist = candidates whose global count exceeds mid_occ (meta[0])
+__global__ void bl_from_cand_kernel(const uint64_t *__restrict__ cand, const unsigned long long *__restrict__ cand_n,
+                                    const unsigned long long *__restrict__ meta, uint64_t *__restrict__ bl, unsigned long long *bl_n,
+                                    uint64_t bl_cap, unsigned long long *bl_ovf) {
+    const unsigned long long n = *cand_n, thr = meta[0];
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint64_t e = cand[i];
+        if ((e & PK_FIELD) <= thr) continue;
+        const unsigned long long slot = atomicAdd(bl_n, 1ull);
+        if (slot < bl_cap) bl[slot] = e >> PK_SHIFT; else *bl_ovf = 1;
     }
 }
 

@@ -306,6 +306,8 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
     uint32_t *vY = reinterpret_cast<uint32_t *>(bufY + (size_t)cap * sizeof(KT));
     uint16_t *rank = reinterpret_cast<uint16_t *>(bufY + (size_t)cap * (sizeof(KT) + 4));
     uint16_t *hist = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(rank) + (size_t)cap * 2);
+    uint32_t *pbm = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(hist) + (size_t)(NT / 32) * 512);   // pair starts, 1 bit per slot
+    uint32_t *gbm = pbm + cap / 32 + 1;                                   // (target, strand) group starts
     uint32_t *bins = reinterpret_cast<uint32_t *>(bufY);                  // round planning only (before staging): <= 8 * cap bytes
     int nbins_log = 11;                                                   // MAP_BINS = 2^11, fewer if the buffer is smaller
     while ((4u << nbins_log) > 8u * cap) --nbins_log;
@@ -496,10 +498,39 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
             __syncthreads();
             { const long long now = clock64(); cy[2] += now - tc; tc = now; }
 
-            // ---- 3. groups: warps claim 32-anchor windows; the (query, target) pairs starting there are theirs ---
-            // NB (racecheck): a warp looking for the end of ITS pair reads keys of later pairs while their owners sort
-            // them in place.  Only the (target, strand) bits are read, and a group sort never changes those bits of any
-            // slot of its group (all its records share them; keys are single 32/64-bit words), so the race is benign.
+            // ---- 3. groups -------------------------------------------------------------------------------------------
+            // 3a. boundaries of the sorted array as bit maps, built BEFORE any group is reordered: bit i of pbm = slot i
+            // starts a (query, target) pair, of gbm = slot i starts a (target, strand) group; bit N closes both.
+            for (uint32_t b = warp * 32; b <= N; b += NT) {
+                const uint32_t i = b + lane;
+                bool ps = i == N || i == 0, gs = ps;
+                if (i > 0 && i < N) {
+                    const KT prev = K[i - 1] >> PB, cur = K[i] >> PB;
+                    ps = (prev >> 1) != (cur >> 1);
+                    gs = prev != cur;
+                }
+                if (i > N) ps = gs = false;
+                const uint32_t pw = __ballot_sync(0xffffffffu, ps), gw = __ballot_sync(0xffffffffu, gs);
+                if (lane == 0) { pbm[b >> 5] = pw; gbm[b >> 5] = gw; }
+            }
+            __syncthreads();
+            // first set bit of a map strictly after slot `after` (bit N always ends the search)
+            auto next_bit = [&](const uint32_t *bm, uint32_t after) -> uint32_t {
+                uint32_t w = (after + 1) >> 5, first = 0xffffffffu << ((after + 1) & 31);
+                for (;;) {
+                    const uint32_t wi = w + lane;
+                    uint32_t x = wi <= (N >> 5) ? bm[wi] : 0u;
+                    if (lane == 0) x &= first;
+                    const uint32_t nz = __ballot_sync(0xffffffffu, x != 0u);
+                    if (nz) {
+                        const int src = __ffs(nz) - 1;
+                        return ((w + (uint32_t)src) << 5) + (uint32_t)(__ffs(__shfl_sync(0xffffffffu, x, src)) - 1);
+                    }
+                    w += 32; first = 0xffffffffu;
+                }
+            };
+            // 3b. warps claim 32-slot windows; the pairs starting there are theirs.  A warp reads keys of its own pairs
+            // only; everything about other pairs comes from the bit maps.
             uint2 *out = A.anc + a0 + round_base;
             for (;;) {
                 uint32_t u = 0;
@@ -507,27 +538,21 @@ __global__ void __launch_bounds__(NT, MINB) sort_query_kernel(SortArgs A) {
                 u = __shfl_sync(0xffffffffu, u, 0);
                 const uint32_t wnd = u * 32;
                 if (wnd >= N) break;
-                const uint32_t i = wnd + lane;
-                bool ps = false;
-                if (i < N) ps = i == 0 || (K[i - 1] >> (PB + 1)) != (K[i] >> (PB + 1));
-                uint32_t pm = __ballot_sync(0xffffffffu, ps);
+                const uint32_t pw = pbm[u], gw = gbm[u];                   // this window's boundary bits (same in every lane)
+                uint32_t pm = pw;
+                if ((N >> 5) == u) pm &= ~(1u << (N & 31));                // the closing bit is not a pair
                 while (pm) {
-                    const uint32_t s = wnd + (uint32_t)(__ffs(pm) - 1);
+                    const uint32_t sb = (uint32_t)(__ffs(pm) - 1), s = wnd + sb;
                     pm &= pm - 1;
-                    const KT pk = K[s] >> (PB + 1);
-                    // pair end and strand split, 32 anchors per step
-                    uint32_t e = N, split = 0xffffffffu;
-                    for (uint32_t b = s; b < N; b += 32) {
-                        const uint32_t j = b + lane;
-                        const bool in = j < N;
-                        const KT kk = in ? K[j] : (KT)0;
-                        const bool same = in && (kk >> (PB + 1)) == pk;
-                        const uint32_t diff = __ballot_sync(0xffffffffu, in && !same);
-                        const uint32_t rv = __ballot_sync(0xffffffffu, same && ((kk >> PB) & 1));
-                        if (split == 0xffffffffu && rv) split = b + (uint32_t)(__ffs(rv) - 1);
-                        if (diff) { e = b + (uint32_t)(__ffs(diff) - 1); break; }
-                    }
-                    if (split == 0xffffffffu || split > e) split = e;
+                    // end of the pair / first strand change: usually inside this window (registers only), else searched
+                    const uint32_t above = sb == 31 ? 0u : 0xffffffffu << (sb + 1);
+                    const uint32_t pe = pw & above, ge = gw & above;
+                    const uint32_t e = pe ? wnd + (uint32_t)(__ffs(pe) - 1) : next_bit(pbm, wnd + 31);
+                    uint32_t split = ge ? wnd + (uint32_t)(__ffs(ge) - 1) : next_bit(gbm, wnd + 31);   // <= e: a pair start is a group start
+                    if (e - s < (uint32_t)A.min_cnt) { if (lane == 0) st_groups += 1 + (split < e); continue; }   // too short for a chain
+                    const KT ks = K[s];
+                    const KT pk = ks >> (PB + 1);
+                    if (split == e && ((ks >> PB) & 1)) split = s;         // one strand only, the reverse one
                     const uint32_t nf = split - s, nr = e - split;
                     if (lane == 0) st_groups += (nf > 0) + (nr > 0);
                     const bool vf = (int32_t)nf >= A.min_cnt && (int64_t)nf * A.max_span >= A.min_sc;

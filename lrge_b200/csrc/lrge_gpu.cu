@@ -218,6 +218,8 @@ struct lrge_ctx {
     DevBuf anc, fp, glist, gmeta, pflag, regs;
     bool chain_v1 = false;                 // LRGE_CHAIN_V1=1 (test build only): literal thread-per-pair kernel
     bool force_global = false;             // LRGE_FORCE_GLOBAL=1: every query through the global-memory path
+    bool local_block = false;              // lrge_gpu_twoset_counts_shard: the staged indexed set IS this rank's block
+    int index_bits_delta = 0;              // LRGE_INDEX_BITS_DELTA=d: 2^d times more (d > 0) or fewer buckets in the index table
     uint32_t map_cap = 0;                  // LRGE_MAP_CAP=n: anchors per shared-memory round (tests force multi-round)
     int map_ctas_per_sm = 1;               // LRGE_MAP_CTAS=1|2
     int smem_optin = 0;                    // cudaDevAttrMaxSharedMemoryPerBlockOptin
@@ -532,6 +534,8 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         c->casc.reserve(resident + 64);
         c->cend.reserve((resident + 1) * 4);
         c->clen.reserve((size_t)std::max(n, 1u) * 4);
+        // compressed reads keep their original offsets: the gaps behind them are read (and masked) by pack_kernel's word loads
+        CUDA_CHECK(cudaMemsetAsync(c->casc.p, 0, resident + 64, c->stream));
         if (n) {
             KLAUNCH(c, "hpc_compress_kernel", 6 * nbases,
                     hpc_compress_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(s->asc.as<uint8_t>(), c->sub_off.as<uint64_t>(), c->len0.as<uint32_t>(), n,
@@ -636,6 +640,7 @@ BuiltIndex build_index_launch(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     // ~8 entries per bucket: the table (4 B x 2^bits) stays L2-resident, a lookup bisects <= 3 steps
     int bits = 8;
     while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
+    bits = std::max(8, std::min({bits + c->index_bits_delta, 2 * o.k, 28}));   // LRGE_INDEX_BITS_DELTA: experiments
     if (bits < 2 * o.k - 32) bits = 2 * o.k - 32;              // tk32: the in-bucket part of a key must fit 32 bits
     const uint32_t nb = 1u << bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
@@ -754,6 +759,7 @@ BuiltIndex build_index_sharded_exact(lrge_ctx *c, const Sketch &sk, const MapOpt
     }
     int bits = 8;
     while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
+    bits = std::max(8, std::min({bits + c->index_bits_delta, 2 * o.k, 28}));   // LRGE_INDEX_BITS_DELTA: experiments
     if (bits < 2 * o.k - 32) bits = 2 * o.k - 32;              // tk32: the in-bucket part of a key must fit 32 bits
     const uint32_t nb = 1u << bits;
     const int shift = 8 + 2 * o.k - bits;
@@ -916,47 +922,72 @@ ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOp
     const uint64_t M = sk.M;
     if (M >= (1ull << 32) - 2) throw std::length_error("more than 2^32 target minimizers per GPU are not supported");
     if (W > 16) throw std::length_error("more than 16 ranks are not supported");
-    c->tx.reserve((M + 1) * 8);
     c->ty.reserve((M + 1) * 8);
-    size_t tb = 0;
-    if (M) {
-        cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
-                                        c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
-        KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", 32.0 * M,
-                cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
-                                                c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
-        c->launches += (2 * o.k + 7) / 8;
-        c->prof.set_passes("cub::DeviceRadixSort(index: u64 key, u64 value)", (2 * o.k + 7) / 8);
-    }
+    c->tk32.reserve((M + 64) * 4);
     int bits = 8;
     while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
     if (bits < 2 * o.k - 32) bits = 2 * o.k - 32;
     const uint32_t nb = 1u << bits;
-    const int shift = 8 + 2 * o.k - bits;
     c->boff.reserve(((size_t)nb + 2) * 4);
     c->hist.reserve((OCC_BINS + 2) * 8);
     CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));      // local histogram: unused here
-    c->tk32.reserve((M + 64) * 4);
-    CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));
-    KLAUNCH(c, "index_post_kernel", 12.0 * M + 4.0 * nb,
-            (index_post_kernel<uint64_t, 8><<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(),
-                                                                            c->hist.as<unsigned long long>())));
-    // distinct local keys, packed with their counts, in key order
-    c->flags.reserve(M + 1);
-    c->pstart.reserve((M + 2) * 4);
+    c->flags.reserve((M + 1) * 4);                                                  // run length at every run start, 0 elsewhere
+    uint32_t *run_n = c->flags.as<uint32_t>();
     c->npairs.reserve(16);
     c->ukey.reserve((M + 1) * 8);
     CUDA_CHECK(cudaMemsetAsync(c->npairs.p, 0, 16, c->stream));
-    if (M) {
-        KLAUNCH(c, "run_flag_kernel", 9.0 * M, run_flag_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, 8, c->flags.as<uint8_t>()));
-        cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(), c->pstart.as<uint32_t>(),
-                                   c->npairs.as<uint32_t>(), (int64_t)M, c->stream);
-        KLAUNCH(c, "cub::DeviceSelect(run starts)", 5.0 * M,
-                cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, cub::CountingInputIterator<uint32_t>(0), c->flags.as<uint8_t>(),
-                                           c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), (int64_t)M, c->stream));
-        KLAUNCH(c, "rle_pack_kernel", 20.0 * M,
-                rle_pack_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(c->tx.as<uint64_t>(), c->pstart.as<uint32_t>(), c->npairs.as<uint32_t>(), M,
-                                                                                    c->ukey.as<uint64_t>()));
+    const bool k32 = !o.is_hpc && 2 * o.k <= 32;               // as in build_index_launch: sort (32-bit hash, y)
+    B.x32 = k32;
+    size_t tb = 0;
+    int shift;
+    if (k32) {
+        c->tx.reserve((M + 1) * 4);                                                 // unsorted 32-bit keys
+        if (M) {
+            KLAUNCH(c, "key32_kernel", 12.0 * M,
+                    key32_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(sk.x.as<uint64_t>(), M, c->tx.as<uint32_t>()));
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, c->tx.as<uint32_t>(), c->tk32.as<uint32_t>(), sk.y.as<uint64_t>(), c->ty.as<uint64_t>(),
+                                            (int64_t)M, 0, 2 * o.k, c->stream);
+            KLAUNCH(c, "cub::DeviceRadixSort(index: u32 key, u64 value)", 32.0 * M,
+                    cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, c->tx.as<uint32_t>(), c->tk32.as<uint32_t>(), sk.y.as<uint64_t>(),
+                                                    c->ty.as<uint64_t>(), (int64_t)M, 0, 2 * o.k, c->stream));
+            c->launches += (2 * o.k + 7) / 8;
+            c->prof.set_passes("cub::DeviceRadixSort(index: u32 key, u64 value)", (2 * o.k + 7) / 8);
+        }
+        CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));
+        shift = 8 + 2 * o.k - bits;
+        KLAUNCH(c, "index_post_kernel", 8.0 * M + 4.0 * nb,
+                (index_post_kernel<uint32_t, 0><<<148 * 8, 256, 0, c->stream>>>(c->tk32.as<uint32_t>(), M, shift - 8, nb, c->boff.as<uint32_t>(), nullptr,
+                                                                                c->hist.as<unsigned long long>(), run_n)));
+        if (M) {
+            PackRunOp<uint32_t, 0> op{c->tk32.as<uint32_t>(), run_n};
+            cub::TransformInputIterator<uint64_t, PackRunOp<uint32_t, 0>, cub::CountingInputIterator<uint32_t>> it(cub::CountingInputIterator<uint32_t>(0), op);
+            cub::DeviceSelect::Flagged(nullptr, tb, it, run_n, c->ukey.as<uint64_t>(), c->npairs.as<uint32_t>(), (int64_t)M, c->stream);
+            KLAUNCH(c, "cub::DeviceSelect(packed runs)", 8.0 * M,
+                    cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, it, run_n, c->ukey.as<uint64_t>(), c->npairs.as<uint32_t>(), (int64_t)M, c->stream));
+        }
+    } else {
+        c->tx.reserve((M + 1) * 8);
+        if (M) {
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                            c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream);
+            KLAUNCH(c, "cub::DeviceRadixSort(index: u64 key, u64 value)", 32.0 * M,
+                    cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, sk.x.as<uint64_t>(), c->tx.as<uint64_t>(), sk.y.as<uint64_t>(),
+                                                    c->ty.as<uint64_t>(), (int64_t)M, 8, 8 + 2 * o.k, c->stream));
+            c->launches += (2 * o.k + 7) / 8;
+            c->prof.set_passes("cub::DeviceRadixSort(index: u64 key, u64 value)", (2 * o.k + 7) / 8);
+        }
+        CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));
+        shift = 8 + 2 * o.k - bits;
+        KLAUNCH(c, "index_post_kernel", 16.0 * M + 4.0 * nb,
+                (index_post_kernel<uint64_t, 8><<<148 * 8, 256, 0, c->stream>>>(c->tx.as<uint64_t>(), M, shift, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(),
+                                                                                c->hist.as<unsigned long long>(), run_n)));
+        if (M) {
+            PackRunOp<uint64_t, 8> op{c->tx.as<uint64_t>(), run_n};
+            cub::TransformInputIterator<uint64_t, PackRunOp<uint64_t, 8>, cub::CountingInputIterator<uint32_t>> it(cub::CountingInputIterator<uint32_t>(0), op);
+            cub::DeviceSelect::Flagged(nullptr, tb, it, run_n, c->ukey.as<uint64_t>(), c->npairs.as<uint32_t>(), (int64_t)M, c->stream);
+            KLAUNCH(c, "cub::DeviceSelect(packed runs)", 12.0 * M,
+                    cub::DeviceSelect::Flagged(cub_temp(c, tb), tb, it, run_n, c->ukey.as<uint64_t>(), c->npairs.as<uint32_t>(), (int64_t)M, c->stream));
+        }
     }
     // xmeta: bounds[W+1] | sendc[W] | mat[W*W] | hist[OCC_BINS+2] | meta[8]
     c->xmeta.reserve(((size_t)(2 * W + 1) + (size_t)W * W + OCC_BINS + 2 + 8) * 8 + 64);
@@ -1008,6 +1039,8 @@ ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOp
     OA.cuts = c->ucnt.as<uint32_t>();
     if (R) KLAUNCH(c, "owner_cuts_kernel", 4.0 * (om_grid + 1) * W,
                    owner_cuts_kernel<<<(unsigned)(((uint64_t)(om_grid + 1) * W + 255) / 256), 256, 0, c->stream>>>(OA, c->ucnt.as<uint32_t>()));
+    c->skey.reserve((R + 1) * 8);                                   // candidates: summed entries above min_mid_occ (<= mid_occ)
+    OA.cand = c->skey.as<uint64_t>(); OA.cand_n = meta_d + 4; OA.cand_thr = (uint64_t)std::max(o.min_mid_occ, 0);
     if (R) KLAUNCH(c, "owner_merge_kernel<hist>", 8.0 * R, owner_merge_kernel<0><<<om_grid, OM_THREADS, om_smem, c->stream>>>(OA));
     const unsigned long long extra = M;
     CUDA_CHECK(cudaMemcpyAsync(hist_d + OCC_BINS + 1, &extra, 8, cudaMemcpyHostToDevice, c->stream));
@@ -1019,12 +1052,13 @@ ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOp
     c->blist.reserve(cap_bl * 8); c->blall.reserve(cap_bl * 8 * W);
     CUDA_CHECK(cudaMemsetAsync(c->blist.p, 0xff, cap_bl * 8, c->stream));
     OA.bl = c->blist.as<uint64_t>(); OA.bl_n = meta_d + 3; OA.bl_cap = cap_bl; OA.bl_ovf = meta_d + 2;
-    if (R) KLAUNCH(c, "owner_merge_kernel<select>", 8.0 * R, owner_merge_kernel<1><<<om_grid, OM_THREADS, om_smem, c->stream>>>(OA));
+    if (R) KLAUNCH(c, "bl_from_cand_kernel", 8.0 * bl_cap,
+                   bl_from_cand_kernel<<<148 * 4, 256, 0, c->stream>>>(OA.cand, OA.cand_n, meta_d, OA.bl, OA.bl_n, OA.bl_cap, OA.bl_ovf));
     NCCL_CHECK(ncclAllGather(c->blist.p, c->blall.p, cap_bl, ncclUint64, c->comm, c->stream));
     NCCL_CHECK(ncclAllReduce(meta_d + 1, meta_d + 1, 2, ncclUint64, ncclMax, c->comm, c->stream));     // fallback flags: every rank alike
     c->blmap.reserve((M / 32 + 2) * 4);
     CUDA_CHECK(cudaMemsetAsync(c->blmap.p, 0, (M / 32 + 2) * 4, c->stream));
-    B.view.tx = c->tx.as<uint64_t>(); B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.tx = k32 ? nullptr : c->tx.as<uint64_t>(); B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
     B.view.M = M; B.view.shift = shift; B.view.bl = nullptr;
     KLAUNCH(c, "bl_mark_kernel", 8.0 * cap_bl * W,
             bl_mark_kernel<<<(unsigned)((cap_bl * W + 255) / 256), 256, 0, c->stream>>>(c->blall.as<uint64_t>(), cap_bl * W, B.view, c->blmap.as<uint32_t>()));
@@ -1167,7 +1201,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     if (sharded_index && (world != c->world || opts.shard_index != c->rank))
         throw std::runtime_error("shard_index/shard_count do not match the communicator");
     uint32_t i0 = 0, i1 = idx->n;
-    if (sharded_index) shard_range(idx->n, c->rank, world, &i0, &i1);
+    if (sharded_index && !c->local_block) shard_range(idx->n, c->rank, world, &i0, &i1);
     Sketch2Job job_idx;
     const bool fast_idx = sketch2_begin(c, idx, o, &c->sk_idx, i0, i1 - i0, &job_idx);
 
@@ -1219,7 +1253,9 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         bool fast_str = false, tried = false;
         c->prof.sbegin(ST_INDEX);
         // the blacklist holds ~2e-4 of the distinct keys; room for 1/512 of a rank's nominal share of the bases
-        const uint64_t bl_cap = std::max<uint64_t>(4096, idx->total_bases / (uint64_t)world / 512);
+        // (a number every rank derives alike: with local blocks only the streamed set is common to all ranks)
+        const uint64_t bl_cap = c->local_block ? std::max<uint64_t>(4096, str->total_bases / 256)
+                                               : std::max<uint64_t>(4096, idx->total_bases / (uint64_t)world / 512);
         ShardedJob J = build_index_sharded_launch(c, c->sk_idx, o, bl_cap, [&]() {
             tried = true;
             fast_str = sketch2_begin(c, str, o, &c->sk_str, 0, str->n, &job_str);
@@ -1342,7 +1378,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
 
     // per-query sort kernel configuration
     uint32_t r0 = 0, r1 = idx->n;
-    if (sharded_index) shard_range(idx->n, c->rank, world, &r0, &r1);
+    if (sharded_index && !c->local_block) shard_range(idx->n, c->rank, world, &r0, &r1);
     const uint32_t n_local = r1 - r0;
     const int key_bits = bits_for(n_local ? n_local - 1 : 0) + 1 + PB;
     const bool k32 = key_bits <= 32, two = c->map_ctas_per_sm == 2;          // 2 CTAs of 512 threads, else 1 CTA of 1024
@@ -1358,9 +1394,10 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         size_t per_cta = (size_t)c->smem_optin;                                // static + dynamic, one CTA per SM
         if (two) per_cta = ((size_t)c->smem_optin + 1024) / 2 - 1024;
         const size_t fixed = fa.sharedSizeBytes + (size_t)NW * 512;
-        map_cap = (uint32_t)std::min<size_t>((per_cta - fixed) / (2 * rec + 2), 65504) / 32 * 32;
+        // per slot: two (key, value) buffers, a u16 rank and 2 bits of the pair / group boundary maps
+        map_cap = (uint32_t)std::min<size_t>((per_cta - fixed - 16) * 4 / (4 * (2 * rec + 2) + 1), 65504) / 32 * 32;
         if (c->map_cap) map_cap = std::max(64u, std::min(map_cap, c->map_cap) / 32 * 32);   // LRGE_MAP_CAP: force many rounds (tests)
-        map_dyn = (size_t)map_cap * (2 * rec + 2) + (size_t)NW * 512;
+        map_dyn = (size_t)map_cap * (2 * rec + 2) + (size_t)NW * 512 + 2 * ((size_t)map_cap / 32 + 1) * 4;
         CUDA_CHECK(cudaFuncSetAttribute(sort_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)map_dyn));
         c->deferred.reserve(((size_t)str->n + 1) * 4);
         c->mapctr.reserve(64);
@@ -1735,7 +1772,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         if (ctr_h[6]) throw std::runtime_error("internal: the per-query sort kernel exceeded a capacity it had planned for");
         S.n_pairs += ctr_h[4]; S.n_rounds = (uint32_t)ctr_h[5];
         S.n_deferred = (uint32_t)deferred.size();
-        if (c->prof.kernels && ctr_h[14]) {                                // phase shares of the per-query sort kernel (SM cycles)
+        if (c->prof.kernels && ctr_h[14] && getenv("LRGE_SORT_PHASES")) {     // phase shares of the per-query sort kernel (SM cycles)
             const double tot = (double)ctr_h[14];
             fprintf(stderr, "[lrge] sort_query_kernel phases: plan %.3f stage %.3f sort %.3f groups %.3f (of CTA lifetime), rounds %llu\n",
                     ctr_h[10] / tot, ctr_h[11] / tot, ctr_h[12] / tot, ctr_h[13] / tot, (unsigned long long)ctr_h[5]);
@@ -1821,6 +1858,7 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         { const char *e = getenv("LRGE_CHAIN_V1"); c->chain_v1 = e && e[0] == '1'; }
         { const char *e = getenv("LRGE_MAX_ANCHORS"); c->max_anchors = e ? strtoull(e, nullptr, 10) : 0; }
         { const char *e = getenv("LRGE_FORCE_GLOBAL"); c->force_global = e && e[0] == '1'; }
+        { const char *e = getenv("LRGE_INDEX_BITS_DELTA"); c->index_bits_delta = e ? atoi(e) : 0; }
         { const char *e = getenv("LRGE_MAP_CAP"); c->map_cap = e ? (uint32_t)strtoul(e, nullptr, 10) : 0; }
         { const char *e = getenv("LRGE_MAP_CTAS"); c->map_ctas_per_sm = e && e[0] == '2' ? 2 : 1; }
         CUDA_CHECK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -1903,6 +1941,28 @@ int lrge_gpu_twoset_counts(lrge_ctx *ctx, const lrge_readset *T, const lrge_read
         if (inverse) run_overlap(ctx, &sQ, &sT, MODE_INVERSE, *opts, counts, nullptr, stats);
         else run_overlap(ctx, &sT, &sQ, MODE_TWOSET, *opts, counts, had_mapping, stats);
         if (stats) {   // host buffers in, counts out: wall time of the whole call
+            stats->ms_h2d = 0.0f;
+            stats->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+    });
+}
+
+int lrge_gpu_twoset_counts_shard(lrge_ctx *ctx, const lrge_readset *T_block, const lrge_readset *Q, const lrge_opts *opts,
+                                 uint32_t *counts, uint8_t *had_mapping, lrge_stats *stats) {
+    if (!T_block || !Q || !counts || !valid_opts(opts)) { if (ctx) ctx->err = "invalid argument"; return LRGE_ERR_INVALID_ARG; }
+    if (!ctx->comm || opts->shard_count != ctx->world || opts->shard_index != ctx->rank || opts->use_min_ref) {
+        ctx->err = "lrge_gpu_twoset_counts_shard needs a communicator, matching shard_index/shard_count and use_min_ref = 0";
+        return LRGE_ERR_INVALID_ARG;
+    }
+    return guarded(ctx, [&] {
+        const auto t0 = std::chrono::steady_clock::now();
+        lrge_staged &sT = ctx->tmp_a, &sQ = ctx->tmp_b;
+        struct Drain { lrge_ctx *c; ~Drain() { c->local_block = false; cudaStreamSynchronize(c->copy_stream); } } drain{ctx};
+        ctx->local_block = true;
+        stage_readset(ctx, T_block, &sT, true, 0, 0xffffffffu, true);
+        stage_readset(ctx, Q, &sQ, true, 0, 0xffffffffu, true);
+        run_overlap(ctx, &sT, &sQ, MODE_TWOSET, *opts, counts, had_mapping, stats);
+        if (stats) {
             stats->ms_h2d = 0.0f;
             stats->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         }
