@@ -407,7 +407,7 @@ bool sketch2_begin(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *o
     const bool subset = first != 0 || count != s->n;
     const uint32_t nw = tiles * (SK_THREADS / 32);
     const uint64_t stage_bytes = (uint64_t)nw * SK_CAP * 16;
-    if (stage_bytes > (8ull << 30) || stage_bytes > (free_estimate(c) + c->stg_x.cap + c->stg_y.cap) / 4) return false;
+    if (stage_bytes > (16ull << 30) || stage_bytes > (free_estimate(c) + c->stg_x.cap + c->stg_y.cap) / 4) return false;
     c->prof.sbegin(ST_SKETCH);
     h2d(c, c->tile_off, tile_off.data(), (size_t)n + 1);
     h2d(c, c->tile_read, tile_read.data(), tiles);
@@ -568,7 +568,7 @@ void sketch_readset(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *
         // single pass when the staging slots (SK_CAP minimizers per 1024-step sub-tile) fit comfortably
         const uint64_t stage_bytes = (uint64_t)nw * SK_CAP * 16;
         const size_t free_b = free_estimate(c);
-        bool single = !c->sketch_two_pass && stage_bytes <= (8ull << 30) && stage_bytes <= (free_b + c->stg_x.cap + c->stg_y.cap) / 4;
+        bool single = !c->sketch_two_pass && stage_bytes <= (16ull << 30) && stage_bytes <= (free_b + c->stg_x.cap + c->stg_y.cap) / 4;
         uint32_t total = 0;
         if (single) {
             c->stg_x.reserve(stage_bytes / 2 + 64); c->stg_y.reserve(stage_bytes / 2 + 64);
