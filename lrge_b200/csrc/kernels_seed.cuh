@@ -63,38 +63,64 @@ __device__ __forceinline__ bool skip_hit(uint64_t r, uint32_t qid, uint32_t q_po
     return false;
 }
 
+// A hit list of at least this many entries is expanded by the whole warp (coalesced reads of the list, coalesced writes
+// of the anchors) instead of by its own thread: ava-pb lists hold up to mid_occ ~ 70 entries.
+constexpr uint32_t COOP_MIN_HITS = 16;
+
 // One thread per query minimizer: lookup, mid_occ filter, exact anchor count.
 __global__ void seed_count_kernel(const uint64_t *__restrict__ qx, const uint64_t *__restrict__ qy,
                                   const uint8_t *__restrict__ flt, uint64_t MQ, IndexView I, int mid_occ, SkipCtx S,
                                   uint32_t *__restrict__ hstart, uint32_t *__restrict__ hn, uint32_t *__restrict__ acnt,
                                   unsigned long long *n_seeds, unsigned long long *n_hits) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const bool live = i < MQ && !flt[i];
+    const bool scan = S.check_names || S.sharded;
     uint32_t cnt = 0, n = 0, start = 0;
-    if (i < MQ && !flt[i]) {
+    uint64_t y = 0;
+    if (live) {
         const uint64_t x = qx[i];
         n = index_lookup(I, x >> 8, (uint32_t)mid_occ, &start);
         bool rep = n > (uint32_t)mid_occ;                     // m[i].flt = 1 (seed.c mm_collect_matches)
         if (n && I.bl && ((I.bl[start >> 5] >> (start & 31)) & 1)) rep = true;   // > mid_occ over all target shards
         if (rep) { n = 0; start = SEED_REPETITIVE; }
-        if (n) {
-            if (S.check_names || S.sharded) {
-                // 128-bit loads, two hit-list entries each, four loads in flight
-                const uint64_t y = qy[i];
-                const uint4 *ty4 = reinterpret_cast<const uint4 *>(I.ty);
-                const uint32_t p1 = (start + n + 1) >> 1;
-                for (uint32_t p = start >> 1; p < p1; p += 4) {
-                    uint4 v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) v[u] = p + u < p1 ? __ldg(ty4 + p + u) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t e0 = 2 * (p + u), e1 = e0 + 1;
-                        if (e0 >= start && e0 < start + n) cnt += !skip_hit((uint64_t)v[u].y << 32 | v[u].x, (uint32_t)(y >> 32), (uint32_t)y, S);
-                        if (e1 >= start && e1 < start + n) cnt += !skip_hit((uint64_t)v[u].w << 32 | v[u].z, (uint32_t)(y >> 32), (uint32_t)y, S);
-                    }
-                }
-            } else cnt = n;
+        if (n && scan) y = qy[i];
+        if (!scan) cnt = n;
+    }
+    if (scan) {
+        // long lists: the warp counts the kept hits of one list together
+        uint32_t big = __ballot_sync(0xffffffffu, n >= COOP_MIN_HITS);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t s_start = __shfl_sync(0xffffffffu, start, src), s_n = __shfl_sync(0xffffffffu, n, src);
+            const uint64_t s_y = __shfl_sync(0xffffffffu, y, src);
+            uint32_t kept = 0;
+            for (uint32_t b = 0; b < s_n; b += 32) {
+                const uint32_t e = b + lane;
+                const bool keep = e < s_n && !skip_hit(__ldg(I.ty + s_start + e), (uint32_t)(s_y >> 32), (uint32_t)s_y, S);
+                kept += __popc(__ballot_sync(0xffffffffu, keep));
+            }
+            if ((int)lane == src) cnt = kept;
         }
+        if (n && n < COOP_MIN_HITS) {
+            // 128-bit loads, two hit-list entries each, four loads in flight
+            const uint4 *ty4 = reinterpret_cast<const uint4 *>(I.ty);
+            const uint32_t p1 = (start + n + 1) >> 1;
+            for (uint32_t p = start >> 1; p < p1; p += 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = p + u < p1 ? __ldg(ty4 + p + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e0 = 2 * (p + u), e1 = e0 + 1;
+                    if (e0 >= start && e0 < start + n) cnt += !skip_hit((uint64_t)v[u].y << 32 | v[u].x, (uint32_t)(y >> 32), (uint32_t)y, S);
+                    if (e1 >= start && e1 < start + n) cnt += !skip_hit((uint64_t)v[u].w << 32 | v[u].z, (uint32_t)(y >> 32), (uint32_t)y, S);
+                }
+            }
+        }
+    }
+    if (live) {
         hstart[i] = start;
         hn[i] = n;                                            // hits to visit
         acnt[i] = cnt;                                        // anchors kept
@@ -120,17 +146,46 @@ __global__ void __launch_bounds__(256) anchor_fill_kernel(const uint64_t *__rest
                                    uint32_t q0, IndexView I, SkipCtx S, KeyLayout K,
                                    KT *__restrict__ akey, uint32_t *__restrict__ aval) {
     const uint64_t i = m0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m1) return;
-    if (acnt[i] == 0) return;
-    const uint32_t n = hn[i];
-    const uint64_t x = qx[i], y = qy[i];
-    const uint32_t qid = (uint32_t)(y >> 32), q_pos = (uint32_t)y, q_span = (uint32_t)(x & 0xff);
-    const uint32_t qlen = S.len_q[qid];
-    const uint64_t qpart = (uint64_t)(qid - q0) << K.RB;
+    const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1;
+    const bool active = i < m1 && acnt[i] != 0;
     const bool scan = S.check_names || S.sharded;
-    uint64_t o = aoff[i] - a0;
-    const uint32_t start = hstart[i];
-    const uint32_t qp_f = q_pos >> 1, qp_r = qlen - ((q_pos >> 1) + 1 - q_span) - 1;
+    uint32_t n = 0, start = 0, q_span = 0, qlen = 0;
+    uint64_t y = 0, o = 0;
+    if (active) {
+        n = hn[i]; start = hstart[i];
+        y = qy[i]; q_span = (uint32_t)(qx[i] & 0xff);
+        qlen = S.len_q[(uint32_t)(y >> 32)];
+        o = aoff[i] - a0;
+    }
+    auto emit = [&](uint64_t at, uint64_t r, uint32_t qid, uint32_t q_pos, uint32_t span, uint32_t ql) {
+        const uint32_t rev = ((uint32_t)r ^ q_pos) & 1;
+        const uint32_t qp_f = q_pos >> 1, qp_r = ql - ((q_pos >> 1) + 1 - span) - 1;
+        if (WITH_QID) akey[at] = (KT)(((((uint64_t)(qid - q0) << K.RB | (r >> 32)) << 1 | rev) << K.PB) | ((uint32_t)r >> 1));
+        else akey[at] = (KT)(((((KT)((uint32_t)(r >> 32) - K.rid_base)) << 1 | (KT)rev) << K.PB) | (KT)((uint32_t)r >> 1));
+        aval[at] = span << 24 | (rev ? qp_r : qp_f);
+    };
+    // long hit lists: one list at a time, 32 consecutive entries per step across the warp
+    uint32_t big = __ballot_sync(0xffffffffu, active && n >= COOP_MIN_HITS);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t s_start = __shfl_sync(0xffffffffu, start, src), s_n = __shfl_sync(0xffffffffu, n, src);
+        const uint32_t s_span = __shfl_sync(0xffffffffu, q_span, src), s_qlen = __shfl_sync(0xffffffffu, qlen, src);
+        const uint64_t s_y = __shfl_sync(0xffffffffu, y, src);
+        uint64_t s_o = __shfl_sync(0xffffffffu, o, src);
+        const uint32_t s_qid = (uint32_t)(s_y >> 32), s_qpos = (uint32_t)s_y;
+        for (uint32_t b = 0; b < s_n; b += 32) {
+            const uint32_t e = b + lane;
+            bool keep = e < s_n;
+            uint64_t r = 0;
+            if (keep) { r = __ldg(I.ty + s_start + e); if (scan && skip_hit(r, s_qid, s_qpos, S)) keep = false; }
+            const uint32_t km = __ballot_sync(0xffffffffu, keep);
+            if (keep) emit(s_o + __popc(km & lt), r, s_qid, s_qpos, s_span, s_qlen);
+            s_o += __popc(km);
+        }
+    }
+    if (!active || n >= COOP_MIN_HITS) return;
+    const uint32_t qid = (uint32_t)(y >> 32), q_pos = (uint32_t)y;
     const uint4 *ty4 = reinterpret_cast<const uint4 *>(I.ty);
     const uint32_t p1 = (start + n + 1) >> 1;
     for (uint32_t p = start >> 1; p < p1; p += 4) {
@@ -145,10 +200,7 @@ __global__ void __launch_bounds__(256) anchor_fill_kernel(const uint64_t *__rest
                 if (e < start || e >= start + n) continue;
                 const uint64_t r = h ? ((uint64_t)v[u].w << 32 | v[u].z) : ((uint64_t)v[u].y << 32 | v[u].x);
                 if (scan && skip_hit(r, qid, q_pos, S)) continue;
-                const uint32_t rev = ((uint32_t)r ^ q_pos) & 1;
-                if (WITH_QID) akey[o] = (KT)((((qpart | (r >> 32)) << 1 | rev) << K.PB) | ((uint32_t)r >> 1));
-                else akey[o] = (KT)(((((KT)((uint32_t)(r >> 32) - K.rid_base)) << 1 | (KT)rev) << K.PB) | (KT)((uint32_t)r >> 1));
-                aval[o] = q_span << 24 | (rev ? qp_r : qp_f);
+                emit(o, r, qid, q_pos, q_span, qlen);
                 ++o;
             }
         }

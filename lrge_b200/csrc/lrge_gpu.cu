@@ -201,6 +201,11 @@ struct lrge_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;    // H2D staging of host read sets, overlapped with compute on `stream`
+    cudaStream_t side_stream = nullptr;    // the sketch of the streamed set runs here, next to the index build on `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool on_side = false;                  // `stream` and `side_stream` are swapped (SideStream)
+    bool no_side = false;                  // LRGE_NO_SIDE_STREAM=1: everything on one stream (A/B measurements)
+    DevBuf cub_tmp2;                       // CUB temporary storage of the side stream
     std::string err;
     uint32_t launches = 0;
     Prof prof;
@@ -255,7 +260,14 @@ size_t free_estimate(const lrge_ctx *c) {
     return base > used + (1ull << 30) ? base - used - (1ull << 30) : 0;
 }
 
-void *cub_temp(lrge_ctx *c, size_t bytes) { c->cub_tmp.reserve(bytes ? bytes : 16); return c->cub_tmp.p; }
+void *cub_temp(lrge_ctx *c, size_t bytes) { DevBuf &b = c->on_side ? c->cub_tmp2 : c->cub_tmp; b.reserve(bytes ? bytes : 16); return b.p; }
+
+// While alive, everything that launches on c->stream (kernels, copies, profiler events, CUB calls) goes to the side stream.
+struct SideStream {
+    lrge_ctx *c;
+    explicit SideStream(lrge_ctx *ctx) : c(ctx) { std::swap(c->stream, c->side_stream); c->prof.s = c->stream; c->on_side = true; }
+    ~SideStream() { std::swap(c->stream, c->side_stream); c->prof.s = c->stream; c->on_side = false; }
+};
 
 template <typename T> void h2d(lrge_ctx *c, DevBuf &d, const T *src, size_t n) {
     d.reserve(std::max<size_t>(n, 1) * sizeof(T));
@@ -1248,22 +1260,36 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     BuiltIndex B;
     Sketch *sq = &c->sk_idx;
     const bool need_str = mode != MODE_AVA || sharded_index;
+    // The sketch of the streamed set goes to the side stream: it only has to wait for the sketch of the indexed set
+    // (shared staging buffers), and then runs next to the index build (sort passes are HBM-bound, the sketch issue-bound).
+    Sketch2Job job_str;
+    bool fast_str = false;
+    if (need_str && !c->no_side) {
+        CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+        SideStream side(c);
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
+        fast_str = sketch2_begin(c, str, o, &c->sk_str, 0, str->n, &job_str);
+    }
+    auto finish_str = [&]() {                      // minimizer total of the streamed set -> compaction; join the main stream
+        bool ok = false;
+        if (fast_str) {
+            SideStream side(c);
+            ok = sketch2_end(c, job_str);          // synchronises the side stream only
+            if (ok) CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream));
+        }
+        if (ok) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        else sketch_readset(c, str, o, &c->sk_str, 0, 0xffffffffu, fast_str);   // not applicable, or a sub-tile overflowed
+        sq = &c->sk_str;
+    };
     if (sharded_index) {
-        Sketch2Job job_str;
-        bool fast_str = false, tried = false;
         c->prof.sbegin(ST_INDEX);
         // the blacklist holds ~2e-4 of the distinct keys; room for 1/512 of a rank's nominal share of the bases
         // (a number every rank derives alike: with local blocks only the streamed set is common to all ranks)
         const uint64_t bl_cap = c->local_block ? std::max<uint64_t>(4096, str->total_bases / 256)
                                                : std::max<uint64_t>(4096, idx->total_bases / (uint64_t)world / 512);
-        ShardedJob J = build_index_sharded_launch(c, c->sk_idx, o, bl_cap, [&]() {
-            tried = true;
-            fast_str = sketch2_begin(c, str, o, &c->sk_str, 0, str->n, &job_str);
-        });
+        ShardedJob J = build_index_sharded_launch(c, c->sk_idx, o, bl_cap, [&]() {});
         c->prof.send(ST_INDEX);
-        (void)tried;
-        if (!fast_str || !sketch2_end(c, job_str)) sketch_readset(c, str, o, &c->sk_str, 0, 0xffffffffu, true);
-        sq = &c->sk_str;
+        finish_str();
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if (build_index_sharded_finish(c, &J, &S)) B = J.B;
         else { c->prof.sbegin(ST_INDEX); B = build_index_sharded_exact(c, c->sk_idx, o, &S); c->prof.send(ST_INDEX); }
@@ -1272,8 +1298,8 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         B = build_index_launch(c, c->sk_idx, o);
         S.n_target_minimizers = c->sk_idx.M;
         c->prof.send(ST_INDEX);
-        if (need_str) { sketch_readset(c, str, o, &c->sk_str); sq = &c->sk_str; }
-        else CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (need_str) finish_str();
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));   // the occurrence histogram of the index
         build_index_finish(c, o, &B);
     }
     S.n_keys = B.n_keys; S.mid_occ = B.mid_occ;
@@ -1867,6 +1893,10 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         { const char *e = getenv("LRGE_SKETCH_LEGACY"); c->sketch_legacy = (e && e[0] == '1') || c->sketch_two_pass; }
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        { const char *e = getenv("LRGE_NO_SIDE_STREAM"); c->no_side = e && e[0] == '1'; }
         c->prof.s = c->stream;
         c->prof.reset();
         { size_t f = 0, t = 0; CUDA_CHECK(cudaMemGetInfo(&f, &t)); c->free_at_create = f; c->held_at_create = dev_bytes_in_use().load(); }
@@ -1885,6 +1915,9 @@ void lrge_gpu_destroy(lrge_ctx *ctx) {
     if (ctx->pin) { cudaFreeHost(ctx->pin); ctx->pin = nullptr; }
     if (ctx->pin2) { cudaFreeHost(ctx->pin2); ctx->pin2 = nullptr; }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
     delete ctx;
 }
