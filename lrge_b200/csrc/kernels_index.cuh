@@ -438,6 +438,65 @@ __global__ void __launch_bounds__(OM_THREADS) owner_merge_kernel(OwnerMergeArgs 
     }
 }
 
+// ---- key exchange over peer memory (NVLink / NVSwitch) --------------------------------------------------------------
+// Every rank exports a receive window and a small array of landing flags (CUDA IPC); a sender stores its slice of packed
+// entries for rank d straight into d's window at the offset the send-count matrix gives it, and then raises
+// flags_d[sender] = epoch.  Replaces ncclSend / ncclRecv (point-to-point NCCL moved ~100 GB/s per peer here).
+struct PeerPushArgs {
+    const uint64_t *src;                      // this rank's packed entries, in key order
+    uint64_t *dst[OM_MAXW];                   // window of every rank (dst[me] = the local one)
+    unsigned long long *flag[OM_MAXW];        // &flags_d[me] in rank d's flag array
+    uint64_t sbeg[OM_MAXW + 1];               // slice of src for rank d: [sbeg[d], sbeg[d + 1])
+    uint64_t doff[OM_MAXW];                   // where this rank's slice starts in d's window (entries)
+    unsigned int *done;                       // [OM_MAXW] CTAs finished per destination (self-resetting)
+    unsigned long long epoch;
+    int W, me;
+    uint32_t ctas_per_dest;
+};
+
+__global__ void __launch_bounds__(256) peer_push_kernel(PeerPushArgs A) {
+    const int d = blockIdx.x / A.ctas_per_dest;
+    const uint32_t j = blockIdx.x % A.ctas_per_dest;
+    const uint64_t n = A.sbeg[d + 1] - A.sbeg[d];
+    const uint64_t per = (n + A.ctas_per_dest - 1) / A.ctas_per_dest;
+    const uint64_t lo = min(n, per * j), hi = min(n, lo + per);
+    const uint64_t *s = A.src + A.sbeg[d];
+    uint64_t *t = A.dst[d] + A.doff[d];
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += 4ull * blockDim.x) {      // four independent 8-byte copies per thread
+        uint64_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint64_t k = i + (uint64_t)u * blockDim.x; v[u] = k < hi ? s[k] : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint64_t k = i + (uint64_t)u * blockDim.x; if (k < hi) t[k] = v[u]; }
+    }
+    __threadfence_system();                                                     // this CTA's stores are visible system-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&A.done[d], 1u);                    // ... before it counts as finished
+        if (prev == A.ctas_per_dest - 1) {                                      // last CTA of this destination: raise the flag
+            A.done[d] = 0;
+            __threadfence_system();
+            if (d != A.me) *reinterpret_cast<volatile unsigned long long *>(A.flag[d]) = A.epoch;
+        }
+    }
+}
+
+// wait until every peer's slice of this epoch has landed in the local window; gives up after ~4 s (err = 1)
+__global__ void peer_wait_kernel(const unsigned long long *flags, int W, int me, unsigned long long epoch, unsigned int *err) {
+    const int s = threadIdx.x;
+    if (s >= W || s == me) return;
+    const volatile unsigned long long *f = flags + s;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*f < epoch) {
+        __nanosleep(200);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) { *err = 1; break; }
+    }
+    __threadfence_system();
+}
+
 // blacklist = candidates whose global count exceeds mid_occ (meta[0])
 __global__ void bl_from_cand_kernel(const uint64_t *__restrict__ cand, const unsigned long long *__restrict__ cand_n,
                                     const unsigned long long *__restrict__ meta, uint64_t *__restrict__ bl, unsigned long long *bl_n,

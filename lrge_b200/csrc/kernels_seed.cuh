@@ -88,20 +88,35 @@ __global__ void seed_count_kernel(const uint64_t *__restrict__ qx, const uint64_
         if (!scan) cnt = n;
     }
     if (scan) {
-        // long lists: the warp counts the kept hits of one list together
+        // long lists: the warp counts the kept hits of one list together; the first 32 entries of up to four lists are
+        // fetched back to back (four loads in flight per lane)
         uint32_t big = __ballot_sync(0xffffffffu, n >= COOP_MIN_HITS);
         while (big) {
-            const int src = __ffs(big) - 1;
-            big &= big - 1;
-            const uint32_t s_start = __shfl_sync(0xffffffffu, start, src), s_n = __shfl_sync(0xffffffffu, n, src);
-            const uint64_t s_y = __shfl_sync(0xffffffffu, y, src);
-            uint32_t kept = 0;
-            for (uint32_t b = 0; b < s_n; b += 32) {
-                const uint32_t e = b + lane;
-                const bool keep = e < s_n && !skip_hit(__ldg(I.ty + s_start + e), (uint32_t)(s_y >> 32), (uint32_t)s_y, S);
-                kept += __popc(__ballot_sync(0xffffffffu, keep));
+            int src[4];
+            uint32_t s_start[4], s_n[4];
+            uint64_t r0[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { src[k] = big ? __ffs(big) - 1 : -1; big &= big - 1; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int sl = src[k] < 0 ? 0 : src[k];
+                s_start[k] = __shfl_sync(0xffffffffu, start, sl);
+                s_n[k] = src[k] < 0 ? 0u : __shfl_sync(0xffffffffu, n, sl);
+                r0[k] = lane < s_n[k] ? __ldg(I.ty + s_start[k] + lane) : 0ull;
             }
-            if ((int)lane == src) cnt = kept;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (src[k] < 0) continue;
+                const uint64_t s_y = __shfl_sync(0xffffffffu, y, src[k]);
+                uint32_t kept = 0;
+                for (uint32_t b = 0; b < s_n[k]; b += 32) {
+                    const uint32_t e = b + lane;
+                    const uint64_t r = b == 0 ? r0[k] : (e < s_n[k] ? __ldg(I.ty + s_start[k] + e) : 0ull);
+                    const bool keep = e < s_n[k] && !skip_hit(r, (uint32_t)(s_y >> 32), (uint32_t)s_y, S);
+                    kept += __popc(__ballot_sync(0xffffffffu, keep));
+                }
+                if ((int)lane == src[k]) cnt = kept;
+            }
         }
         if (n && n < COOP_MIN_HITS) {
             // 128-bit loads, two hit-list entries each, four loads in flight
@@ -164,24 +179,38 @@ __global__ void __launch_bounds__(256) anchor_fill_kernel(const uint64_t *__rest
         else akey[at] = (KT)(((((KT)((uint32_t)(r >> 32) - K.rid_base)) << 1 | (KT)rev) << K.PB) | (KT)((uint32_t)r >> 1));
         aval[at] = span << 24 | (rev ? qp_r : qp_f);
     };
-    // long hit lists: one list at a time, 32 consecutive entries per step across the warp
+    // long hit lists: 32 consecutive entries per step across the warp; the first 32 entries of up to four lists are
+    // fetched back to back (four loads in flight per lane)
     uint32_t big = __ballot_sync(0xffffffffu, active && n >= COOP_MIN_HITS);
     while (big) {
-        const int src = __ffs(big) - 1;
-        big &= big - 1;
-        const uint32_t s_start = __shfl_sync(0xffffffffu, start, src), s_n = __shfl_sync(0xffffffffu, n, src);
-        const uint32_t s_span = __shfl_sync(0xffffffffu, q_span, src), s_qlen = __shfl_sync(0xffffffffu, qlen, src);
-        const uint64_t s_y = __shfl_sync(0xffffffffu, y, src);
-        uint64_t s_o = __shfl_sync(0xffffffffu, o, src);
-        const uint32_t s_qid = (uint32_t)(s_y >> 32), s_qpos = (uint32_t)s_y;
-        for (uint32_t b = 0; b < s_n; b += 32) {
-            const uint32_t e = b + lane;
-            bool keep = e < s_n;
-            uint64_t r = 0;
-            if (keep) { r = __ldg(I.ty + s_start + e); if (scan && skip_hit(r, s_qid, s_qpos, S)) keep = false; }
-            const uint32_t km = __ballot_sync(0xffffffffu, keep);
-            if (keep) emit(s_o + __popc(km & lt), r, s_qid, s_qpos, s_span, s_qlen);
-            s_o += __popc(km);
+        int src[4];
+        uint32_t s_start[4], s_n[4];
+        uint64_t r0[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { src[k] = big ? __ffs(big) - 1 : -1; big &= big - 1; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int sl = src[k] < 0 ? 0 : src[k];
+            s_start[k] = __shfl_sync(0xffffffffu, start, sl);
+            s_n[k] = src[k] < 0 ? 0u : __shfl_sync(0xffffffffu, n, sl);
+            r0[k] = lane < s_n[k] ? __ldg(I.ty + s_start[k] + lane) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (src[k] < 0) continue;
+            const uint32_t s_span = __shfl_sync(0xffffffffu, q_span, src[k]), s_qlen = __shfl_sync(0xffffffffu, qlen, src[k]);
+            const uint64_t s_y = __shfl_sync(0xffffffffu, y, src[k]);
+            uint64_t s_o = __shfl_sync(0xffffffffu, o, src[k]);
+            const uint32_t s_qid = (uint32_t)(s_y >> 32), s_qpos = (uint32_t)s_y;
+            for (uint32_t b = 0; b < s_n[k]; b += 32) {
+                const uint32_t e = b + lane;
+                bool keep = e < s_n[k];
+                const uint64_t r = b == 0 ? r0[k] : (keep ? __ldg(I.ty + s_start[k] + e) : 0ull);
+                if (keep && scan && skip_hit(r, s_qid, s_qpos, S)) keep = false;
+                const uint32_t km = __ballot_sync(0xffffffffu, keep);
+                if (keep) emit(s_o + __popc(km & lt), r, s_qid, s_qpos, s_span, s_qlen);
+                s_o += __popc(km);
+            }
         }
     }
     if (!active || n >= COOP_MIN_HITS) return;

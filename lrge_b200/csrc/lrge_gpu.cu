@@ -249,6 +249,17 @@ struct lrge_ctx {
     // one process per GPU: NCCL communicator for the per-read count reduction
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    // key exchange over peer memory (kernels_index.cuh: peer_push_kernel): IPC-exported flags and receive window
+    struct PeerLink {
+        bool ok = false;                                   // every rank exported / mapped its flags (agreed collectively)
+        unsigned long long *flags = nullptr;
+        unsigned long long *flags_peer[16] = {};
+        DevBuf win;                                        // receive window
+        uint64_t *win_peer[16] = {};
+        size_t win_bytes = 0;                              // agreed size: the same on every rank
+        unsigned long long epoch = 0;
+        DevBuf hbuf, done;
+    } link;
 };
 
 namespace {
@@ -916,6 +927,58 @@ BuiltIndex build_index_sharded_exact(lrge_ctx *c, const Sketch &sk, const MapOpt
     return B;
 }
 
+// ---- peer-memory link: collective helpers (every rank calls them at the same point) ----------------------------------
+bool all_agree(lrge_ctx *c, bool mine) {                  // true iff every rank passes true (also a barrier)
+    c->link.hbuf.reserve(4096);
+    uint32_t v = mine ? 1u : 0u;
+    CUDA_CHECK(cudaMemcpyAsync(c->link.hbuf.p, &v, 4, cudaMemcpyHostToDevice, c->stream));
+    NCCL_CHECK(ncclAllReduce(c->link.hbuf.p, c->link.hbuf.p, 1, ncclUint32, ncclMin, c->comm, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&v, c->link.hbuf.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return v != 0;
+}
+
+// all-gather the IPC handle of `ptr` and map every peer's allocation; out[d] = mapped pointer (out[me] = ptr).
+// Returns the collective verdict; on false everything that was opened here has been closed again.
+bool exchange_and_open(lrge_ctx *c, void *ptr, bool have, void **out) {
+    const int W = c->world, me = c->rank;
+    struct Rec { cudaIpcMemHandle_t h; unsigned long long ok; unsigned long long pad; };
+    static_assert(sizeof(Rec) == 80, "record layout");
+    Rec mine{};
+    if (have && cudaIpcGetMemHandle(&mine.h, ptr) == cudaSuccess) mine.ok = 1; else cudaGetLastError();
+    c->link.hbuf.reserve(4096 + sizeof(Rec) * (size_t)(W + 1));
+    uint8_t *base = c->link.hbuf.as<uint8_t>() + 4096;
+    CUDA_CHECK(cudaMemcpyAsync(base + sizeof(Rec) * W, &mine, sizeof(Rec), cudaMemcpyHostToDevice, c->stream));
+    NCCL_CHECK(ncclAllGather(base + sizeof(Rec) * W, base, sizeof(Rec), ncclUint8, c->comm, c->stream));
+    std::vector<Rec> all(W);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), base, sizeof(Rec) * W, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    bool ok = true;
+    for (int d = 0; d < W; ++d) ok = ok && all[d].ok;
+    for (int d = 0; d < W; ++d) out[d] = nullptr;
+    if (ok) {
+        out[me] = ptr;
+        for (int d = 0; d < W && ok; ++d) {
+            if (d == me) continue;
+            if (cudaIpcOpenMemHandle(&out[d], all[d].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); out[d] = nullptr; ok = false; }
+        }
+    }
+    const bool agreed = all_agree(c, ok);
+    if (!agreed) for (int d = 0; d < W; ++d) { if (d != me && out[d]) cudaIpcCloseMemHandle(out[d]); out[d] = nullptr; }
+    return agreed;
+}
+
+void peer_link_close(lrge_ctx *c) {
+    auto &L = c->link;
+    for (int d = 0; d < 16; ++d) {
+        if (d != c->rank && L.flags_peer[d]) cudaIpcCloseMemHandle(L.flags_peer[d]);
+        if (d != c->rank && L.win_peer[d]) cudaIpcCloseMemHandle(L.win_peer[d]);
+        L.flags_peer[d] = nullptr; L.win_peer[d] = nullptr;
+    }
+    if (L.flags) { cudaFree(L.flags); L.flags = nullptr; }
+    L.win.release(); L.win_bytes = 0; L.ok = false;
+}
+
 // The same, fast path: ONE host synchronisation (the W x W matrix of send counts, which ncclSend/ncclRecv need on the
 // host), hidden behind `while_waiting` (the caller launches the sketch of the streamed set there).  Packed
 // (key << 24 | count) entries, one array per exchange; the owner sorts keys only; mid_occ is computed on the device from
@@ -1021,22 +1084,61 @@ ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOp
     for (int s2 = 0; s2 < W; ++s2) roff[s2 + 1] = roff[s2] + mat[(size_t)s2 * W + me];
     const uint64_t R = roff[W];
     if (R >= (1ull << 32) - 2) throw std::length_error("too many distinct keys per owner rank");
-    c->rkey.reserve((R + 1) * 8);
-    c->prof.kbegin("ncclSend/Recv(key ranges)", 8.0 * R);
-    NCCL_CHECK(ncclGroupStart());
-    for (int d = 0; d < W; ++d) {
-        const uint64_t sc = bounds[d + 1] - bounds[d];
-        if (sc) NCCL_CHECK(ncclSend(c->ukey.as<uint64_t>() + bounds[d], sc, ncclUint64, d, c->comm, c->stream));
+    uint64_t Rmax = 0;                                            // the largest receive total of any rank (every rank knows the matrix)
+    for (int d = 0; d < W; ++d) { uint64_t t = 0; for (int s2 = 0; s2 < W; ++s2) t += mat[(size_t)s2 * W + d]; Rmax = std::max(Rmax, t); }
+    const uint64_t *recv_buf = nullptr;
+    if (c->link.ok && (Rmax + 1) * 8 > c->link.win_bytes) {
+        // (re)establish the receive windows -- the same decision on every rank; warm-up calls only.  Nobody frees a
+        // window before everybody has unmapped it.
+        auto &L = c->link;
+        for (int d = 0; d < W; ++d) { if (d != me && L.win_peer[d]) cudaIpcCloseMemHandle(L.win_peer[d]); L.win_peer[d] = nullptr; }
+        all_agree(c, true);
+        const size_t nb = (Rmax + 1) * 8 + (Rmax + 1) * 2 + 4096;
+        bool have = true;
+        L.win.release();
+        try { L.win.reserve(nb); } catch (const std::exception &) { have = false; }
+        void *mapped[16] = {};
+        if (exchange_and_open(c, L.win.p, have, mapped)) { for (int d = 0; d < W; ++d) L.win_peer[d] = (uint64_t *)mapped[d]; L.win_bytes = nb; }
+        else { L.ok = false; L.win_bytes = 0; }                   // every rank falls back to NCCL send / recv alike
     }
-    for (int s2 = 0; s2 < W; ++s2)
-        if (roff[s2 + 1] > roff[s2]) NCCL_CHECK(ncclRecv(c->rkey.as<uint64_t>() + roff[s2], roff[s2 + 1] - roff[s2], ncclUint64, s2, c->comm, c->stream));
-    NCCL_CHECK(ncclGroupEnd());
-    c->prof.kend();
+    if (c->link.ok) {
+        auto &L = c->link;
+        ++L.epoch;
+        L.done.reserve(256);
+        PeerPushArgs PA{};
+        PA.src = c->ukey.as<uint64_t>(); PA.done = L.done.as<unsigned int>(); PA.epoch = L.epoch; PA.W = W; PA.me = me;
+        PA.ctas_per_dest = (uint32_t)std::max(1, 148 * 4 / W);
+        for (int d = 0; d < W; ++d) {
+            PA.dst[d] = d == me ? L.win.as<uint64_t>() : L.win_peer[d];
+            PA.flag[d] = d == me ? nullptr : L.flags_peer[d] + me;
+            PA.sbeg[d] = bounds[d];
+            uint64_t off = 0;
+            for (int s2 = 0; s2 < me; ++s2) off += mat[(size_t)s2 * W + d];
+            PA.doff[d] = off;
+        }
+        PA.sbeg[W] = bounds[W];
+        KLAUNCH(c, "peer_push_kernel", 8.0 * R, peer_push_kernel<<<PA.ctas_per_dest * W, 256, 0, c->stream>>>(PA));
+        KLAUNCH(c, "peer_wait_kernel", 8.0 * W, peer_wait_kernel<<<1, 32, 0, c->stream>>>(L.flags, W, me, L.epoch, L.done.as<unsigned int>() + 32));
+        recv_buf = L.win.as<uint64_t>();
+    } else {
+        c->rkey.reserve((R + 1) * 8);
+        c->prof.kbegin("ncclSend/Recv(key ranges)", 8.0 * R);
+        NCCL_CHECK(ncclGroupStart());
+        for (int d = 0; d < W; ++d) {
+            const uint64_t sc = bounds[d + 1] - bounds[d];
+            if (sc) NCCL_CHECK(ncclSend(c->ukey.as<uint64_t>() + bounds[d], sc, ncclUint64, d, c->comm, c->stream));
+        }
+        for (int s2 = 0; s2 < W; ++s2)
+            if (roff[s2 + 1] > roff[s2]) NCCL_CHECK(ncclRecv(c->rkey.as<uint64_t>() + roff[s2], roff[s2 + 1] - roff[s2], ncclUint64, s2, c->comm, c->stream));
+        NCCL_CHECK(ncclGroupEnd());
+        c->prof.kend();
+        recv_buf = c->rkey.as<uint64_t>();
+    }
     // owner: sum the <= W partial counts of every key (owner_merge_kernel: slices of the key range through a
     // shared-memory table), histogram of the sums
     CUDA_CHECK(cudaMemsetAsync(hist_d, 0, (OCC_BINS + 2 + 8) * 8, c->stream));
     OwnerMergeArgs OA{};
-    OA.rk = c->rkey.as<uint64_t>(); OA.W = W;
+    OA.rk = recv_buf; OA.W = W;
     for (int s2 = 0; s2 <= W; ++s2) OA.roff[s2] = roff[s2];
     const int kbits = 2 * o.k;
     OA.klo = (((uint64_t)me << kbits) + W - 1) / (uint64_t)W;
@@ -1079,6 +1181,8 @@ ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOp
     // results for build_index_sharded_finish: meta[0..2], then n_keys and the minimizer total of all shards
     CUDA_CHECK(cudaMemcpyAsync(pin64, meta_d, 24, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(pin64 + 3, hist_d + OCC_BINS, 16, cudaMemcpyDeviceToHost, c->stream));
+    pin64[5] = 0;
+    if (c->link.ok) CUDA_CHECK(cudaMemcpyAsync(pin64 + 5, c->link.done.as<unsigned int>() + 32, 4, cudaMemcpyDeviceToHost, c->stream));
     B.mid_occ = -1; B.n_keys = 0;
     J.active = true;
     return J;
@@ -1087,6 +1191,7 @@ ShardedJob build_index_sharded_launch(lrge_ctx *c, const Sketch &sk, const MapOp
 // after a synchronisation of the stream: false = one of the fallback conditions held on some rank (run the exact path)
 bool build_index_sharded_finish(lrge_ctx *c, ShardedJob *J, lrge_stats *S) {
     const unsigned long long *r = reinterpret_cast<const unsigned long long *>(c->pin2);
+    if (r[5]) throw std::runtime_error("key exchange over peer memory timed out (a peer rank did not deliver its slice)");
     if (r[1] || r[2]) return false;
     J->B.mid_occ = (int)r[0];
     J->B.n_keys = r[3];
@@ -1911,6 +2016,7 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
 void lrge_gpu_destroy(lrge_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    peer_link_close(ctx);
     if (ctx->comm) { ncclCommDestroy(ctx->comm); ctx->comm = nullptr; }
     if (ctx->pin) { cudaFreeHost(ctx->pin); ctx->pin = nullptr; }
     if (ctx->pin2) { cudaFreeHost(ctx->pin2); ctx->pin2 = nullptr; }
@@ -2068,6 +2174,23 @@ int lrge_gpu_comm_init(lrge_ctx *ctx, int rank, int world, const uint8_t *unique
         ncclResult_t r = ncclCommInitRank(&ctx->comm, world, id, rank);
         if (r != ncclSuccess) { ctx->comm = nullptr; throw NcclError(std::string("ncclCommInitRank: ") + ncclGetErrorString(r)); }
         ctx->rank = rank; ctx->world = world;
+        // peer-memory link for the key exchange: flags now, receive windows on first use.  Collective; any failure on
+        // any rank (no IPC in this container, no peer access) leaves every rank on ncclSend / ncclRecv.
+        peer_link_close(ctx);
+        ctx->link.epoch = 0;
+        if (world > 1 && world <= 16) {
+            const char *e = getenv("LRGE_NO_PEER_PUSH");
+            bool have = !(e && e[0] == '1');
+            if (have && cudaMalloc((void **)&ctx->link.flags, 4096) != cudaSuccess) { cudaGetLastError(); ctx->link.flags = nullptr; have = false; }
+            if (ctx->link.flags) CUDA_CHECK(cudaMemset(ctx->link.flags, 0, 4096));
+            ctx->link.done.reserve(256);
+            CUDA_CHECK(cudaMemset(ctx->link.done.p, 0, 256));
+            void *mapped[16] = {};
+            if (exchange_and_open(ctx, ctx->link.flags, have, mapped)) {
+                for (int d = 0; d < world; ++d) ctx->link.flags_peer[d] = (unsigned long long *)mapped[d];
+                ctx->link.ok = true;
+            }
+        }
     });
 }
 
