@@ -305,6 +305,20 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0])
     assert np.array_equal(e2e_last.counts, last.counts)
+    # what the link gives a plain pinned copy of the same size (context for e2e - value): one cudaMemcpyAsync, CUDA events
+    h2d_gbs = None
+    try:
+        nb = int(T.off[T.n * (rank + 1) // world] - T.off[T.n * rank // world]) + int(Q.total_bases)
+        host = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        devb = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        devb.copy_(host, non_blocking=True); torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); devb.copy_(host, non_blocking=True); e1.record(); torch.cuda.synchronize()
+        h2d_gbs = nb / 1e9 / (e0.elapsed_time(e1) / 1e3)
+        del host, devb
+    except Exception:
+        pass
     lo, hi = T.n * rank // world, T.n * (rank + 1) // world          # a rank copies its own target block + all queries
     h2d_rank = int(T.off[hi] - T.off[lo]) + int(Q.total_bases)
     h2d_all = int(T.total_bases) + world * int(Q.total_bases)
@@ -396,7 +410,8 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": overlaps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h * world,
-                "h2d_bytes_per_step_per_rank": h2d_rank, "d2h_bytes_per_step_per_rank": d2h, "ms_per_step": e2e_ms},
+                "h2d_bytes_per_step_per_rank": h2d_rank, "d2h_bytes_per_step_per_rank": d2h, "ms_per_step": e2e_ms,
+                "plain_pinned_h2d_gbs_rank0": h2d_gbs},
         "gpu_launches": launches,
         "clocks": clocks,
     }
