@@ -94,7 +94,8 @@ typedef struct lrge_stats {
     float ms_comm;               /* NCCL reduction of the per-read counts */
     uint32_t n_deferred;         /* queries the per-query shared-memory sort handed to the device-wide sort */
     uint32_t n_rounds;           /* shared-memory rounds of the per-query sort (>= queries holding anchors) */
-    float reserved[3];
+    uint32_t n_index_runs;       /* sorted runs the index was merged from: 1, or 2 when the host-buffer path sorted per half */
+    float reserved[2];
 } lrge_stats;
 
 typedef struct lrge_ctx lrge_ctx;

@@ -77,7 +77,8 @@ class Stats(ctypes.Structure):
         ("ms_index", ctypes.c_float), ("ms_seed", ctypes.c_float), ("ms_sort", ctypes.c_float),
         ("ms_chain", ctypes.c_float), ("ms_d2h", ctypes.c_float), ("ms_total", ctypes.c_float),
         ("ms_chain_kernel", ctypes.c_float), ("ms_comm", ctypes.c_float),
-        ("n_deferred", ctypes.c_uint32), ("n_rounds", ctypes.c_uint32), ("reserved", ctypes.c_float * 3),
+        ("n_deferred", ctypes.c_uint32), ("n_rounds", ctypes.c_uint32), ("n_index_runs", ctypes.c_uint32),
+        ("reserved", ctypes.c_float * 2),
     ]
 
     def as_dict(self):

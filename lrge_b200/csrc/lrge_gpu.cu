@@ -25,6 +25,8 @@
 #endif
 
 #include <cub/cub.cuh>
+#include <cub/device/device_merge.cuh>
+#include <functional>
 #include <nccl.h>
 
 #include <algorithm>
@@ -153,7 +155,26 @@ struct Prof {
         if (!kernels) return;
         for (size_t i = 0; i < names.size(); ++i) if (names[i] == name) passes[ST_COUNT + i] = n;
     }
-    void resolve() {                                   // the stream must be idle
+    // LRGE_TIMELINE=1: marks (any stream) and spans as offsets from the start of the call, printed by resolve()
+    struct Mark { const char *what; cudaEvent_t e; };
+    std::vector<Mark> marks;
+    bool timeline = false;
+    void mark(const char *what, cudaStream_t st) {     // own events: marks are recorded before reset() opens the call
+        if (!timeline) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.push_back({what, e});
+    }
+    void resolve() {                                   // the streams must be idle
+        if (timeline && stage_ev[ST_TOTAL]) {
+            static const char *stn[] = {"pack", "sketch", "index", "seed", "sort", "chain", "d2h", "total", "comm"};
+            for (auto &m : marks) { float t = 0; if (cudaEventElapsedTime(&t, stage_ev[ST_TOTAL], m.e) == cudaSuccess) fprintf(stderr, "[timeline] %8.3f ms  %s\n", t, m.what); else cudaGetLastError(); }
+            for (auto &sp : spans) {
+                float a = 0, b = 0;
+                if (cudaEventElapsedTime(&a, stage_ev[ST_TOTAL], sp.a) != cudaSuccess || cudaEventElapsedTime(&b, stage_ev[ST_TOTAL], sp.b) != cudaSuccess) { cudaGetLastError(); continue; }
+                fprintf(stderr, "[timeline] %8.3f .. %8.3f ms  %s\n", a, b, sp.id < ST_COUNT ? stn[sp.id] : names[sp.id - ST_COUNT].c_str());
+            }
+        }
+        for (auto &m : marks) cudaEventDestroy(m.e);
+        marks.clear();
         for (auto &sp : spans) { float t = 0; cudaEventElapsedTime(&t, sp.a, sp.b); ms[sp.id] += t; ++count[sp.id]; }
         spans.clear();
     }
@@ -188,6 +209,13 @@ struct lrge_staged {
     // copy of chunk i + 1: chunk j = reads [chunk_hi[j-1], chunk_hi[j]) (absolute read ids)
     std::vector<uint32_t> chunk_hi;
     std::vector<cudaEvent_t> chunk_ev;
+    // async staging also uploads the tile tables of the lane-serial sketch for the staged block, AHEAD of the bases: queued
+    // behind them (one H2D engine, FIFO) they would hold the first sketch launch back until every base has arrived
+    DevBuf t_tile_off, t_tile_read, t_sub_off, t_len, t_rid_map;
+    std::vector<uint32_t> tab_tile_off;                    // host copy of tile_off (launch offsets per chunk)
+    uint32_t tab_first = 0, tab_count = 0, tab_tiles = 0;
+    uint64_t tab_bases = 0;
+    bool tab_valid = false;
     ~lrge_staged() { if (ready) cudaEventDestroy(ready); for (auto e : chunk_ev) cudaEventDestroy(e); }
 };
 
@@ -204,6 +232,12 @@ struct lrge_ctx {
     cudaStream_t side_stream = nullptr;    // the sketch of the streamed set runs here, next to the index build on `stream`
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool on_side = false;                  // `stream` and `side_stream` are swapped (SideStream)
+    uint64_t min_chunk = 8ull << 20;       // LRGE_MIN_CHUNK=bytes: smallest async staging chunk (tests reach the chunked paths with small sets)
+    bool fork_recorded = false;            // ev_fork already marks the point the side stream has to wait for
+    bool no_halves = true;                 // LRGE_INDEX_HALVES=1 turns the per-half index build of the host-buffer path ON: measured
+                                           // slower on B200 (7.84 vs 7.39 ms for C2: the copy takes 1.3 ms at ~60 GB/s, the
+                                           // indexed set's GPU work 3 ms, and two half sorts + a merge cost more than one sort)
+    DevBuf hk_a, hk_b, hv_b;               // per-half index build: composite keys (two buffers), values of the sorted halves
     bool no_side = false;                  // LRGE_NO_SIDE_STREAM=1: everything on one stream (A/B measurements)
     DevBuf cub_tmp2;                       // CUB temporary storage of the side stream
     std::string err;
@@ -339,8 +373,43 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool asy
     s->asc.reserve((b1 - b0) + 64);
     CUDA_CHECK(cudaMemsetAsync(s->asc.as<uint8_t>() + (b1 - b0), 0, 64, c->copy_stream));   // slack read by the word-wise packers
     s->chunk_hi.clear();
+    s->tab_valid = false;
+    if (async && blk_count) {
+        const uint32_t n = blk_count;
+        std::vector<uint64_t> soff(n);
+        std::vector<uint32_t> slen(n);
+        s->tab_tile_off.resize((size_t)n + 1);
+        uint32_t tiles = 0;
+        uint64_t nbases = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint64_t l = rs->off[blk_first + i + 1] - rs->off[blk_first + i];
+            s->tab_tile_off[i] = tiles;
+            soff[i] = rs->off[blk_first + i] - b0;
+            slen[i] = (uint32_t)std::min<uint64_t>(l, 0xffffffffu);
+            nbases += l;
+            tiles += (uint32_t)((l + TILE_POS - 1) / TILE_POS);
+        }
+        s->tab_tile_off[n] = tiles;
+        std::vector<uint32_t> tile_read(tiles);
+        for (uint32_t i = 0; i < n; ++i) for (uint32_t t = s->tab_tile_off[i]; t < s->tab_tile_off[i + 1]; ++t) tile_read[t] = i;
+        auto up = [&](DevBuf &d, const void *src, size_t bytes) {
+            d.reserve(std::max<size_t>(bytes, 16));
+            if (bytes) CUDA_CHECK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        };
+        up(s->t_tile_off, s->tab_tile_off.data(), ((size_t)n + 1) * 4);
+        up(s->t_tile_read, tile_read.data(), (size_t)tiles * 4);
+        up(s->t_sub_off, soff.data(), (size_t)n * 8);
+        up(s->t_len, slen.data(), (size_t)n * 4);
+        if (blk_first != 0 || blk_count != rs->n) {             // a proper block: read ids of its entries
+            std::vector<uint32_t> rid_map(n);
+            std::iota(rid_map.begin(), rid_map.end(), blk_first);
+            up(s->t_rid_map, rid_map.data(), (size_t)n * 4);
+        }
+        s->tab_first = blk_first; s->tab_count = n; s->tab_tiles = tiles; s->tab_bases = nbases;
+        s->tab_valid = true;
+    }
     if (b1 > b0) {
-        const uint64_t min_chunk = 8ull << 20;
+        const uint64_t min_chunk = c->min_chunk;
         const uint32_t n_chunks = async ? (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(8, (b1 - b0) / min_chunk)) : 1;
         uint32_t lo = blk_first;
         for (uint32_t j = 0; j < n_chunks && lo < blk_first + blk_count; ++j) {
@@ -381,6 +450,7 @@ void stage_readset(lrge_ctx *c, const lrge_readset *rs, lrge_staged *s, bool asy
     if (async) {
         if (!s->ready) CUDA_CHECK(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventRecord(s->ready, c->copy_stream));
+        c->prof.mark("bases of a staged set have arrived (copy stream)", c->copy_stream);
         s->pending = true;
     } else CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
 }
@@ -390,6 +460,18 @@ __global__ void gather_u32_kernel(const uint32_t *__restrict__ src, const uint32
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[(size_t)idx[i] * mul];
 }
+__global__ void gather_u32_base_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t mul, uint32_t n,
+                                       uint32_t base, uint32_t *__restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[(size_t)idx[i] * mul] + base;
+}
+// sort keys of one half of the indexed set: hash << 2 | half -- equal hashes of different halves never tie, so the
+// (unstable) merge of the two sorted runs reproduces the stable sort of the whole set
+__global__ void key32_half_kernel(const uint64_t *__restrict__ x, uint64_t M, uint32_t g, uint32_t *__restrict__ k32) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) k32[i] = (uint32_t)(x[i] >> 8) << 2 | g;
+}
+struct LessU32 { __host__ __device__ bool operator()(uint32_t a, uint32_t b) const { return a < b; } };
 __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32_t *__restrict__ idx, uint32_t n,
                                   uint64_t *__restrict__ dst) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,9 +483,13 @@ __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32
 // sketch2_begin launches and returns without waiting (false: not applicable / no room, nothing launched); sketch2_end
 // waits for the minimizer total, then packs.  It returns false if a sub-tile overflowed its slot (very dense reads):
 // the caller falls back to the exact two-pass path.
-struct Sketch2Job { bool active = false; uint32_t n = 0, nw = 0; Sketch *out = nullptr; };
+struct Sketch2Job { bool active = false; uint32_t n = 0, nw = 0; Sketch *out = nullptr; const uint32_t *d_tile_off = nullptr; };
 
-bool sketch2_begin(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first, uint32_t count, Sketch2Job *job) {
+// half: called after the launches of the first and of the second half of the staged chunks with the sub-tile range
+// [w0, w1) and the reads [r_lo, r_hi) they cover (sketch_index_halves); the scan over all sub-tiles is then left out.
+using HalfFn = std::function<bool(uint32_t w0, uint32_t w1, uint32_t r_lo, uint32_t r_hi, bool last)>;
+bool sketch2_begin(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, uint32_t first, uint32_t count, Sketch2Job *job,
+                   const HalfFn *half = nullptr) {
     job->active = false;
     if (o.is_hpc || o.k != 15 || c->sketch_legacy) return false;
     if (first > s->n) first = s->n;
@@ -411,47 +497,85 @@ bool sketch2_begin(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *o
     if (count && (first < s->blk_first || first + count > s->blk_first + s->blk_count))
         throw std::runtime_error("internal: sketch of reads that were not staged");
     const uint32_t n = count;
-    std::vector<uint64_t> soff(n);
-    std::vector<uint32_t> tile_off((size_t)n + 1), slen(n), rid_map(n);
+    // tables uploaded ahead of the bases by the async staging (same block): nothing to build or copy here
+    const bool pre = s->tab_valid && s->pending && first == s->tab_first && count == s->tab_count;
+    std::vector<uint64_t> soff;
+    std::vector<uint32_t> tile_off_own, slen, rid_map, tile_read;
     uint32_t tiles = 0;
     uint64_t nbases = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t r = first + i;
-        tile_off[i] = tiles;
-        soff[i] = s->h_off[r] - s->blk_base;
-        slen[i] = s->h_len[r];
-        rid_map[i] = r;
-        nbases += s->h_len[r];
-        tiles += (s->h_len[r] + TILE_POS - 1) / TILE_POS;
+    if (pre) { tiles = s->tab_tiles; nbases = s->tab_bases; }
+    else {
+        soff.resize(n); tile_off_own.resize((size_t)n + 1); slen.resize(n); rid_map.resize(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t r = first + i;
+            tile_off_own[i] = tiles;
+            soff[i] = s->h_off[r] - s->blk_base;
+            slen[i] = s->h_len[r];
+            rid_map[i] = r;
+            nbases += s->h_len[r];
+            tiles += (s->h_len[r] + TILE_POS - 1) / TILE_POS;
+        }
+        tile_off_own[n] = tiles;
+        tile_read.resize(tiles);
+        for (uint32_t i = 0; i < n; ++i) for (uint32_t t = tile_off_own[i]; t < tile_off_own[i + 1]; ++t) tile_read[t] = i;
     }
-    tile_off[n] = tiles;
-    std::vector<uint32_t> tile_read(tiles);
-    for (uint32_t i = 0; i < n; ++i) for (uint32_t t = tile_off[i]; t < tile_off[i + 1]; ++t) tile_read[t] = i;
+    const std::vector<uint32_t> &tile_off = pre ? s->tab_tile_off : tile_off_own;
     const bool subset = first != 0 || count != s->n;
     const uint32_t nw = tiles * (SK_THREADS / 32);
     const uint64_t stage_bytes = (uint64_t)nw * SK_CAP * 16;
     if (stage_bytes > (16ull << 30) || stage_bytes > (free_estimate(c) + c->stg_x.cap + c->stg_y.cap) / 4) return false;
     c->prof.sbegin(ST_SKETCH);
-    h2d(c, c->tile_off, tile_off.data(), (size_t)n + 1);
-    h2d(c, c->tile_read, tile_read.data(), tiles);
-    h2d(c, c->sub_off, soff.data(), n);
-    h2d(c, c->len0, slen.data(), n);
-    if (subset) h2d(c, c->rid_map, rid_map.data(), n);
+    if (!pre) {
+        h2d(c, c->tile_off, tile_off.data(), (size_t)n + 1);
+        h2d(c, c->tile_read, tile_read.data(), tiles);
+        h2d(c, c->sub_off, soff.data(), n);
+        h2d(c, c->len0, slen.data(), n);
+        if (subset) h2d(c, c->rid_map, rid_map.data(), n);
+    }
+    const uint32_t *d_rid_map = !subset ? nullptr : pre ? s->t_rid_map.as<uint32_t>() : c->rid_map.as<uint32_t>();
+    const uint32_t *d_tile_off = pre ? s->t_tile_off.as<uint32_t>() : c->tile_off.as<uint32_t>();
     out->moff.reserve(((size_t)n + 1) * 4);
     out->M = 0;
     c->wcnt.reserve(((size_t)nw + 1) * 4);
     c->woff.reserve(((size_t)nw + 1) * 4);
-    job->n = n; job->nw = nw; job->out = out; job->active = true;
+    job->n = n; job->nw = nw; job->out = out; job->active = true; job->d_tile_off = d_tile_off;
     if (tiles == 0) { CUDA_CHECK(cudaMemsetAsync(out->moff.p, 0, ((size_t)n + 1) * 4, c->stream)); c->sk_total() = 0; c->sk_ovf() = 0; c->prof.send(ST_SKETCH); return true; }
     c->stg_x.reserve(stage_bytes / 2 + 64); c->stg_y.reserve(stage_bytes / 2 + 64);
     c->xflag.reserve(16);
     CUDA_CHECK(cudaMemsetAsync(c->xflag.p, 0, 16, c->stream));
     CUDA_CHECK(cudaMemsetAsync(c->wcnt.as<uint32_t>() + nw, 0, 4, c->stream));
     Sketch2Args A{};
-    A.asc = s->asc.as<uint8_t>(); A.off = c->sub_off.as<uint64_t>(); A.len = c->len0.as<uint32_t>();
-    A.rid_map = subset ? c->rid_map.as<uint32_t>() : nullptr; A.tile_off = c->tile_off.as<uint32_t>();
-    A.tile_read = c->tile_read.as<uint32_t>();
+    A.asc = s->asc.as<uint8_t>();
+    A.off = pre ? s->t_sub_off.as<uint64_t>() : c->sub_off.as<uint64_t>();
+    A.len = pre ? s->t_len.as<uint32_t>() : c->len0.as<uint32_t>();
+    A.rid_map = d_rid_map; A.tile_off = d_tile_off;
+    A.tile_read = pre ? s->t_tile_read.as<uint32_t>() : c->tile_read.as<uint32_t>();
     A.ox = c->stg_x.as<uint64_t>(); A.oy = c->stg_y.as<uint64_t>(); A.wcnt = c->wcnt.as<uint32_t>(); A.overflow = c->xflag.as<uint32_t>();
+    if (half) {
+        // two launches groups, each followed by its own compaction / sort (the callback), instead of one scan at the end
+        const size_t nc = s->chunk_hi.size(), mid = nc / 2;
+        uint32_t lo = first, w_prev = 0, r_prev = first;
+        for (size_t j = 0; j < nc; ++j) {
+            const uint32_t hi = std::min(s->chunk_hi[j], first + count);
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, s->chunk_ev[j], 0));
+            if (hi > lo) {
+                A.tile0 = tile_off[lo - first];
+                const uint32_t t = tile_off[hi - first] - A.tile0;
+                if (t) KLAUNCH(c, "sketch2_kernel", (double)(hi - lo) / n * ((double)nbases / 4 + 16.0 * nbases / 3), (sketch2_kernel<15><<<t, SK_THREADS, 0, c->stream>>>(A)));
+                lo = hi;
+            }
+            if (j + 1 == mid || j + 1 == nc) {
+                const bool last = j + 1 == nc;
+                const uint32_t r_hi = last ? first + count : lo;
+                const uint32_t w1 = tile_off[r_hi - first] * (SK_THREADS / 32);
+                CUDA_CHECK(cudaGetLastError());
+                if (!(*half)(w_prev, w1, r_prev, r_hi, last)) { c->prof.send(ST_SKETCH); job->active = false; return false; }
+                w_prev = w1; r_prev = r_hi;
+            }
+        }
+        c->prof.send(ST_SKETCH);
+        return true;
+    }
     KLAUNCH(c, "sketch2_kernel", (double)nbases / 4 + 16.0 * nbases / 3, {     // SURVEY.md 8(d) K1 (M ~ bases / 3 at launch time)
         if (s->pending && !s->chunk_hi.empty()) {
             // one launch per staged chunk, each waiting only for its own copy
@@ -498,7 +622,7 @@ bool sketch2_end(lrge_ctx *c, const Sketch2Job &job) {
                                                                c->woff.as<uint32_t>(), nw, SK_CAP, out->x.as<uint64_t>(), out->y.as<uint64_t>()));
     // per-read minimizer offsets: woff at the first warp sub-tile of every read
     KLAUNCH(c, "gather_kernel", 12.0 * n,
-            gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), c->tile_off.as<uint32_t>(),
+            gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), job.d_tile_off,
                                                                          SK_THREADS / 32, n + 1, out->moff.as<uint32_t>()));
     CUDA_CHECK(cudaGetLastError());
     c->prof.send(ST_SKETCH);
@@ -756,6 +880,99 @@ BuiltIndex build_index(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     build_index_finish(c, o, &B);
     return B;
+}
+
+// Host-buffer path, ava-ont, one GPU: the indexed set arrives in chunks (stage_readset, async).  Its sketch, compaction
+// and index sort are done per HALF of the chunks, so the first half's index work runs while the second half is still on
+// the wire; the two sorted runs are merged (keys carry the half in their low bits, see key32_half_kernel) and
+// index_post_kernel strips the tag.  Leaves `out` complete (x, y, moff) and the index launched like build_index_launch.
+// host_work runs once while the first half is in flight.  false: not applicable or a capacity was exceeded -- the
+// caller takes the ordinary path (nothing it depends on has been touched).
+bool sketch_index_halves(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *out, const std::function<void()> &host_work,
+                         BuiltIndex *Bout) {
+    if (c->no_halves || c->sketch_legacy || o.is_hpc || o.k != 15 || !s->pending || s->chunk_hi.size() < 2) return false;
+    if (s->blk_first != 0 || s->blk_count != s->n || s->n == 0) return false;
+    const uint32_t n = s->n;
+    const uint64_t cap = s->total_bases / 2 + 4096;               // minimizers (density ~ 1/3 at w = 5)
+    if (cap >= (1ull << 31) - 64) return false;
+    if (cap * 64 > free_estimate(c) + out->x.cap + out->y.cap + c->ty.cap + c->tk32.cap + c->hk_a.cap + c->hk_b.cap + c->hv_b.cap + c->ukey.cap) return false;
+    out->x.reserve((cap + 1) * 8); out->y.reserve((cap + 1) * 8);
+    c->ukey.reserve((cap + 1) * 4);
+    c->hk_a.reserve((cap + 1) * 4); c->hk_b.reserve((cap + 1) * 4); c->hv_b.reserve((cap + 1) * 8);
+    c->ty.reserve((cap + 1) * 8); c->tk32.reserve((cap + 64) * 4);
+    uint64_t base = 0;
+    uint32_t run[2] = {0, 0}, g = 0;
+    bool did_host = false;
+    Sketch2Job job;
+    const HalfFn half = [&](uint32_t w0, uint32_t w1, uint32_t r_lo, uint32_t r_hi, bool last) -> bool {
+        const uint32_t nwg = w1 - w0;
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, c->wcnt.as<uint32_t>() + w0, c->woff.as<uint32_t>() + w0, nwg + 1, c->stream);
+        KLAUNCH(c, "cub::DeviceScan(u32)", 8.0 * nwg,
+                cub::DeviceScan::ExclusiveSum(cub_temp(c, tb), tb, c->wcnt.as<uint32_t>() + w0, c->woff.as<uint32_t>() + w0, nwg + 1, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&c->sk_total(), c->woff.as<uint32_t>() + w1, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&c->sk_ovf(), c->xflag.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        if (!did_host) { host_work(); did_host = true; }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (c->sk_ovf()) return false;
+        const uint32_t total = c->sk_total();
+        if (base + total > cap) return false;
+        uint64_t *x = out->x.as<uint64_t>() + base, *y = out->y.as<uint64_t>() + base;
+        if (nwg) KLAUNCH(c, "compact_kernel", 32.0 * total,
+                         compact_kernel<<<(nwg + 7) / 8, 256, 0, c->stream>>>(c->stg_x.as<uint64_t>() + (size_t)w0 * SK_CAP, c->stg_y.as<uint64_t>() + (size_t)w0 * SK_CAP,
+                                                                             c->wcnt.as<uint32_t>() + w0, c->woff.as<uint32_t>() + w0, nwg, SK_CAP, x, y));
+        const uint32_t ng = r_hi - r_lo + (last ? 1u : 0u);
+        if (ng) KLAUNCH(c, "gather_kernel", 12.0 * ng,
+                        gather_u32_base_kernel<<<(ng + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), job.d_tile_off + r_lo, SK_THREADS / 32, ng,
+                                                                                         (uint32_t)base, out->moff.as<uint32_t>() + r_lo));
+        if (last) { CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream)); c->fork_recorded = true; }   // the staging slots are free again
+        if (total) {
+            uint32_t *kin = c->ukey.as<uint32_t>() + base;
+            KLAUNCH(c, "key32_kernel", 12.0 * total, key32_half_kernel<<<(total + 255) / 256, 256, 0, c->stream>>>(x, total, g, kin));
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, c->hk_b.as<uint32_t>() + base, y, c->hv_b.as<uint64_t>() + base, (int64_t)total, 0, 32, c->stream);
+            KLAUNCH(c, "cub::DeviceRadixSort(index: u32 key, u64 value)", 32.0 * total,
+                    cub::DeviceRadixSort::SortPairs(cub_temp(c, tb), tb, kin, c->hk_b.as<uint32_t>() + base, y, c->hv_b.as<uint64_t>() + base, (int64_t)total, 0, 32, c->stream));
+            c->launches += 4;
+            c->prof.set_passes("cub::DeviceRadixSort(index: u32 key, u64 value)", 4);
+        }
+        run[g] = total; base += total; ++g;
+        return true;
+    };
+    if (!sketch2_begin(c, s, o, out, 0, n, &job, &half) || g != 2) { if (!did_host) host_work(); return false; }
+    const uint64_t M = base;
+    out->M = M;
+    // merge the two runs; strip the tag, bucket table, occurrence histogram
+    BuiltIndex B{};
+    int bits = 8;
+    while (bits < 2 * o.k && bits < 28 && (8ull << bits) < M) ++bits;
+    const uint32_t nb = 1u << bits;
+    c->boff.reserve(((size_t)nb + 2) * 4);
+    c->hist.reserve((OCC_BINS + 2) * 8);
+    c->prof.sbegin(ST_INDEX);
+    CUDA_CHECK(cudaMemsetAsync(c->hist.p, 0, (OCC_BINS + 2) * 8, c->stream));
+    if (M) {
+        size_t tb = 0;
+        cub::DeviceMerge::MergePairs(nullptr, tb, c->hk_b.as<uint32_t>(), c->hv_b.as<uint64_t>(), (int)run[0], c->hk_b.as<uint32_t>() + run[0],
+                                     c->hv_b.as<uint64_t>() + run[0], (int)run[1], c->hk_a.as<uint32_t>(), c->ty.as<uint64_t>(), LessU32{}, c->stream);
+        KLAUNCH(c, "cub::DeviceMerge(index halves)", 24.0 * M,
+                cub::DeviceMerge::MergePairs(cub_temp(c, tb), tb, c->hk_b.as<uint32_t>(), c->hv_b.as<uint64_t>(), (int)run[0], c->hk_b.as<uint32_t>() + run[0],
+                                             c->hv_b.as<uint64_t>() + run[0], (int)run[1], c->hk_a.as<uint32_t>(), c->ty.as<uint64_t>(), LessU32{}, c->stream));
+    }
+    CUDA_CHECK(cudaMemsetAsync(c->tk32.as<uint32_t>() + M, 0, 64 * 4, c->stream));
+    const int shift = 2 * o.k - bits;
+    KLAUNCH(c, "index_post_kernel", 8.0 * M + 4.0 * nb,
+            (index_post_kernel<uint32_t, 2><<<148 * 8, 256, 0, c->stream>>>(c->hk_a.as<uint32_t>(), M, shift + 2, nb, c->boff.as<uint32_t>(), c->tk32.as<uint32_t>(),
+                                                                            c->hist.as<unsigned long long>())));
+    CUDA_CHECK(cudaMemcpyAsync(c->hist_h(), c->hist.p, (OCC_BINS + 2) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaGetLastError());
+    c->prof.send(ST_INDEX);
+    B.x32 = true;
+    B.view.tx = nullptr; B.view.shift = 8 + shift;
+    B.view.tk32 = c->tk32.as<uint32_t>(); B.view.ty = c->ty.as<uint64_t>(); B.view.boff = c->boff.as<uint32_t>();
+    B.view.M = M; B.view.bl = nullptr;
+    B.mid_occ = -1; B.n_keys = 0;
+    *Bout = B;
+    return true;
 }
 
 #define NCCL_CHECK(x) do { ncclResult_t _r = (x); if (_r != ncclSuccess) throw NcclError(std::string(#x) + ": " + ncclGetErrorString(_r)); } while (0)
@@ -1320,7 +1537,11 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     uint32_t i0 = 0, i1 = idx->n;
     if (sharded_index && !c->local_block) shard_range(idx->n, c->rank, world, &i0, &i1);
     Sketch2Job job_idx;
-    const bool fast_idx = sketch2_begin(c, idx, o, &c->sk_idx, i0, i1 - i0, &job_idx);
+    BuiltIndex Bh{};
+    c->fork_recorded = false;
+    // host buffers, one GPU, ava-ont: sketch + index sort per half of the staged chunks (the name analysis runs inside)
+    const bool halves = !sharded_index && sketch_index_halves(c, idx, o, &c->sk_idx, [&]() { finish_staging(idx); finish_staging(str); }, &Bh);
+    const bool fast_idx = !halves && sketch2_begin(c, idx, o, &c->sk_idx, i0, i1 - i0, &job_idx);
 
     // names -> ranks.  Only equality (two-set: NO_DIAG, HashSet<name>) or strcmp order (AVA: NO_DUAL) is ever used.
     finish_staging(idx);
@@ -1358,7 +1579,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     const std::vector<uint32_t> &rank_idx = R.a, &rank_str = mode == MODE_AVA ? R.a : R.b;
     drain.armed = false;
 
-    if (!fast_idx || !sketch2_end(c, job_idx)) sketch_readset(c, idx, o, &c->sk_idx, i0, i1 - i0, true);
+    if (!halves && (!fast_idx || !sketch2_end(c, job_idx))) sketch_readset(c, idx, o, &c->sk_idx, i0, i1 - i0, true);
     // K2/K3, then K1 on the streamed set.  Single GPU: the sketch's synchronisation also delivers the occurrence histogram
     // of the index (build_index_finish).  Sharded index: the sketch is launched while the host waits for the send counts
     // of the key exchange, and its synchronisation delivers mid_occ and the fallback flags.
@@ -1369,18 +1590,31 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     // (shared staging buffers), and then runs next to the index build (sort passes are HBM-bound, the sketch issue-bound).
     Sketch2Job job_str;
     bool fast_str = false;
-    if (need_str && !c->no_side) {
-        CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+    if (!c->fork_recorded) CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));   // the indexed set's sketch is complete here
+    auto fork_str = [&]() {
+        if (!need_str || c->no_side) return;
         SideStream side(c);
         CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
         fast_str = sketch2_begin(c, str, o, &c->sk_str, 0, str->n, &job_str);
-    }
+    };
+    // small tables of the seed stage (name ranks, read lengths, gap penalties): uploaded on the side stream behind the
+    // streamed set's sketch when there is one, so that they are not on the path between the index and the first lookup
+    bool seed_tables_up = false;
+    auto upload_seed_tables = [&]() {
+        h2d(c, c->rank_idx, rank_idx.data(), idx->n);
+        h2d(c, c->rank_str, rank_str.data(), str->n);
+        h2d(c, c->len_idx, idx->h_len.data(), idx->n);
+        h2d(c, c->len_str, str->h_len.data(), str->n);
+        if (c->pen_k != o.k || c->pen_bw != o.bw) { gap_penalty_table(o.k, o.chain_gap_scale, o.bw + 1, c->pen_host); c->pen_k = o.k; c->pen_bw = o.bw; }
+        h2d(c, c->pen, c->pen_host.data(), c->pen_host.size());
+        seed_tables_up = true;
+    };
     auto finish_str = [&]() {                      // minimizer total of the streamed set -> compaction; join the main stream
         bool ok = false;
         if (fast_str) {
             SideStream side(c);
             ok = sketch2_end(c, job_str);          // synchronises the side stream only
-            if (ok) CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream));
+            if (ok) { upload_seed_tables(); CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream)); }
         }
         if (ok) CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         else sketch_readset(c, str, o, &c->sk_str, 0, 0xffffffffu, fast_str);   // not applicable, or a sub-tile overflowed
@@ -1392,6 +1626,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         // (a number every rank derives alike: with local blocks only the streamed set is common to all ranks)
         const uint64_t bl_cap = c->local_block ? std::max<uint64_t>(4096, str->total_bases / 256)
                                                : std::max<uint64_t>(4096, idx->total_bases / (uint64_t)world / 512);
+        fork_str();
         ShardedJob J = build_index_sharded_launch(c, c->sk_idx, o, bl_cap, [&]() {});
         c->prof.send(ST_INDEX);
         finish_str();
@@ -1399,10 +1634,15 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         if (build_index_sharded_finish(c, &J, &S)) B = J.B;
         else { c->prof.sbegin(ST_INDEX); B = build_index_sharded_exact(c, c->sk_idx, o, &S); c->prof.send(ST_INDEX); }
     } else {
-        c->prof.sbegin(ST_INDEX);
-        B = build_index_launch(c, c->sk_idx, o);
+        if (halves) B = Bh;                        // already launched, behind the second half's sort
+        else {
+            c->prof.sbegin(ST_INDEX);
+            B = build_index_launch(c, c->sk_idx, o);
+            c->prof.send(ST_INDEX);
+        }
+        fork_str();                                // after the index launches: those are on the critical path
         S.n_target_minimizers = c->sk_idx.M;
-        c->prof.send(ST_INDEX);
+        S.n_index_runs = halves ? 2 : 1;
         if (need_str) finish_str();
         CUDA_CHECK(cudaStreamSynchronize(c->stream));   // the occurrence histogram of the index
         build_index_finish(c, o, &B);
@@ -1412,12 +1652,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     S.n_query_minimizers = MQ;
 
     c->prof.sbegin(ST_SEED);
-    h2d(c, c->rank_idx, rank_idx.data(), idx->n);
-    h2d(c, c->rank_str, rank_str.data(), str->n);
-    h2d(c, c->len_idx, idx->h_len.data(), idx->n);
-    h2d(c, c->len_str, str->h_len.data(), str->n);
-    if (c->pen_k != o.k || c->pen_bw != o.bw) { gap_penalty_table(o.k, o.chain_gap_scale, o.bw + 1, c->pen_host); c->pen_k = o.k; c->pen_bw = o.bw; }
-    h2d(c, c->pen, c->pen_host.data(), c->pen_host.size());
+    if (!seed_tables_up) upload_seed_tables();
 
     SkipCtx K{};
     K.rank_q = c->rank_str.as<uint32_t>(); K.rank_t = c->rank_idx.as<uint32_t>();
@@ -2002,6 +2237,9 @@ int lrge_gpu_create(int device, lrge_ctx **out) {
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         { const char *e = getenv("LRGE_NO_SIDE_STREAM"); c->no_side = e && e[0] == '1'; }
+        { const char *e = getenv("LRGE_MIN_CHUNK"); if (e && atoll(e) > 0) c->min_chunk = (uint64_t)atoll(e); }
+        { const char *e = getenv("LRGE_INDEX_HALVES"); c->no_halves = !(e && e[0] == '1'); }
+        { const char *e = getenv("LRGE_TIMELINE"); c->prof.timeline = e && e[0] == '1'; }
         c->prof.s = c->stream;
         c->prof.reset();
         { size_t f = 0, t = 0; CUDA_CHECK(cudaMemGetInfo(&f, &t)); c->free_at_create = f; c->held_at_create = dev_bytes_in_use().load(); }

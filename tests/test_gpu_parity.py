@@ -469,6 +469,34 @@ def test_fused_rounds_and_deferral(ctx, monkeypatch, cap):
     assert _reg_set(ov) == _reg_set(regs, qidx)
 
 
+def test_host_buffer_chunked_index_build(ctx, monkeypatch):
+    """Host-buffer calls copy the indexed set in chunks; with LRGE_INDEX_HALVES=1 (an experiment kept off by default:
+    measured slower on B200) the sketch, the compaction and the index sort of an ava-ont set run per HALF of the chunks and
+    the two sorted runs are merged (sketch_index_halves).  LRGE_MIN_CHUNK makes small sets arrive in chunks.  The index (mid_occ, keys, hit order through the anchors) and every result must equal the
+    unchunked path and the oracle -- including the overlap records, whose tie order depends on the hit-list order."""
+    T, Q = small_sets()
+    want, had, st = oracle.twoset_counts(T, Q, "ont", threads=8)
+    g = readsim.genome(150_000)
+    R = readsim.reads(g, 300, 3000, readsim.ONT, readsim.SEED_AVA, "r")
+    av_want, av_st = oracle.ava_counts(R, "ont", threads=8)
+    c1 = _ctx_with(monkeypatch, LRGE_MIN_CHUNK=50_000, LRGE_INDEX_HALVES=1)
+    try:
+        a = c1.twoset_counts(T, Q, "ont")
+        a2 = c1.twoset_counts(T, Q, "ont", remove_internal=True)
+        av = c1.ava_counts(R, "ont")                     # the indexed set's minimizers (x, y, per-read offsets) are also the queries
+    finally:
+        c1.close()
+    base = ctx.twoset_counts(T, Q, "ont")
+    assert a.stats["n_index_runs"] == 2 and av.stats["n_index_runs"] == 2      # the chunked path did run
+    assert base.stats["n_index_runs"] == 1
+    assert np.array_equal(a.counts, want) and np.array_equal(a.had_mapping, had)
+    for k in ("n_anchors", "mid_occ", "n_keys", "n_target_minimizers", "n_query_minimizers", "n_seeds", "n_hits", "n_overlaps"):
+        assert a.stats[k] == base.stats[k], k
+    assert a.stats["n_anchors"] == st["n_anchors"] and a.stats["mid_occ"] == st["mid_occ"]
+    assert np.array_equal(a2.counts, ctx.twoset_counts(T, Q, "ont", remove_internal=True).counts)
+    assert np.array_equal(av.counts, av_want) and av.stats["n_anchors"] == av_st["n_anchors"]
+
+
 def _branch_report(st):
     return {k: int(st[k]) for k in ("mid_occ", "n_anchors", "n_tie_x_queries", "n_tie_x_anchors", "n_mz_flt_deleted",
                                     "n_occ_filtered", "n_max_iter_clamp", "n_skip_break")}
