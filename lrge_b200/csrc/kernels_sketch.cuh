@@ -522,12 +522,17 @@ __global__ void __launch_bounds__(SK_THREADS) sketch2_kernel(Sketch2Args A) {
 // MODE 2 follow-up: pack the staging slots into the contiguous (rid, position)-ordered arrays. One warp per sub-tile.
 __global__ void __launch_bounds__(256) compact_kernel(const uint64_t *__restrict__ sx, const uint64_t *__restrict__ sy,
                                                       const uint32_t *__restrict__ wcnt, const uint32_t *__restrict__ woff, uint32_t nw,
-                                                      uint32_t cap, uint64_t *__restrict__ ox, uint64_t *__restrict__ oy) {
+                                                      uint32_t cap, uint64_t *__restrict__ ox, uint64_t *__restrict__ oy,
+                                                      uint32_t *__restrict__ k32 = nullptr) {
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= nw) return;
     const uint32_t n = wcnt[w], o = woff[w];
     const uint64_t b = (uint64_t)w * cap;
-    for (uint32_t e = lane_id(); e < n; e += 32) { ox[o + e] = sx[b + e]; oy[o + e] = sy[b + e]; }
+    for (uint32_t e = lane_id(); e < n; e += 32) {
+        const uint64_t x = sx[b + e];
+        ox[o + e] = x; oy[o + e] = sy[b + e];
+        if (k32) k32[o + e] = (uint32_t)(x >> 8);      // the index's 32-bit sort keys (2k <= 32), saving a pass over x
+    }
 }
 
 }  // namespace lrge

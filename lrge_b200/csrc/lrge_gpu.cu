@@ -483,7 +483,11 @@ __global__ void gather_u64_kernel(const uint64_t *__restrict__ src, const uint32
 // sketch2_begin launches and returns without waiting (false: not applicable / no room, nothing launched); sketch2_end
 // waits for the minimizer total, then packs.  It returns false if a sub-tile overflowed its slot (very dense reads):
 // the caller falls back to the exact two-pass path.
-struct Sketch2Job { bool active = false; uint32_t n = 0, nw = 0; Sketch *out = nullptr; const uint32_t *d_tile_off = nullptr; };
+struct Sketch2Job {
+    bool active = false; uint32_t n = 0, nw = 0; Sketch *out = nullptr; const uint32_t *d_tile_off = nullptr;
+    bool want_k32 = false;      // in: also write the 32-bit index sort keys into c->ukey while compacting
+    bool have_k32 = false;      // out: c->ukey holds them
+};
 
 // half: called after the launches of the first and of the second half of the staged chunks with the sub-tile range
 // [w0, w1) and the reads [r_lo, r_hi) they cover (sketch_index_halves); the scan over all sub-tiles is then left out.
@@ -606,7 +610,7 @@ bool sketch2_begin(lrge_ctx *c, const lrge_staged *s, const MapOpt &o, Sketch *o
     return true;
 }
 
-bool sketch2_end(lrge_ctx *c, const Sketch2Job &job) {
+bool sketch2_end(lrge_ctx *c, Sketch2Job &job) {
     Sketch *out = job.out;
     const uint32_t n = job.n, nw = job.nw;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -617,9 +621,12 @@ bool sketch2_end(lrge_ctx *c, const Sketch2Job &job) {
     out->M = total;
     out->x.reserve(((size_t)total + 1) * 8);
     out->y.reserve(((size_t)total + 1) * 8);
-    KLAUNCH(c, "compact_kernel", 32.0 * total,
+    uint32_t *k32 = nullptr;
+    if (job.want_k32) { c->ukey.reserve(((size_t)total + 1) * 8); k32 = c->ukey.as<uint32_t>(); }
+    KLAUNCH(c, "compact_kernel", 32.0 * total + (k32 ? 4.0 * total : 0.0),
             compact_kernel<<<(nw + 7) / 8, 256, 0, c->stream>>>(c->stg_x.as<uint64_t>(), c->stg_y.as<uint64_t>(), c->wcnt.as<uint32_t>(),
-                                                               c->woff.as<uint32_t>(), nw, SK_CAP, out->x.as<uint64_t>(), out->y.as<uint64_t>()));
+                                                               c->woff.as<uint32_t>(), nw, SK_CAP, out->x.as<uint64_t>(), out->y.as<uint64_t>(), k32));
+    job.have_k32 = k32 != nullptr;
     // per-read minimizer offsets: woff at the first warp sub-tile of every read
     KLAUNCH(c, "gather_kernel", 12.0 * n,
             gather_u32_kernel<<<(n + 1 + 255) / 256, 256, 0, c->stream>>>(c->woff.as<uint32_t>(), job.d_tile_off,
@@ -780,7 +787,7 @@ struct BuiltIndex { IndexView view; int mid_occ; uint64_t n_keys; bool x32 = fal
 // K2 + K3.  build_index_launch queues the sort, the bucket table and the occurrence histogram (+ its copy to pinned
 // host memory) and returns; build_index_finish -- after any later synchronisation of the stream -- turns the histogram
 // into mid_occ on the host.  Nothing in between may depend on mid_occ (the sketch of the streamed set does not).
-BuiltIndex build_index_launch(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
+BuiltIndex build_index_launch(lrge_ctx *c, const Sketch &sk, const MapOpt &o, bool have_k32 = false) {   // have_k32: c->ukey holds the keys
     BuiltIndex B{};
     const uint64_t M = sk.M;
     if (M >= (1ull << 32) - 2) throw std::length_error("more than 2^32 target minimizers per GPU are not supported");
@@ -803,8 +810,8 @@ BuiltIndex build_index_launch(lrge_ctx *c, const Sketch &sk, const MapOpt &o) {
         // sort (32-bit hash, y): 12-byte records instead of 16, and the sorted keys ARE the compact lookup keys
         c->ukey.reserve((M + 1) * 4);
         if (M) {
-            KLAUNCH(c, "key32_kernel", 12.0 * M,
-                    key32_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(sk.x.as<uint64_t>(), M, c->ukey.as<uint32_t>()));
+            if (!have_k32) KLAUNCH(c, "key32_kernel", 12.0 * M,
+                                   key32_kernel<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(sk.x.as<uint64_t>(), M, c->ukey.as<uint32_t>()));
             cub::DeviceRadixSort::SortPairs(nullptr, tb, c->ukey.as<uint32_t>(), c->tk32.as<uint32_t>(), sk.y.as<uint64_t>(), c->ty.as<uint64_t>(),
                                             (int64_t)M, 0, 2 * o.k, c->stream);
             KLAUNCH(c, "cub::DeviceRadixSort(index: u32 key, u64 value)", 32.0 * M,       // 2 x 16 x M_T
@@ -1541,6 +1548,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     c->fork_recorded = false;
     // host buffers, one GPU, ava-ont: sketch + index sort per half of the staged chunks (the name analysis runs inside)
     const bool halves = !sharded_index && sketch_index_halves(c, idx, o, &c->sk_idx, [&]() { finish_staging(idx); finish_staging(str); }, &Bh);
+    job_idx.want_k32 = !sharded_index && !o.is_hpc && 2 * o.k <= 32;      // the compaction also writes the index's sort keys
     const bool fast_idx = !halves && sketch2_begin(c, idx, o, &c->sk_idx, i0, i1 - i0, &job_idx);
 
     // names -> ranks.  Only equality (two-set: NO_DIAG, HashSet<name>) or strcmp order (AVA: NO_DUAL) is ever used.
@@ -1579,7 +1587,11 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     const std::vector<uint32_t> &rank_idx = R.a, &rank_str = mode == MODE_AVA ? R.a : R.b;
     drain.armed = false;
 
-    if (!halves && (!fast_idx || !sketch2_end(c, job_idx))) sketch_readset(c, idx, o, &c->sk_idx, i0, i1 - i0, true);
+    bool idx_k32 = false;
+    if (!halves) {
+        if (fast_idx && sketch2_end(c, job_idx)) idx_k32 = job_idx.have_k32;
+        else sketch_readset(c, idx, o, &c->sk_idx, i0, i1 - i0, true);
+    }
     // K2/K3, then K1 on the streamed set.  Single GPU: the sketch's synchronisation also delivers the occurrence histogram
     // of the index (build_index_finish).  Sharded index: the sketch is launched while the host waits for the send counts
     // of the key exchange, and its synchronisation delivers mid_occ and the fallback flags.
@@ -1637,7 +1649,7 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
         if (halves) B = Bh;                        // already launched, behind the second half's sort
         else {
             c->prof.sbegin(ST_INDEX);
-            B = build_index_launch(c, c->sk_idx, o);
+            B = build_index_launch(c, c->sk_idx, o, idx_k32);
             c->prof.send(ST_INDEX);
         }
         fork_str();                                // after the index launches: those are on the critical path
