@@ -1604,7 +1604,9 @@ void run_overlap(lrge_ctx *c, lrge_staged *idx, lrge_staged *str, Mode mode, con
     bool fast_str = false;
     if (!c->fork_recorded) CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));   // the indexed set's sketch is complete here
     auto fork_str = [&]() {
-        if (!need_str || c->no_side) return;
+        // per-kernel profiling (lrge_gpu_set_profiling) keeps everything on one stream: spans of kernels that share the
+        // SMs with another stream's work would not be comparable with the serialised launch list of a profiler
+        if (!need_str || c->no_side || c->prof.kernels) return;
         SideStream side(c);
         CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_fork, 0));
         fast_str = sketch2_begin(c, str, o, &c->sk_str, 0, str->n, &job_str);
