@@ -66,6 +66,18 @@ extern "C" {
         no_mapping_count: *mut u32,
         stats: *mut LrgeStats,
     ) -> c_int;
+    // one process per GPU: rank 0 draws the id, every rank joins, then each rank passes ITS block of the targets
+    fn lrge_gpu_comm_unique_id(out: *mut u8, size: usize) -> c_int;
+    fn lrge_gpu_comm_init(ctx: *mut LrgeCtx, rank: c_int, world: c_int, unique_id: *const u8, size: usize) -> c_int;
+    fn lrge_gpu_twoset_counts_shard(
+        ctx: *mut LrgeCtx,
+        t_block: *const LrgeReadset,
+        q: *const LrgeReadset,
+        o: *const LrgeOpts,
+        counts: *mut u32,
+        had_mapping: *mut u8,
+        stats: *mut LrgeStats,
+    ) -> c_int;
 }
 
 /// The temp FASTA as flat buffers (what `lrge_readset` points into).  The read id is the header up to the first
@@ -188,6 +200,54 @@ pub fn ava_estimates(
     let rc = unsafe { lrge_ava_generate_estimates(ctx.0, &r.view(), &o, est.as_mut_ptr(), &mut no_mapping, std::ptr::null_mut()) };
     if rc == 0 {
         Ok((est, no_mapping))
+    } else {
+        Err(map_err(rc, ctx.0))
+    }
+}
+
+/// Communicator id for a multi-GPU run (128 bytes): rank 0 calls this and hands the bytes to the other ranks by any
+/// means (MPI, a file, a socket).
+pub fn comm_unique_id() -> crate::Result<[u8; 128]> {
+    let mut id = [0u8; 128];
+    let rc = unsafe { lrge_gpu_comm_unique_id(id.as_mut_ptr(), id.len()) };
+    if rc == 0 {
+        Ok(id)
+    } else {
+        Err(map_err(rc, std::ptr::null()))
+    }
+}
+
+/// Target sets that do not fit one host (README.md:173-175): every rank (one process per GPU) passes only ITS block of the
+/// target FASTA and the whole query FASTA, and gets the complete per-query overlap counts and `had_mapping` flags back --
+/// the inputs of `per_read_estimate` (estimate.rs:129-157; `avg_target_len` and the target count are taken over all blocks
+/// by the caller).  Target read ids must be unique across blocks.
+pub fn twoset_counts_shard(
+    device: c_int,
+    rank: c_int,
+    world: c_int,
+    unique_id: &[u8; 128],
+    target_block: &Path,
+    query: &Path,
+    platform: &Platform,
+    remove_internal: bool,
+    max_overhang_ratio: f32,
+) -> crate::Result<(Vec<u32>, Vec<u8>)> {
+    let (t, q) = (Flat::load(target_block)?, Flat::load(query)?);
+    let mut o = opts(platform, remove_internal, max_overhang_ratio, false);
+    o.shard_index = rank;
+    o.shard_count = world;
+    let ctx = Ctx::new(device)?;
+    let rc = unsafe { lrge_gpu_comm_init(ctx.0, rank, world, unique_id.as_ptr(), unique_id.len()) };
+    if rc != 0 {
+        return Err(map_err(rc, ctx.0));
+    }
+    let mut counts = vec![0u32; q.n()];
+    let mut had = vec![0u8; q.n()];
+    let rc = unsafe {
+        lrge_gpu_twoset_counts_shard(ctx.0, &t.view(), &q.view(), &o, counts.as_mut_ptr(), had.as_mut_ptr(), std::ptr::null_mut())
+    };
+    if rc == 0 {
+        Ok((counts, had))
     } else {
         Err(map_err(rc, ctx.0))
     }
