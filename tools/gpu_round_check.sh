@@ -13,6 +13,7 @@ timeout 600 ncu --set full --clock-control none --import-source on \
     -k regex:"sort_query_kernel|sketch2_kernel|seed_lookup_kernel|anchor_fill_kernel|chain_group_kernel|index_post_kernel|compact_kernel|mz_flt_kernel|key32_kernel" \
     -s 27 -c 10 -o gpurun_out/prof_${TAG} python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -1 gpurun_out/ncu_full_${TAG}.log | cut -c1-120
+LRGE_TIMELINE=1 timeout 200 python tests/manual/e2e_timeline.py > gpurun_out/e2e_timeline_${TAG}.txt 2>&1
 bash tools/sanitize.sh 2>&1 | grep -E "rc=|SUMMARY" | tee gpurun_out/sanitize_${TAG}.log
 python - <<PY
 import json
