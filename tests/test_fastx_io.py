@@ -90,3 +90,24 @@ def test_two_pass_subsampled_ingestion(tmp_path, reads):
     for bad in ([3, 3], [5, 2], [reads.n]):             # duplicates, descending, beyond the last record
         with pytest.raises(lrge_b200.LrgeError):
             lrge_b200.read_fastx_subsets(str(fa), bad)
+
+
+def test_reader_edge_cases(tmp_path):
+    """Shapes needletail accepts (io.rs:121-184 reads through it): no trailing newline, blank lines, multi-member gzip,
+    lower-case and IUPAC bases kept verbatim, an empty record, '@' as the first quality character."""
+    def rd(name, data):
+        p = tmp_path / name
+        p.write_bytes(data)
+        r = lrge_b200.read_fastx(str(p))
+        return [(r.name(i), r.seq(i)) for i in range(r.n)]
+
+    assert rd("a.fa", b">r1\nACGT\n>r2 x\nGGTT") == [(b"r1", b"ACGT"), (b"r2", b"GGTT")]
+    assert rd("b.fa", b">r1\nACGT\n\n>r2\nGG\n\nTT\n\n") == [(b"r1", b"ACGT"), (b"r2", b"GGTT")]
+    assert rd("c.fa.gz", gzip.compress(b">r1\nACGT\n") + gzip.compress(b">r2\nGGTT\n")) == [(b"r1", b"ACGT"), (b"r2", b"GGTT")]
+    assert rd("d.fa", b">r1\nacgtNnRy\n") == [(b"r1", b"acgtNnRy")]
+    assert rd("e.fa", b">r1\n>r2\nACGT\n") == [(b"r1", b""), (b"r2", b"ACGT")]
+    assert rd("f.fq", b"@r1\nACGT\n+r1\nIIII\n@r2\nGG\n+\nII") == [(b"r1", b"ACGT"), (b"r2", b"GG")]
+    assert rd("g.fq", b"@r1\nACGT\n+\n@III\n@r2\nGG\n+\n@@\n") == [(b"r1", b"ACGT"), (b"r2", b"GG")]
+    with pytest.raises(lrge_b200.LrgeError) as e:
+        rd("h.fa", b"hello\nworld\n")
+    assert e.value.kind == "FastqParseError"
