@@ -9,12 +9,13 @@
 //     1. stage   its anchors HBM -> shared memory (coalesced), as (sort key, payload)
 //     2. sort    block-wide stable LSD radix sort in smem on the (target, strand) bits: groups become contiguous and keep
 //                their generation order
-//     3. groups  warps claim 32-anchor windows of the sorted array, find the (query, target) pairs that start in them and,
+//     3. groups  one pass writes the pair / group boundaries of the sorted array as bit maps (read-only from here on);
+//                warps claim 32-anchor windows of the sorted array, take the (query, target) pairs that start in them and,
 //                for every strand group that can hold a chain, bring it into target-position order (already ascending /
 //                strictly descending for a colinear overlap; warp-level radix sort otherwise), write it back as compact
 //                anchors and append a group descriptor for the chaining kernel (chain_group_kernel, kernels_chain.cuh)
 //   A query whose anchors exceed the smem capacity is sorted in ROUNDS over disjoint target-id ranges (groups never span
-//   targets, so rounds are independent); ranges come from a 1024-bin histogram of its anchors over target ids.
+//   targets, so rounds are independent); ranges come from a 2048-bin histogram of its anchors over target ids.
 //   A query that cannot be planned (one bin alone above capacity, > 255 rounds) is appended to `deferred` and the host
 //   sorts it with the device-wide radix sort of the global path.
 //

@@ -1,17 +1,19 @@
 // lrge_gpu.cu -- context, device pipeline and C-ABI of liblrge_b200.so (include/lrge_b200.h).
 //
-// Pipeline (one CUDA stream per context; every kernel is hand-written except the radix sorts and
-// prefix sums, which are CUB device primitives):
-//   K0  pack_kernel            ASCII -> 2-bit + ambiguity mask          (+ K0h hpc_compress for ava-pb)
-//   K1  sketch_kernel<stage>   minimizers into per-sub-tile slots -> scan -> compact_kernel
-//                              (fallback: sketch_kernel<count> -> scan -> sketch_kernel<emit>)
-//   K2  radix sort of target minimizers by hash                         (index in HBM)
-//   K3  index_post_kernel      bucket table + compact lookup keys + occurrence histogram -> mid_occ (mm_mapopt_update)
-//       build_index_sharded    the same with the index sharded over ranks: exact occurrence exchange over NCCL
-//   K4  mz_flt_kernel, seed_count_kernel -> scan -> anchor_fill_kernel  (per query batch)
-//   K5  radix sort of anchors by (query, target, strand, target pos), group_mark_kernel + select + group_classify_kernel
+// Pipeline (main stream + a side stream for the streamed set's sketch + a copy stream; every kernel is hand-written
+// except the index radix sort, the prefix sums / selects and the optional merge, which are CUB device primitives):
+//   K1  ava-ont: sketch2_kernel (TMA-staged ASCII, lane-serial state machine) -> scan -> compact_kernel (+ 32-bit sort keys)
+//       ava-pb / fallback: hpc_compress_kernel, pack_kernel, sketch_kernel<stage | count, emit>
+//   K2  radix sort of the indexed set's minimizers by hash (12-byte records for ava-ont)       (index in HBM)
+//   K3  index_post_kernel      bucket table (+ compact lookup keys) + occurrence histogram -> mid_occ (mm_mapopt_update)
+//       build_index_sharded_*  the index sharded over ranks: packed key|count entries pushed over peer memory (CUDA IPC
+//                              windows; ncclSend/Recv as the agreed fallback), owner_merge_kernel, mid_occ on the device
+//   K4  mz_flt_kernel, seed_lookup_kernel (seed_count_kernel when name rules apply) -> scan -> anchor_fill_kernel
+//   K5  sort_query_kernel      per query in shared memory: stage, radix sort on (target, strand), boundary bit maps,
+//                              per-group order, compact anchors + group descriptors
+//       (deferred queries / LRGE_FORCE_GLOBAL: device-wide radix sort, group_mark + select + group_classify_kernel)
 //   K6  chain_group_kernel     chaining DP + backtrack + overlap decision, one warp per (query, target, strand) group
-//                              (chain_pair_kernel: literal one-thread-per-pair cross-check, LRGE_CHAIN_V1=1)
+//                              (test build only: chain_pair_kernel, the literal one-thread-per-pair cross-check)
 // There is no CPU fallback anywhere in this file: without a device every entry point fails.
 #include "../../include/lrge_b200.h"
 #include "common.cuh"
